@@ -1,0 +1,19 @@
+"""gnnfc — B200-native graph-filter hot path of soosiey/gnn-formation-control.
+
+Import as ``import gnnfc`` (the repo-root shim maps that name onto this
+directory, whose name is not a Python identifier).
+
+    from gnnfc import GraphFilterBatch          # drop-in for utils/graphUtils/graphML.py:2369
+    gf = GraphFilterBatch(G, F, K).cuda()
+    gf.addGSO(S)                                 # S [B,E,N,N]
+    y = gf(x)                                    # x [B,G,N] -> y [B,F,N]
+"""
+from . import _cabi
+from ._cabi import GfcError, version, last_launch_count
+from .gso import build_gso, build_csr, SparseGSO
+from .graph_filter import GraphFilterBatch, graph_filter
+from .dp import GradBucket, shard_range, broadcast_parameters
+
+__all__ = ["GraphFilterBatch", "graph_filter", "build_gso", "build_csr", "SparseGSO",
+           "GradBucket", "shard_range", "broadcast_parameters", "GfcError", "version",
+           "last_launch_count"]

@@ -1,0 +1,471 @@
+// gfc_api.cu — the extern "C" surface declared in include/gfc.h: validation,
+// dispatch between the fused tile kernels (path A) and the workspace pipeline
+// (path B, incl. the CSR variant), second-stage gradient reductions.
+#include "gfc_tile.cuh"
+#include "gfc_generic.cuh"
+#include <string.h>
+
+namespace gfc {
+
+static thread_local char g_err[512] = "";
+static thread_local int g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int& launch_counter() { return g_launches; }
+
+int get_device_info(DeviceInfo* out) {
+  static thread_local int cached_dev = -1;
+  static thread_local DeviceInfo cached;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    // no device visible (CPU-only planning / unit tests): assume one B200
+    (void)cudaGetLastError();
+    out->sm_count = 148; out->cc_major = 10; out->cc_minor = 0; out->smem_optin = 232448;
+    return GFC_OK;
+  }
+  if (dev != cached_dev) {
+    GFC_CUDA_TRY(cudaDeviceGetAttribute(&cached.sm_count, cudaDevAttrMultiProcessorCount, dev));
+    GFC_CUDA_TRY(cudaDeviceGetAttribute(&cached.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    GFC_CUDA_TRY(cudaDeviceGetAttribute(&cached.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    GFC_CUDA_TRY(cudaDeviceGetAttribute(&cached.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    cached_dev = dev;
+  }
+  *out = cached;
+  return GFC_OK;
+}
+
+int gso_mode_threshold(int mode, double radius, double* thr, bool* norm);  // gfc_gso.cu
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+struct GsoSrc {
+  int kind;  // GSRC_DENSE / GSRC_POS
+  const float* S;
+  const float* pos;
+  double radius;
+  int mode;
+};
+
+// ---- path B workspace plan -----------------------------------------------------
+struct GenericPlan {
+  int nsplit;          // split of the dH reduction
+  int nchunks, rows_per_chunk;  // db partial sums
+  size_t ws_s, ws_z, ws_d, ws_dhp, ws_dbp, ws_bytes;
+};
+
+static void plan_generic(int B, int N, int G, int F, int K, int E, int backward, int need_s, GenericPlan* g) {
+  const long long rows = (long long)B * N;
+  const long long C = (long long)E * K * G;
+  size_t off = 0;
+  g->ws_s = off; if (need_s) off += align_up((size_t)rows * N * sizeof(float), 256);
+  g->ws_z = off; off += align_up((size_t)rows * C * sizeof(float), 256);
+  g->ws_d = off;
+  g->nsplit = 1; g->nchunks = 1; g->rows_per_chunk = (int)(rows > 0 ? rows : 1);
+  g->ws_dhp = g->ws_dbp = off;
+  if (backward) {
+    off += align_up((size_t)rows * F * sizeof(float), 256);
+    const long long blocks = (long long)ceil_div(F, 32) * ((C + 31) / 32);
+    long long ns = (148LL * 4 + blocks - 1) / blocks;
+    long long maxns = (rows + 255) / 256;
+    if (ns > maxns) ns = maxns;
+    if (ns > 128) ns = 128;
+    if (ns < 1) ns = 1;
+    g->nsplit = (int)ns;
+    g->ws_dhp = off; off += align_up((size_t)g->nsplit * F * C * sizeof(float), 256);
+    long long nc = (rows + 511) / 512;
+    if (nc > 1024) nc = 1024;
+    if (nc < 1) nc = 1;
+    g->nchunks = (int)nc;
+    g->rows_per_chunk = (int)((rows + nc - 1) / nc);
+    g->nchunks = (int)((rows + g->rows_per_chunk - 1) / g->rows_per_chunk);
+    if (g->nchunks < 1) g->nchunks = 1;
+    g->ws_dbp = off; off += align_up((size_t)g->nchunks * F * sizeof(float), 256);
+  }
+  g->ws_bytes = off;
+}
+
+static int check_common(const char* fn, int B, int N, int G, int F, int K, int E, int act, int prec) {
+  GFC_REQUIRE(B >= 0 && N > 0 && G > 0 && F > 0 && K > 0 && E > 0, GFC_ERR_BAD_ARG,
+              "%s: bad shape B=%d N=%d G=%d F=%d K=%d E=%d", fn, B, N, G, F, K, E);
+  GFC_REQUIRE(act >= GFC_ACT_NONE && act <= GFC_ACT_LEAKY_RELU, GFC_ERR_BAD_ARG, "%s: bad activation %d", fn, act);
+  GFC_REQUIRE(prec == GFC_PREC_FP32_3XTF32 || prec == GFC_PREC_TF32, GFC_ERR_BAD_ARG, "%s: bad precision %d", fn, prec);
+  return GFC_OK;
+}
+
+static int need_ws(const char* fn, const void* ws, size_t have, size_t need) {
+  if (need == 0) return GFC_OK;
+  GFC_REQUIRE(ws != nullptr && have >= need, GFC_ERR_WORKSPACE, "%s: workspace %zu B < required %zu B", fn, have, need);
+  GFC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, GFC_ERR_WORKSPACE, "%s: workspace must be 256-byte aligned", fn);
+  return GFC_OK;
+}
+
+// ---- forward ------------------------------------------------------------------
+static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, const float* h, const float* bias,
+                           float* y, int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
+                           void* ws, size_t ws_bytes, cudaStream_t st) {
+  launch_counter() = 0;
+  int rc = check_common(fn, B, N, G, F, K, E, act, prec);
+  if (rc) return rc;
+  if (B == 0) return GFC_OK;
+  GFC_REQUIRE(x && h && y, GFC_ERR_BAD_ARG, "%s: NULL tensor pointer", fn);
+  GFC_REQUIRE(gs.kind == GSRC_DENSE ? gs.S != nullptr : gs.pos != nullptr, GFC_ERR_BAD_ARG, "%s: NULL graph source", fn);
+  double thr = 0; bool norm = false;
+  if (gs.kind == GSRC_POS) {
+    GFC_REQUIRE(E == 1, GFC_ERR_UNSUPPORTED, "%s: position-built GSO has E = 1", fn);
+    rc = gso_mode_threshold(gs.mode, gs.radius, &thr, &norm);
+    if (rc) return rc;
+  }
+  TilePlan p;
+  if (E == 1 && plan_tile(B, N, G, F, K, 0, gs.kind, &p)) {
+    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes);
+    if (rc) return rc;
+    TileArgs a{};
+    a.S = gs.S; a.pos = gs.pos; a.thr = thr; a.norm = norm ? 1 : 0;
+    a.x = x; a.h = h; a.bias = bias; a.y = y;
+    a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+    a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
+    a.p = p;
+    if (!p.h_smem) {
+      float4* hp = reinterpret_cast<float4*>(static_cast<char*>(ws) + p.ws_hpack);
+      rc = launch_pack_taps(h, F, p.KG, 0, hp, st);
+      if (rc) return rc;
+      a.hpack = hp;
+    }
+    return launch_tile_fwd(a, gs.kind, st);
+  }
+  // path B
+  GenericPlan g;
+  plan_generic(B, N, G, F, K, E, 0, gs.kind == GSRC_POS, &g);
+  rc = need_ws(fn, ws, ws_bytes, g.ws_bytes);
+  if (rc) return rc;
+  char* wsb = static_cast<char*>(ws);
+  const float* S = gs.S;
+  if (gs.kind == GSRC_POS) {
+    float* Sw = reinterpret_cast<float*>(wsb + g.ws_s);
+    int lc = launch_counter();
+    rc = gfc_gso_build(gs.pos, B, N, gs.radius, gs.mode, nullptr, Sw, st);
+    launch_counter() += lc;
+    if (rc) return rc;
+    S = Sw;
+  }
+  float* Zw = reinterpret_cast<float*>(wsb + g.ws_z);
+  const long long C = (long long)E * K * G;
+  rc = launch_xpose_in(x, Zw, B, N, G, E, K, st);
+  if (rc) return rc;
+  for (int k = 1; k < K; ++k) {
+    rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
+    if (rc) return rc;
+  }
+  return launch_sgemm(Zw, C, 1, h, 1, C, y, F, 0, (long long)B * N, F, C, 1, bias, act, slope, st);
+}
+
+// ---- backward -----------------------------------------------------------------
+static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, const float* h, const float* yout,
+                           const float* dY, float* dX, float* dH, float* db,
+                           int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
+                           void* ws, size_t ws_bytes, cudaStream_t st) {
+  launch_counter() = 0;
+  int rc = check_common(fn, B, N, G, F, K, E, act, prec);
+  if (rc) return rc;
+  const size_t nH = (size_t)F * E * K * G;
+  if (B == 0) {
+    if (dH) GFC_CUDA_TRY(cudaMemsetAsync(dH, 0, nH * sizeof(float), st));
+    if (db) GFC_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)F * sizeof(float), st));
+    return GFC_OK;
+  }
+  GFC_REQUIRE(h && dY, GFC_ERR_BAD_ARG, "%s: NULL tensor pointer", fn);
+  GFC_REQUIRE(!dH || x, GFC_ERR_BAD_ARG, "%s: x is required for dH", fn);
+  GFC_REQUIRE(act == GFC_ACT_NONE || yout, GFC_ERR_BAD_ARG, "%s: y_out is required with a fused activation", fn);
+  GFC_REQUIRE(gs.kind == GSRC_DENSE ? gs.S != nullptr : gs.pos != nullptr, GFC_ERR_BAD_ARG, "%s: NULL graph source", fn);
+  if (!dX && !dH && !db) return GFC_OK;
+  double thr = 0; bool norm = false;
+  if (gs.kind == GSRC_POS) {
+    GFC_REQUIRE(E == 1, GFC_ERR_UNSUPPORTED, "%s: position-built GSO has E = 1", fn);
+    rc = gso_mode_threshold(gs.mode, gs.radius, &thr, &norm);
+    if (rc) return rc;
+  }
+  TilePlan p;
+  if (E == 1 && plan_tile(B, N, G, F, K, 1, gs.kind, &p)) {
+    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes);
+    if (rc) return rc;
+    char* wsb = static_cast<char*>(ws);
+    TileArgs a{};
+    a.S = gs.S; a.pos = gs.pos; a.thr = thr; a.norm = norm ? 1 : 0;
+    a.x = x; a.h = h; a.yout = yout; a.dY = dY; a.dX = dX;
+    a.dHp = dH ? reinterpret_cast<float*>(wsb + p.ws_dhp) : nullptr;
+    a.dbp = db ? reinterpret_cast<float*>(wsb + p.ws_dbp) : nullptr;
+    a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+    a.vec_ok = aligned16(dY) && (!x || aligned16(x)) && (!yout || aligned16(yout)) &&
+               (gs.kind == GSRC_POS || aligned16(gs.S));
+    a.p = p;
+    if (!p.h_smem && dX) {
+      float4* hp = reinterpret_cast<float4*>(wsb + p.ws_hpack);
+      rc = launch_pack_taps(h, F, p.KG, 1, hp, st);
+      if (rc) return rc;
+      a.hpack = hp;
+    }
+    if (dH && !p.acc_regs)
+      GFC_CUDA_TRY(cudaMemsetAsync(a.dHp, 0, (size_t)p.nparts * nH * sizeof(float), st));
+    rc = launch_tile_bwd(a, gs.kind, st);
+    if (rc) return rc;
+    if (dH) {
+      rc = launch_reduce_parts(a.dHp, p.nparts, (int)nH, dH, st);
+      if (rc) return rc;
+    }
+    if (db) {
+      rc = launch_reduce_parts(a.dbp, p.grid, F, db, st);
+      if (rc) return rc;
+    }
+    return GFC_OK;
+  }
+  // path B
+  GenericPlan g;
+  plan_generic(B, N, G, F, K, E, 1, gs.kind == GSRC_POS, &g);
+  rc = need_ws(fn, ws, ws_bytes, g.ws_bytes);
+  if (rc) return rc;
+  char* wsb = static_cast<char*>(ws);
+  const float* S = gs.S;
+  if (gs.kind == GSRC_POS) {
+    float* Sw = reinterpret_cast<float*>(wsb + g.ws_s);
+    int lc = launch_counter();
+    rc = gfc_gso_build(gs.pos, B, N, gs.radius, gs.mode, nullptr, Sw, st);
+    launch_counter() += lc;
+    if (rc) return rc;
+    S = Sw;
+  }
+  float* Zw = reinterpret_cast<float*>(wsb + g.ws_z);
+  float* Dw = reinterpret_cast<float*>(wsb + g.ws_d);
+  const long long rows = (long long)B * N;
+  const long long C = (long long)E * K * G;
+  rc = launch_dpre(dY, yout, Dw, rows * F, act, slope, st);
+  if (rc) return rc;
+  if (db) {
+    float* part = reinterpret_cast<float*>(wsb + g.ws_dbp);
+    rc = launch_colsum(Dw, rows, F, g.rows_per_chunk, g.nchunks, part, st);
+    if (rc) return rc;
+    rc = launch_reduce_parts(part, g.nchunks, F, db, st);
+    if (rc) return rc;
+  }
+  if (dH) {
+    rc = launch_xpose_in(x, Zw, B, N, G, E, K, st);
+    if (rc) return rc;
+    for (int k = 1; k < K; ++k) {
+      rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
+      if (rc) return rc;
+    }
+    float* part = reinterpret_cast<float*>(wsb + g.ws_dhp);
+    // dH[f][c] = sum_r D[r][f] Zw[r][c]
+    rc = launch_sgemm(Dw, 1, F, Zw, C, 1, part, C, (long long)nH, F, (int)C, rows, g.nsplit, nullptr,
+                      GFC_ACT_NONE, 0.f, st);
+    if (rc) return rc;
+    rc = launch_reduce_parts(part, g.nsplit, (int)nH, dH, st);
+    if (rc) return rc;
+  }
+  if (dX) {
+    // U[r][c] = sum_f D[r][f] h[f][c]
+    rc = launch_sgemm(Dw, F, 1, h, C, 1, Zw, C, 0, rows, (int)C, F, 1, nullptr, GFC_ACT_NONE, 0.f, st);
+    if (rc) return rc;
+    for (int k = K - 2; k >= 0; --k) {
+      rc = launch_hop_dense(Zw, S, B, N, G, E, K, k + 1, k, 1, st);
+      if (rc) return rc;
+    }
+    rc = launch_xpose_out(Zw, dX, B, N, G, E, K, st);
+    if (rc) return rc;
+  }
+  return GFC_OK;
+}
+
+}  // namespace gfc
+
+using namespace gfc;
+
+extern "C" int gfc_version(void) { return GFC_VERSION; }
+extern "C" const char* gfc_last_error(void) { return g_err; }
+extern "C" int gfc_last_launch_count(void) { return g_launches; }
+
+extern "C" int gfc_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes) {
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  if (sm_count) *sm_count = di.sm_count;
+  if (cc_major) *cc_major = di.cc_major;
+  if (cc_minor) *cc_minor = di.cc_minor;
+  if (smem_optin_bytes) *smem_optin_bytes = di.smem_optin;
+  return GFC_OK;
+}
+
+extern "C" int gfc_filter_path(int B, int N, int G, int F, int K, int E, int backward) {
+  if (B <= 0 || N <= 0 || G <= 0 || F <= 0 || K <= 0 || E <= 0) return 0;
+  TilePlan p;
+  if (E == 1 && plan_tile(B, N, G, F, K, backward, GSRC_DENSE, &p)) return 1;
+  return 2;
+}
+
+extern "C" int gfc_tile_plan_info(int B, int N, int G, int F, int K, int backward, int from_positions, int* out) {
+  if (!out) return GFC_ERR_BAD_ARG;
+  TilePlan p;
+  plan_tile(B, N, G, F, K, backward, from_positions ? GSRC_POS : GSRC_DENSE, &p);
+  out[0] = p.ok; out[1] = p.gpc; out[2] = p.rows; out[3] = p.rpad; out[4] = p.ntiles; out[5] = p.grid;
+  out[6] = (int)p.smem_bytes; out[7] = p.h_smem; out[8] = p.acc_regs; out[9] = p.nb_dh; out[10] = p.nparts;
+  out[11] = p.ldz;
+  return GFC_OK;
+}
+
+extern "C" size_t gfc_filter_workspace_bytes(int B, int N, int G, int F, int K, int E, int backward) {
+  if (B <= 0 || N <= 0 || G <= 0 || F <= 0 || K <= 0 || E <= 0) return 0;
+  size_t need = 0;
+  TilePlan p;
+  bool all_tile = (E == 1);
+  for (int src = 0; src < 2 && E == 1; ++src) {
+    if (plan_tile(B, N, G, F, K, backward, src, &p)) { if (p.ws_bytes > need) need = p.ws_bytes; }
+    else all_tile = false;
+  }
+  if (!all_tile) {
+    GenericPlan g;
+    plan_generic(B, N, G, F, K, E, backward, E == 1, &g);
+    if (g.ws_bytes > need) need = g.ws_bytes;
+  }
+  return need;
+}
+
+extern "C" int gfc_filter_fwd(const float* x, const float* S, const float* h, const float* bias, float* y,
+                              int B, int N, int G, int F, int K, int E, int act, float slope, int precision,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
+  return filter_fwd_impl("gfc_filter_fwd", gs, x, h, bias, y, B, N, G, F, K, E, act, slope, precision,
+                         workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gfc_filter_fwd_pos(const float* x, const float* pos, double radius, int mode, const float* h,
+                                  const float* bias, float* y, int B, int N, int G, int F, int K,
+                                  int act, float slope, int precision,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
+  return filter_fwd_impl("gfc_filter_fwd_pos", gs, x, h, bias, y, B, N, G, F, K, 1, act, slope, precision,
+                         workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gfc_filter_bwd(const float* x, const float* S, const float* h, const float* y_out,
+                              const float* dY, float* dX, float* dH, float* db,
+                              int B, int N, int G, int F, int K, int E, int act, float slope, int precision,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
+  return filter_bwd_impl("gfc_filter_bwd", gs, x, h, y_out, dY, dX, dH, db, B, N, G, F, K, E, act, slope,
+                         precision, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int gfc_filter_bwd_pos(const float* x, const float* pos, double radius, int mode, const float* h,
+                                  const float* y_out, const float* dY, float* dX, float* dH, float* db,
+                                  int B, int N, int G, int F, int K, int act, float slope, int precision,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
+  return filter_bwd_impl("gfc_filter_bwd_pos", gs, x, h, y_out, dY, dX, dH, db, B, N, G, F, K, 1, act, slope,
+                         precision, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- (d) CSR variant: workspace pipeline with SpMM hops -------------------------
+extern "C" size_t gfc_filter_csr_workspace_bytes(int B, int N, int G, int F, int K, int backward) {
+  if (B <= 0 || N <= 0 || G <= 0 || F <= 0 || K <= 0) return 0;
+  GenericPlan g;
+  plan_generic(B, N, G, F, K, 1, backward, 0, &g);
+  return g.ws_bytes;
+}
+
+extern "C" int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                                  int64_t nnz_stride, const float* h, const float* bias, float* y,
+                                  int B, int N, int G, int F, int K, int act, float slope, int precision,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  const char* fn = "gfc_filter_csr_fwd";
+  launch_counter() = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_common(fn, B, N, G, F, K, 1, act, precision);
+  if (rc) return rc;
+  if (B == 0) return GFC_OK;
+  GFC_REQUIRE(x && rowptr && colidx && h && y, GFC_ERR_BAD_ARG, "%s: NULL pointer", fn);
+  GFC_REQUIRE((G & 3) == 0, GFC_ERR_UNSUPPORTED, "%s: G=%d must be a multiple of 4", fn, G);
+  GenericPlan g;
+  plan_generic(B, N, G, F, K, 1, 0, 0, &g);
+  rc = need_ws(fn, workspace, workspace_bytes, g.ws_bytes);
+  if (rc) return rc;
+  float* Zw = reinterpret_cast<float*>(static_cast<char*>(workspace) + g.ws_z);
+  const long long C = (long long)K * G;
+  rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);
+  if (rc) return rc;
+  for (int k = 1; k < K; ++k) {
+    rc = launch_hop_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, k - 1, k, 0, st);
+    if (rc) return rc;
+  }
+  return launch_sgemm(Zw, C, 1, h, 1, C, y, F, 0, (long long)B * N, F, C, 1, bias, act, slope, st);
+}
+
+extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                                  const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                                  int64_t nnz_stride, const float* h, const float* y_out, const float* dY,
+                                  float* dX, float* dH, float* db, int B, int N, int G, int F, int K,
+                                  int act, float slope, int precision,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  const char* fn = "gfc_filter_csr_bwd";
+  launch_counter() = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = check_common(fn, B, N, G, F, K, 1, act, precision);
+  if (rc) return rc;
+  const size_t nH = (size_t)F * K * G;
+  if (B == 0) {
+    if (dH) GFC_CUDA_TRY(cudaMemsetAsync(dH, 0, nH * sizeof(float), st));
+    if (db) GFC_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)F * sizeof(float), st));
+    return GFC_OK;
+  }
+  GFC_REQUIRE(rowptr && colidx && rowptr_t && colidx_t && h && dY, GFC_ERR_BAD_ARG, "%s: NULL pointer", fn);
+  GFC_REQUIRE(!dH || x, GFC_ERR_BAD_ARG, "%s: x is required for dH", fn);
+  GFC_REQUIRE(act == GFC_ACT_NONE || y_out, GFC_ERR_BAD_ARG, "%s: y_out is required with a fused activation", fn);
+  GFC_REQUIRE((G & 3) == 0, GFC_ERR_UNSUPPORTED, "%s: G=%d must be a multiple of 4", fn, G);
+  if (!dX && !dH && !db) return GFC_OK;
+  GenericPlan g;
+  plan_generic(B, N, G, F, K, 1, 1, 0, &g);
+  rc = need_ws(fn, workspace, workspace_bytes, g.ws_bytes);
+  if (rc) return rc;
+  char* wsb = static_cast<char*>(workspace);
+  float* Zw = reinterpret_cast<float*>(wsb + g.ws_z);
+  float* Dw = reinterpret_cast<float*>(wsb + g.ws_d);
+  const long long rows = (long long)B * N;
+  const long long C = (long long)K * G;
+  rc = launch_dpre(dY, y_out, Dw, rows * F, act, slope, st);
+  if (rc) return rc;
+  if (db) {
+    float* part = reinterpret_cast<float*>(wsb + g.ws_dbp);
+    rc = launch_colsum(Dw, rows, F, g.rows_per_chunk, g.nchunks, part, st);
+    if (rc) return rc;
+    rc = launch_reduce_parts(part, g.nchunks, F, db, st);
+    if (rc) return rc;
+  }
+  if (dH) {
+    rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);
+    if (rc) return rc;
+    for (int k = 1; k < K; ++k) {
+      rc = launch_hop_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, k - 1, k, 0, st);
+      if (rc) return rc;
+    }
+    float* part = reinterpret_cast<float*>(wsb + g.ws_dhp);
+    rc = launch_sgemm(Dw, 1, F, Zw, C, 1, part, C, (long long)nH, F, (int)C, rows, g.nsplit, nullptr,
+                      GFC_ACT_NONE, 0.f, st);
+    if (rc) return rc;
+    rc = launch_reduce_parts(part, g.nsplit, (int)nH, dH, st);
+    if (rc) return rc;
+  }
+  if (dX) {
+    rc = launch_sgemm(Dw, F, 1, h, C, 1, Zw, C, 0, rows, (int)C, F, 1, nullptr, GFC_ACT_NONE, 0.f, st);
+    if (rc) return rc;
+    for (int k = K - 2; k >= 0; --k) {
+      rc = launch_hop_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, k + 1, k, 1, st);
+      if (rc) return rc;
+    }
+    rc = launch_xpose_out(Zw, dX, B, N, G, 1, K, st);
+    if (rc) return rc;
+  }
+  return GFC_OK;
+}

@@ -1,0 +1,278 @@
+// gfc_generic.cu — path B: the same filter through a node-major workspace
+// Zw[b][n][(e*K+k)*G+g] in HBM.  Covers every shape the fused tile kernels do not
+// (E > 1, odd G/F, graphs too large for shared memory) and carries kernel (d),
+// the CSR SpMM diffusion for large sparse swarms.  Simple, general CUDA; still
+// no library calls and no CPU fallback.
+//
+// Reference semantics: BatchLSIGF utils/graphUtils/graphML.py:2273-2367.
+#include "gfc_generic.cuh"
+
+namespace gfc {
+
+// x[b][g][n] -> Zw[(b*N+n)*C + (e*K)*G + g] for every e (k = 0 slice, graphML.py:2345)
+__global__ void __launch_bounds__(256)
+xpose_in_kernel(const float* __restrict__ x, float* __restrict__ Zw, int B, int N, int G, int E, int K) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int C = E * K * G;
+  for (int i = ty; i < 32; i += 8) {
+    const int g = g0 + i, n = n0 + tx;
+    tile[i][tx] = (g < G && n < N) ? x[((size_t)b * G + g) * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, g = g0 + tx;
+    if (n < N && g < G) {
+      const float v = tile[tx][i];
+      float* row = Zw + ((size_t)b * N + n) * C + g;
+      for (int e = 0; e < E; ++e) row[(size_t)e * K * G] = v;
+    }
+  }
+}
+
+// dX[b][g][n] = sum_e Uw[(b*N+n)*C + (e*K)*G + g]
+__global__ void __launch_bounds__(256)
+xpose_out_kernel(const float* __restrict__ Uw, float* __restrict__ dX, int B, int N, int G, int E, int K) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int n0 = blockIdx.x * 32, g0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int C = E * K * G;
+  for (int i = ty; i < 32; i += 8) {
+    const int n = n0 + i, g = g0 + tx;
+    float v = 0.f;
+    if (n < N && g < G) {
+      const float* row = Uw + ((size_t)b * N + n) * C + g;
+      for (int e = 0; e < E; ++e) v += row[(size_t)e * K * G];
+    }
+    tile[i][tx] = v;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int g = g0 + i, n = n0 + tx;
+    if (g < G && n < N) dX[((size_t)b * G + g) * N + n] = tile[tx][i];
+  }
+}
+
+// dense hop over the workspace, one thread per (b, e, n, g)
+//   !T: W[b][n][dst] = sum_m S[b][e][m][n] W[b][m][src]      (z_k = z_{k-1} S)
+//    T: W[b][n][dst] += sum_m S[b][e][n][m] W[b][m][src]     (acc S^T + U_k)
+template <bool T>
+__global__ void __launch_bounds__(256)
+hop_dense_kernel(float* __restrict__ W, const float* __restrict__ S, int B, int N, int G, int E, int K,
+                 int ksrc, int kdst) {
+  const long long total = (long long)B * E * N * G;
+  const int C = E * K * G;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(idx % G);
+    long long q = idx / G;
+    const int n = (int)(q % N); q /= N;
+    const int e = (int)(q % E);
+    const int b = (int)(q / E);
+    const float* Sb = S + ((size_t)b * E + e) * N * N;
+    const float* src = W + (size_t)b * N * C + (size_t)(e * K + ksrc) * G + g;
+    float* dst = W + ((size_t)b * N + n) * C + (size_t)(e * K + kdst) * G + g;
+    float acc = T ? *dst : 0.f;
+    for (int m = 0; m < N; ++m) {
+      const float w = T ? Sb[(size_t)n * N + m] : Sb[(size_t)m * N + n];
+      if (w != 0.f) acc = fmaf(w, src[(size_t)m * C], acc);
+    }
+    *dst = acc;
+  }
+}
+
+// CSR hop (E = 1): lists of row n give the m to gather and the weight.
+template <bool ACCUM>
+__global__ void __launch_bounds__(256)
+hop_csr_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+               const float* __restrict__ vals, long long nnz_stride, int B, int N, int G, int K,
+               int ksrc, int kdst) {
+  const int C = K * G;
+  const int G4 = G >> 2;
+  const long long total = (long long)B * N * G4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int g4 = (int)(idx % G4);
+    const long long q = idx / G4;
+    const int n = (int)(q % N);
+    const int b = (int)(q / N);
+    const int32_t* rp = rowptr + (size_t)b * (N + 1);
+    const int32_t* ci = colidx + (size_t)b * nnz_stride;
+    const float* vv = vals ? vals + (size_t)b * nnz_stride : nullptr;
+    const float* src = W + (size_t)b * N * C + (size_t)ksrc * G + (g4 << 2);
+    float* dst = W + ((size_t)b * N + n) * C + (size_t)kdst * G + (g4 << 2);
+    float4 acc = ACCUM ? *reinterpret_cast<const float4*>(dst) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int beg = rp[n], end = rp[n + 1];
+    for (int i = beg; i < end; ++i) {
+      const int m = ci[i];
+      const float w = vv ? vv[i] : 1.f;
+      const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * C);
+      acc.x = fmaf(w, z.x, acc.x);
+      acc.y = fmaf(w, z.y, acc.y);
+      acc.z = fmaf(w, z.z, acc.z);
+      acc.w = fmaf(w, z.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(dst) = acc;
+  }
+}
+
+// D = dY * act'(y_out)
+__global__ void __launch_bounds__(256)
+dpre_kernel(const float* __restrict__ dY, const float* __restrict__ yout, float* __restrict__ D,
+            long long n, int act, float slope) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v = dY[i];
+    if (act != GFC_ACT_NONE) v = act_grad(v, yout[i], act, slope);
+    D[i] = v;
+  }
+}
+
+// partial column sums: part[chunk][f] = sum over the chunk's rows of D[r][f]
+__global__ void __launch_bounds__(256)
+colsum_kernel(const float* __restrict__ D, long long rows, int F, int rows_per_chunk, float* __restrict__ part) {
+  const long long r0 = (long long)blockIdx.x * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float s = 0.f;
+    for (long long r = r0; r < r1; ++r) s += D[r * F + f];
+    part[(size_t)blockIdx.x * F + f] = s;
+  }
+}
+
+// Generic strided SGEMM, 32x32 tile, 2x2 per thread, optional split over k
+// (gridDim.z, partial results at Cout + z*c_zstride), optional bias(n)+activation.
+__global__ void __launch_bounds__(256)
+sgemm_kernel(const float* __restrict__ A, long long a_rs, long long a_cs,
+             const float* __restrict__ Bm, long long b_rs, long long b_cs,
+             float* __restrict__ Cout, long long ldc, long long c_zstride,
+             long long M, int Nn, long long Kd, long long k_per_z,
+             const float* __restrict__ bias, int act, float slope) {
+  __shared__ float As[32][17];
+  __shared__ float Bs[16][33];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = (long long)blockIdx.x * 32;
+  const int n0 = blockIdx.y * 32;
+  const long long kbeg = (long long)blockIdx.z * k_per_z;
+  long long kend = kbeg + k_per_z;
+  if (kend > Kd) kend = Kd;
+  float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+  for (long long k0 = kbeg; k0 < kend; k0 += 16) {
+    for (int i = tid; i < 512; i += 256) {
+      const int mm = i >> 4, kk = i & 15;
+      const long long m = m0 + mm, k = k0 + kk;
+      As[mm][kk] = (m < M && k < kend) ? A[m * a_rs + k * a_cs] : 0.f;
+    }
+    for (int i = tid; i < 512; i += 256) {
+      const int kk = i >> 5, nn = i & 31;
+      const long long k = k0 + kk;
+      const int n = n0 + nn;
+      Bs[kk][nn] = (k < kend && n < Nn) ? Bm[k * b_rs + (long long)n * b_cs] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float a0 = As[ty * 2][kk], a1 = As[ty * 2 + 1][kk];
+      const float b0 = Bs[kk][tx * 2], b1 = Bs[kk][tx * 2 + 1];
+      c00 = fmaf(a0, b0, c00); c01 = fmaf(a0, b1, c01);
+      c10 = fmaf(a1, b0, c10); c11 = fmaf(a1, b1, c11);
+    }
+    __syncthreads();
+  }
+  float* Cz = Cout + (size_t)blockIdx.z * c_zstride;
+  const float cc[2][2] = {{c00, c01}, {c10, c11}};
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const long long m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int n = n0 + tx * 2 + j;
+      if (n >= Nn) continue;
+      float v = cc[i][j];
+      if (bias) v += bias[n];
+      v = apply_act(v, act, slope);
+      Cz[m * ldc + n] = v;
+    }
+  }
+}
+
+static unsigned grid_for(long long total, int block, int cap) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+int launch_xpose_in(const float* x, float* Zw, int B, int N, int G, int E, int K, cudaStream_t st) {
+  dim3 grid(ceil_div(N, 32), ceil_div(G, 32), B);
+  GFC_REQUIRE(B <= 65535, GFC_ERR_UNSUPPORTED, "path B: B=%d > 65535 graphs per call; split the batch", B);
+  xpose_in_kernel<<<grid, 256, 0, st>>>(x, Zw, B, N, G, E, K);
+  GFC_LAUNCH_CHECK("xpose_in_kernel");
+  return GFC_OK;
+}
+
+int launch_xpose_out(const float* Uw, float* dX, int B, int N, int G, int E, int K, cudaStream_t st) {
+  dim3 grid(ceil_div(N, 32), ceil_div(G, 32), B);
+  GFC_REQUIRE(B <= 65535, GFC_ERR_UNSUPPORTED, "path B: B=%d > 65535 graphs per call; split the batch", B);
+  xpose_out_kernel<<<grid, 256, 0, st>>>(Uw, dX, B, N, G, E, K);
+  GFC_LAUNCH_CHECK("xpose_out_kernel");
+  return GFC_OK;
+}
+
+int launch_hop_dense(float* W, const float* S, int B, int N, int G, int E, int K, int ksrc, int kdst,
+                     int transposed, cudaStream_t st) {
+  const long long total = (long long)B * E * N * G;
+  const unsigned grid = grid_for(total, 256, 148 * 32);
+  if (transposed) hop_dense_kernel<true><<<grid, 256, 0, st>>>(W, S, B, N, G, E, K, ksrc, kdst);
+  else hop_dense_kernel<false><<<grid, 256, 0, st>>>(W, S, B, N, G, E, K, ksrc, kdst);
+  GFC_LAUNCH_CHECK("hop_dense_kernel");
+  return GFC_OK;
+}
+
+int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                   long long nnz_stride, int B, int N, int G, int K, int ksrc, int kdst, int accum,
+                   cudaStream_t st) {
+  const long long total = (long long)B * N * (G >> 2);
+  const unsigned grid = grid_for(total, 256, 148 * 32);
+  if (accum) hop_csr_kernel<true><<<grid, 256, 0, st>>>(W, rowptr, colidx, vals, nnz_stride, B, N, G, K, ksrc, kdst);
+  else hop_csr_kernel<false><<<grid, 256, 0, st>>>(W, rowptr, colidx, vals, nnz_stride, B, N, G, K, ksrc, kdst);
+  GFC_LAUNCH_CHECK("hop_csr_kernel");
+  return GFC_OK;
+}
+
+int launch_dpre(const float* dY, const float* yout, float* D, long long n, int act, float slope, cudaStream_t st) {
+  dpre_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st>>>(dY, yout, D, n, act, slope);
+  GFC_LAUNCH_CHECK("dpre_kernel");
+  return GFC_OK;
+}
+
+int launch_colsum(const float* D, long long rows, int F, int rows_per_chunk, int nchunks, float* part,
+                  cudaStream_t st) {
+  colsum_kernel<<<nchunks, 256, 0, st>>>(D, rows, F, rows_per_chunk, part);
+  GFC_LAUNCH_CHECK("colsum_kernel");
+  return GFC_OK;
+}
+
+int launch_sgemm(const float* A, long long a_rs, long long a_cs, const float* Bm, long long b_rs, long long b_cs,
+                 float* C, long long ldc, long long c_zstride, long long M, int Nn, long long Kd,
+                 int nsplit, const float* bias, int act, float slope, cudaStream_t st) {
+  if (M == 0 || Nn == 0) return GFC_OK;
+  const long long mblocks = (M + 31) / 32;
+  GFC_REQUIRE(mblocks <= 0x7fffffffLL, GFC_ERR_UNSUPPORTED, "sgemm: M too large");
+  long long k_per_z = (Kd + nsplit - 1) / nsplit;
+  k_per_z = (k_per_z + 15) / 16 * 16;
+  if (k_per_z < 16) k_per_z = 16;
+  dim3 grid((unsigned)mblocks, ceil_div(Nn, 32), nsplit);
+  sgemm_kernel<<<grid, 256, 0, st>>>(A, a_rs, a_cs, Bm, b_rs, b_cs, C, ldc, c_zstride, M, Nn, Kd, k_per_z,
+                                     bias, act, slope);
+  GFC_LAUNCH_CHECK("sgemm_kernel");
+  return GFC_OK;
+}
+
+}  // namespace gfc

@@ -1,0 +1,23 @@
+// gfc_generic.cuh — launchers of the workspace pipeline (path B).
+#pragma once
+#include "gfc_common.cuh"
+
+namespace gfc {
+
+int launch_xpose_in(const float* x, float* Zw, int B, int N, int G, int E, int K, cudaStream_t st);
+int launch_xpose_out(const float* Uw, float* dX, int B, int N, int G, int E, int K, cudaStream_t st);
+int launch_hop_dense(float* W, const float* S, int B, int N, int G, int E, int K, int ksrc, int kdst,
+                     int transposed, cudaStream_t st);
+int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                   long long nnz_stride, int B, int N, int G, int K, int ksrc, int kdst, int accum,
+                   cudaStream_t st);
+int launch_dpre(const float* dY, const float* yout, float* D, long long n, int act, float slope, cudaStream_t st);
+int launch_colsum(const float* D, long long rows, int F, int rows_per_chunk, int nchunks, float* part,
+                  cudaStream_t st);
+// C[m][n] = act(sum_k A(m,k) B(k,n) + bias[n]);  A(m,k) = A[m*a_rs + k*a_cs], B(k,n) = B[k*b_rs + n*b_cs].
+// nsplit > 1 writes nsplit partial matrices at C + z*c_zstride (bias/act must be off).
+int launch_sgemm(const float* A, long long a_rs, long long a_cs, const float* Bm, long long b_rs, long long b_cs,
+                 float* C, long long ldc, long long c_zstride, long long M, int Nn, long long Kd,
+                 int nsplit, const float* bias, int act, float slope, cudaStream_t st);
+
+}  // namespace gfc

@@ -1,0 +1,170 @@
+/*
+ * gfc.h — C ABI of libgfc.so: the B200 (sm_100a) graph-filter hot path of
+ * soosiey/gnn-formation-control.
+ *
+ * The reference has no native seam around this path: the seam is the Python
+ * nn.Module surface (utils/graphUtils/graphML.py:2369-2488).  Its only FFI
+ * precedent is ctypes -> remoteApi.so with int32 status returns (sim.py:21,
+ * simConst.py simx_return_ok = 0); this ABI mirrors that convention:
+ *   - plain pointers and sizes, no torch types;
+ *   - every entry point returns int (0 = GFC_OK); gfc_last_error() gives text;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); the library
+ *     keeps no pointer after return, never synchronises, never touches the
+ *     default stream: all work is enqueued on the cudaStream_t passed as
+ *     `stream` (void*; pass torch.cuda.current_stream().cuda_stream).
+ *
+ * Layouts (all device pointers, fp32 unless stated, contiguous row-major):
+ *   pos   [B, N, 2]      robot xy positions                (scene.py:147-148)
+ *   adj   [B, N, N] u8   1-hop mask, adj[b,i,j] in {0,1}   (scene.py:140-154)
+ *   S     [B, E, N, N]   graph shift operator              (graphML.py:2449-2456)
+ *   x     [B, G, N]      node signals, feature-major       (graphML.py:2458)
+ *   h     [F, E, K, G]   filter taps  (nn.Parameter weight, graphML.py:2434)
+ *   bias  [F]            (nn.Parameter bias [F,1],          graphML.py:2436)
+ *   y     [B, N, F]      NODE-major memory.  The reference returns a [B,F,N]
+ *                        view with strides (N*F, 1, F) over exactly this
+ *                        memory (graphML.py:2361-2362: matmul -> permute).
+ *   dY    [B, N, F]      upstream gradient in the same memory layout
+ *   dX    [B, G, N]
+ *   dH    [F, E, K, G],  db [F]
+ * Row-vector convention of the reference: z_k = z_{k-1} . S  (graphML.py:2350),
+ * y[b,f,n] = sum_{e,k,g} h[f,e,k,g] z[b,e,k,g,n] + bias[f]   (graphML.py:2361-2366).
+ */
+#ifndef GFC_H_
+#define GFC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GFC_VERSION 100 /* major*100 + minor */
+
+/* status codes (0 = ok, like simx_return_ok) */
+enum {
+  GFC_OK = 0,
+  GFC_ERR_BAD_ARG = 1,     /* null pointer / non-positive size / bad enum      */
+  GFC_ERR_UNSUPPORTED = 2, /* shape outside what the kernels cover             */
+  GFC_ERR_WORKSPACE = 3,   /* workspace missing or too small                   */
+  GFC_ERR_CUDA = 4         /* a CUDA call failed; text in gfc_last_error()     */
+};
+
+/* position -> GSO rule */
+enum {
+  GFC_GSO_BINARY_LE = 0,   /* scene.py:147-152: a = (i!=j) && sqrt(dx^2+dy^2) <= R   */
+  GFC_GSO_SYM_NORM_LT = 1, /* multirobotsim_dcenlocal.py:306-315: W=(d<R), D^-1/2 W D^-1/2 */
+  GFC_GSO_BINARY_LT = 2    /* the unnormalised W of mode 1                            */
+};
+
+/* activation fused behind the filter (suhaas_model.py:120, decentralplanner.py:221) */
+enum { GFC_ACT_NONE = 0, GFC_ACT_RELU = 1, GFC_ACT_LEAKY_RELU = 2 };
+
+/* arithmetic of the tap contraction (the diffusion hops are always fp32 FMA)  */
+enum {
+  GFC_PREC_FP32_3XTF32 = 0, /* tensor cores, hi/lo split, fp32-equivalent (<=1e-5) */
+  GFC_PREC_TF32 = 1         /* single pass tf32, looser bound (~1e-3), opt-in       */
+};
+
+int gfc_version(void);
+/* thread-local text of the last non-zero status returned on this thread */
+const char* gfc_last_error(void);
+/* SM count, compute capability and opt-in shared memory of the current device */
+int gfc_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes);
+
+/* ---- (a) position -> GSO -------------------------------------------------- *
+ * Replaces Scene.readADjMatrix (scene.py:140-154) and
+ * multiRobotSim.computeAdjacencyMatrix_fixedCommRadius
+ * (utils/multirobotsim_dcenlocal.py:291-317).  The comparison is carried out in
+ * fp64 on the device so the mask is bit-identical to the reference's python /
+ * numpy float64 arithmetic.  adj_out and/or S_out may be NULL.                */
+int gfc_gso_build(const float* pos, int B, int N, double radius, int mode,
+                  uint8_t* adj_out, float* S_out, void* stream);
+
+/* ---- (b) filter forward --------------------------------------------------- *
+ * Replaces GraphFilterBatch.forward -> BatchLSIGF (graphML.py:2458-2477,
+ * 2273-2367) plus the activation that follows it in the policy.  Workspace:
+ * gfc_filter_workspace_bytes(); may be NULL when that returns 0.              */
+size_t gfc_filter_workspace_bytes(int B, int N, int G, int F, int K, int E, int backward);
+
+int gfc_filter_fwd(const float* x, const float* S, const float* h, const float* bias,
+                   float* y, int B, int N, int G, int F, int K, int E,
+                   int act, float slope, int precision,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same filter with the GSO rebuilt on chip from positions (E = 1): S never
+ * exists in HBM.  Replaces robot.py:654 + suhaas_model.py:149-159,182-185.    */
+int gfc_filter_fwd_pos(const float* x, const float* pos, double radius, int mode,
+                       const float* h, const float* bias, float* y,
+                       int B, int N, int G, int F, int K,
+                       int act, float slope, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (c) filter backward (replaces autograd through graphML.py:2342-2366) -- *
+ * y_out is the forward OUTPUT (after the activation); it is only read when
+ * act != GFC_ACT_NONE (to recover the activation mask) and may be NULL
+ * otherwise.  dX / dH / db may each be NULL to skip that gradient.  dH and db
+ * are overwritten (not accumulated) and are reduced deterministically.        */
+int gfc_filter_bwd(const float* x, const float* S, const float* h, const float* y_out,
+                   const float* dY, float* dX, float* dH, float* db,
+                   int B, int N, int G, int F, int K, int E,
+                   int act, float slope, int precision,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+int gfc_filter_bwd_pos(const float* x, const float* pos, double radius, int mode,
+                       const float* h, const float* y_out, const float* dY,
+                       float* dX, float* dH, float* db,
+                       int B, int N, int G, int F, int K,
+                       int act, float slope, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- (d) CSR variant for large sparse swarms ------------------------------ *
+ * gfc_csr_count : deg[b,n] = in-degree under the radius rule (int32 [B,N]).
+ * gfc_csr_fill  : given rowptr [B, N+1] (exclusive scan of deg per graph, int32,
+ *                 offsets relative to the graph's own segment base b*nnz_stride)
+ *                 writes colidx (ascending per row) and, for SYM_NORM, vals.
+ * The position-built GSOs are symmetric, so one CSR serves both S and S^T.   */
+int gfc_csr_count(const float* pos, int B, int N, double radius, int mode,
+                  int32_t* deg, void* stream);
+/* rowptr[b, 0..N] = exclusive scan of deg[b, :] (rowptr[b, N] = nnz of graph b) */
+int gfc_csr_scan(const int32_t* deg, int B, int N, int32_t* rowptr, void* stream);
+int gfc_csr_fill(const float* pos, int B, int N, double radius, int mode,
+                 const int32_t* rowptr, int64_t nnz_stride,
+                 int32_t* colidx, float* vals, void* stream);
+
+/* CSR of S^T ("gather lists": row n holds the m with S[m,n] != 0, value S[m,n]).
+ * vals may be NULL (all ones).  csr_t_* is the CSR of S itself, needed by the
+ * backward; pass the same arrays when S is symmetric.                         */
+size_t gfc_filter_csr_workspace_bytes(int B, int N, int G, int F, int K, int backward);
+
+int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const int32_t* colidx,
+                       const float* vals, int64_t nnz_stride,
+                       const float* h, const float* bias, float* y,
+                       int B, int N, int G, int F, int K,
+                       int act, float slope, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const int32_t* colidx,
+                       const float* vals,
+                       const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                       int64_t nnz_stride,
+                       const float* h, const float* y_out, const float* dY,
+                       float* dX, float* dH, float* db,
+                       int B, int N, int G, int F, int K,
+                       int act, float slope, int precision,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- introspection used by bench.py / tests -------------------------------- *
+ * Which kernel family a shape dispatches to: 1 = fused shared-memory tile
+ * kernel, 2 = workspace pipeline (dense hops), 0 = unsupported.               */
+int gfc_filter_path(int B, int N, int G, int F, int K, int E, int backward);
+/* Tile plan of path A for a shape: out[12] = {ok, graphs_per_tile, rows, rows_padded,
+ * ntiles, grid, smem_bytes, taps_in_smem, dH_in_registers, nb_dh, nparts, ldz}.  */
+int gfc_tile_plan_info(int B, int N, int G, int F, int K, int backward, int from_positions, int* out);
+/* number of kernel launches the last call on this thread enqueued */
+int gfc_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFC_H_ */

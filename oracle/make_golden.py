@@ -1,0 +1,189 @@
+"""TEST INFRASTRUCTURE ONLY — generate ``tests/golden/*.npz`` by EXECUTING THE
+REFERENCE ITSELF (only possible in the build container where /root/reference
+exists).  Re-run with ``python -m oracle.make_golden`` from the repo root.
+
+Everything stored under "expected" comes out of reference code:
+  * ``Scene.readADjMatrix``                             (scene.py:140-154)
+  * ``computeAdjacencyMatrix_fixedCommRadius``          (utils/multirobotsim_dcenlocal.py:291-317)
+  * ``GraphFilterBatch.addGSO/forward`` + autograd      (utils/graphUtils/graphML.py:2369-2488)
+  * ``nn.LeakyReLU`` as wired in the policy             (graphs/models/suhaas_model.py:120)
+Inputs are the reference's recorded trajectories (positionList_*.npy; layout
+index = t*N + robot, test5_more_robots.py:176-178) or seeded random tensors.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+from oracle import refimport as ri  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+def load_frames(name, n):
+    """positionList_* [episodes, T*n, 2] float64 -> [episodes*T, n, 2]."""
+    a = np.load(os.path.join(ri.REF_ROOT, name))
+    ep, tn, _ = a.shape
+    assert tn % n == 0
+    return a.reshape(ep * (tn // n), n, 2)
+
+
+def ref_binary(frames, radius):
+    out = np.zeros((len(frames), frames.shape[1], frames.shape[1]), dtype=np.uint8)
+    for i, fr in enumerate(frames):
+        a = ri.scene_read_adj(fr.tolist(), radius)
+        assert a.shape == (1, fr.shape[0] ** 2)
+        out[i] = a.reshape(fr.shape[0], fr.shape[0]).astype(np.uint8)
+    return out
+
+
+def ref_symnorm(frames, radius):
+    out = np.zeros((len(frames), frames.shape[1], frames.shape[1]), dtype=np.float64)
+    for i, fr in enumerate(frames):
+        W, _ = ri.fixed_radius_gso(fr[None].astype(np.float64), radius)
+        out[i] = W[0]
+    return out
+
+
+def gso_goldens():
+    # cfg1: every frame of the 3-robot expert run (3000 graphs)
+    f3 = load_frames("positionList_expert_3.npy", 3)
+    assert np.array_equal(f3.astype(np.float32).astype(np.float64), f3), "fixture not fp32-exact"
+    np.savez_compressed(os.path.join(OUT, "gso_expert3.npz"),
+                        pos=f3.astype(np.float32), radius=2.0,
+                        adj_le=ref_binary(f3, 2), )
+    # 8 robots: every 8th frame; both builders
+    f8 = load_frames("positionList_expert_8.npy", 8)[::8]
+    np.savez_compressed(os.path.join(OUT, "gso_expert8.npz"),
+                        pos=f8.astype(np.float32), radius=2.0,
+                        adj_le=ref_binary(f8, 2), s_symnorm=ref_symnorm(f8, 2.0))
+    # 12 robots (long run): 250 frames spread over the file
+    f12 = load_frames("positionList_expert_12_longer.npy", 12)
+    f12 = f12[:: max(1, len(f12) // 250)][:250]
+    np.savez_compressed(os.path.join(OUT, "gso_expert12.npz"),
+                        pos=f12.astype(np.float32), radius=2.0,
+                        adj_le=ref_binary(f12, 2), s_symnorm=ref_symnorm(f12, 2.0))
+    # ties d == R and near-threshold pairs; isolated nodes; coincident robots
+    ties = np.array([
+        [[0, 0], [2, 0], [0, -2], [2, 2], [4, 0], [1, 0]],
+        [[0, 0], [1.2, 1.6], [-1.2, 1.6], [0, 2.0000002], [0, 1.9999999], [9, 9]],
+        [[0, 0], [0, 0], [2, 0], [2, 0], [50, 50], [-50, 50]],
+        [[1, 1], [1 + 2 ** -20, 1], [3, 1], [3 + 2 ** -22, 1], [1, 3], [1, 3 - 2 ** -22]],
+    ], dtype=np.float32).astype(np.float64)
+    np.savez_compressed(os.path.join(OUT, "gso_ties.npz"),
+                        pos=ties.astype(np.float32), radius=2.0,
+                        adj_le=ref_binary(ties, 2), s_symnorm=ref_symnorm(ties, 2.0))
+    tri = np.array([[[0, 0], [3, 4], [-3, 4], [6, 8], [3, 4.000001], [0, 5]]],
+                   dtype=np.float32).astype(np.float64)
+    np.savez_compressed(os.path.join(OUT, "gso_ties_r5.npz"),
+                        pos=tri.astype(np.float32), radius=5.0,
+                        adj_le=ref_binary(tri, 5), s_symnorm=ref_symnorm(tri, 5.0))
+
+
+def run_ref_filter(gml, h, b, S, x, dOut, leaky, nin=None):
+    F, E, K, G = h.shape
+    m = gml.GraphFilterBatch(G, F, K, E, bias=b is not None)
+    with torch.no_grad():
+        m.weight.copy_(torch.from_numpy(h))
+        if b is not None:
+            m.bias.copy_(torch.from_numpy(b))
+    xt = torch.from_numpy(x).clone().requires_grad_(True)
+    m.addGSO(torch.from_numpy(S))
+    y = m(xt)
+    if leaky:
+        y = torch.nn.LeakyReLU()(y)
+    assert y.dtype == torch.float64
+    (y * torch.from_numpy(dOut)).sum().backward()
+    out = dict(h=h, S=S, x=x, dOut=dOut, leaky=np.int32(leaky),
+               y=y.detach().numpy(), dX=xt.grad.numpy().astype(np.float64),
+               dH=m.weight.grad.numpy().astype(np.float64))
+    if b is not None:
+        out["b"] = b
+        out["db"] = m.bias.grad.numpy().astype(np.float64)
+    return out
+
+
+def filter_goldens():
+    gml = ri.graphml()
+    rng = np.random.default_rng(1234)
+
+    def taps(G, F, K, E, bias, seed):
+        torch.manual_seed(seed)
+        m = gml.GraphFilterBatch(G, F, K, E, bias=bias)  # reference reset_parameters()
+        return (m.weight.detach().numpy().copy(),
+                m.bias.detach().numpy().copy() if bias else None)
+
+    # case cfg1: first 64 graphs of the 3-robot expert fixture, 128->128, K=3, LeakyReLU
+    g = np.load(os.path.join(OUT, "gso_expert3.npz"))
+    idx = np.arange(0, 3000, 3000 // 64)[:64]
+    S = g["adj_le"][idx].astype(np.float32)[:, None]
+    h, b = taps(128, 128, 3, 1, True, 0)
+    torch.manual_seed(0)
+    x = torch.randn(64, 128, 3).numpy()
+    dOut = rng.standard_normal((64, 128, 3))
+    np.savez_compressed(os.path.join(OUT, "filter_cfg1.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, True))
+
+    # case general: asymmetric weighted S, E=2, odd sizes, no activation
+    h, b = taps(5, 7, 4, 2, True, 1)
+    S = rng.standard_normal((3, 2, 6, 6)).astype(np.float32)
+    x = rng.standard_normal((3, 5, 6)).astype(np.float32)
+    dOut = rng.standard_normal((3, 7, 6))
+    np.savez_compressed(os.path.join(OUT, "filter_general_e2.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, False))
+
+    # case K=1, no bias
+    h, b = taps(8, 4, 1, 1, False, 2)
+    S = rng.standard_normal((5, 1, 4, 4)).astype(np.float32)
+    x = rng.standard_normal((5, 8, 4)).astype(np.float32)
+    dOut = rng.standard_normal((5, 4, 4))
+    np.savez_compressed(os.path.join(OUT, "filter_k1_nobias.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, False))
+
+    # case Nin < N zero-pad (graphML.py:2464-2476)
+    h, b = taps(6, 6, 3, 1, True, 3)
+    S = (rng.random((4, 1, 6, 6)) < 0.4).astype(np.float32)
+    x = rng.standard_normal((4, 6, 4)).astype(np.float32)
+    dOut = rng.standard_normal((4, 6, 4))
+    np.savez_compressed(os.path.join(OUT, "filter_nin_lt_n.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, True))
+
+    # case cfg2-shaped slice with the normalised GSO of the 8-robot fixture
+    g8 = np.load(os.path.join(OUT, "gso_expert8.npz"))
+    S = g8["s_symnorm"][:32].astype(np.float32)[:, None]
+    h, b = taps(32, 32, 3, 1, True, 4)
+    x = rng.standard_normal((32, 32, 8)).astype(np.float32)
+    dOut = rng.standard_normal((32, 32, 8))
+    np.savez_compressed(os.path.join(OUT, "filter_cfg2_symnorm.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, True))
+
+    # case cyclic (asymmetric) GSO from suhaas_test.py:16
+    cyc = np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]], dtype=np.float32)
+    S = np.broadcast_to(cyc, (2, 1, 3, 3)).copy()
+    h, b = taps(16, 16, 3, 1, True, 5)
+    x = rng.standard_normal((2, 16, 3)).astype(np.float32)
+    dOut = rng.standard_normal((2, 16, 3))
+    np.savez_compressed(os.path.join(OUT, "filter_cyclic.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, True))
+
+    # case 12 robots, binary GSO, 128->128 (rollout layer shape, cfg4)
+    g12 = np.load(os.path.join(OUT, "gso_expert12.npz"))
+    S = g12["adj_le"][:8].astype(np.float32)[:, None]
+    h, b = taps(128, 128, 3, 1, True, 6)
+    x = rng.standard_normal((8, 128, 12)).astype(np.float32)
+    dOut = rng.standard_normal((8, 128, 12))
+    np.savez_compressed(os.path.join(OUT, "filter_cfg4_n12.npz"),
+                        **run_ref_filter(gml, h, b, S, x, dOut, True))
+
+
+if __name__ == "__main__":
+    assert ri.available(), "run in the build container (needs /root/reference)"
+    os.makedirs(OUT, exist_ok=True)
+    gso_goldens()
+    filter_goldens()
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -1,0 +1,93 @@
+"""CPU: the nn.Module surface mirrors the reference layer
+(utils/graphUtils/graphML.py:2369-2488) — names, shapes, init law, asserts, repr,
+state_dict compatibility — and the product refuses to run without CUDA."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import gnnfc
+from oracle import refimport
+
+
+def test_constructor_and_parameters():
+    torch.manual_seed(0)
+    m = gnnfc.GraphFilterBatch(128, 64, 3)
+    assert (m.G, m.F, m.K, m.E) == (128, 64, 3, 1) and m.S is None
+    assert tuple(m.weight.shape) == (64, 1, 3, 128) and tuple(m.bias.shape) == (64, 1)
+    assert list(m.state_dict().keys()) == ["weight", "bias"]
+    s = 1.0 / math.sqrt(128 * 3)
+    assert float(m.weight.abs().max()) <= s and float(m.bias.abs().max()) <= s
+    assert float(m.weight.abs().max()) > 0.9 * s        # uniform, not tiny
+    m2 = gnnfc.GraphFilterBatch(4, 8, 2, E=2, bias=False)
+    assert m2.bias is None and list(m2.state_dict().keys()) == ["weight"]
+    assert tuple(m2.weight.shape) == (8, 2, 2, 4)
+
+
+def test_extra_repr_matches_reference_format():
+    m = gnnfc.GraphFilterBatch(4, 8, 3)
+    assert repr(m) == ("GraphFilterBatch(in_features=4, out_features=8, filter_taps=3, "
+                       "edge_features=1, bias=True, no GSO stored)")
+    m.addGSO(torch.zeros(2, 1, 5, 5))
+    assert repr(m).endswith("GSO stored)") and "no GSO" not in repr(m)
+
+
+def test_addgso_asserts_like_reference():
+    m = gnnfc.GraphFilterBatch(4, 8, 3, E=1)
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(2, 5, 5))            # rank != 4   (graphML.py:2451)
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(2, 2, 5, 5))         # E mismatch  (graphML.py:2453)
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(2, 1, 5, 4))         # non-square  (graphML.py:2455)
+    S = torch.zeros(2, 1, 5, 5)
+    m.addGSO(S)
+    assert m.N == 5 and m.S is S                  # stored by reference (graphML.py:2456)
+
+
+def test_no_cpu_fallback():
+    m = gnnfc.GraphFilterBatch(8, 8, 2)
+    m.addGSO(torch.zeros(2, 1, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(2, 8, 4))
+    with pytest.raises(RuntimeError, match="no CPU|CUDA"):
+        gnnfc.build_gso(torch.zeros(2, 4, 2), 2.0)
+
+
+@pytest.mark.skipif(not refimport.available(), reason="reference tree only exists in the build container")
+def test_state_dict_roundtrip_with_reference_layer():
+    gml = refimport.graphml()
+    torch.manual_seed(3)
+    ref = gml.GraphFilterBatch(16, 8, 3)
+    ours = gnnfc.GraphFilterBatch(16, 8, 3)
+    ours.load_state_dict(ref.state_dict())        # same keys / shapes
+    assert torch.equal(ours.weight, ref.weight) and torch.equal(ours.bias, ref.bias)
+    ref.load_state_dict(ours.state_dict())
+    # same init law under the same seed
+    torch.manual_seed(5); a = gml.GraphFilterBatch(16, 8, 3)
+    torch.manual_seed(5); b = gnnfc.GraphFilterBatch(16, 8, 3)
+    assert torch.equal(a.weight, b.weight) and torch.equal(a.bias, b.bias)
+    assert repr(a) == repr(b)
+
+
+def test_shard_range_partitions_batch():
+    for total in (0, 1, 7, 64, 4096, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [gnnfc.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_grad_bucket_pack_unpack_single_process():
+    p1 = torch.nn.Parameter(torch.randn(3, 4)); p2 = torch.nn.Parameter(torch.randn(5))
+    p1.grad = torch.randn(3, 4); p2.grad = None
+    b = gnnfc.GradBucket([p1, p2])
+    flat = b.pack()
+    assert flat.numel() == 17 and torch.equal(flat[:12].view(3, 4), p1.grad) and float(flat[12:].abs().sum()) == 0
+    flat.mul_(2)
+    g1 = p1.grad.clone()
+    b.allreduce(); b.unpack()
+    assert torch.allclose(p1.grad, 2 * g1) and p2.grad is not None and float(p2.grad.abs().sum()) == 0
