@@ -1,0 +1,557 @@
+#!/usr/bin/env python
+"""bench.py — agent-graphs/s of the fused GSO-build + K-hop graph filter, forward +
+backward, on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --steps K --warmup W     # reference CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                        # one rank per GPU, weak scaling
+
+One "step" = one pass of the hot path over ONE batch of the workload: positions ->
+GSO (rebuilt on chip), filter forward (+bias, LeakyReLU), filter backward (dX, dH,
+db) from a resident synthetic upstream gradient, deterministic gradient reduction,
+and — for N > 1 — the all-reduce of the flat [dH | db] bucket (NCCL over NVLink).
+
+Timing: CUDA events on the launching stream around exactly K steps, barrier +
+synchronize on both sides, max over ranks.  Inputs rotate through a ring of
+distinct batches larger than L2 (or a single batch that is itself > L2).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "agent-graphs/sec fwd+bwd (GSO build+K-hop filter)"
+L2_BYTES = 126 * 1024 * 1024
+
+# BASELINE.json configs -> concrete synthetic inputs
+WORKLOADS = {
+    "cfg1": dict(desc="cfg1: 3-robot expert fixture shape, GraphFilterBatch K=3 128->128, batch 64",
+                 B=64, N=3, G=128, F=128, K=3, box=4.0, seed=0, mode="binary_le", train=True),
+    "cfg2": dict(desc="cfg2: 8-robot formation policy, K=3, F=32->32, synthetic random-geometric graphs, "
+                      "batch 4096 graphs", B=4096, N=8, G=32, F=32, K=3, box=5.0, seed=1,
+                 mode="binary_le", train=True),
+    "cfg3": dict(desc="cfg3: 64-agent synthetic swarm, K=4, F=128->128, batch 65536 graphs",
+                 B=65536, N=64, G=128, F=128, K=4, box=10.0, seed=2, mode="binary_le", train=True),
+    "cfg4": dict(desc="cfg4: rollout inference, 16384 parallel 12-robot swarms, per-step GSO rebuild + "
+                      "2-layer graph filter 128->128->128, K=3", B=16384, N=12, G=128, F=128, K=3, box=6.0,
+                 seed=3, mode="binary_le", train=False, layers=2),
+}
+RADIUS = 2.0
+SLOPE = 0.01
+
+
+def bytes_per_graph(w):
+    """algorithmic HBM bytes per graph: positions + x + y (+ dY, dX, activation mask)."""
+    N, G, F = w["N"], w["G"], w["F"]
+    fwd = 8 * N + 4 * G * N + 4 * F * N
+    if not w["train"]:
+        return dict(fwd=fwd, bwd=0, total=fwd)
+    bwd = 8 * N + 4 * G * N + 4 * F * N + 4 * G * N + 4 * F * N   # pos, x, dY, dX, y (activation mask)
+    return dict(fwd=fwd, bwd=bwd, total=fwd + bwd)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the measured section (profiling guide)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["no samples"])
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                    samples=len(sm), reasons=sorted(reasons))
+
+
+# ----------------------------------------------------------------------------- inputs
+def make_positions(B, N, box, seed):
+    rng = np.random.default_rng(seed)
+    return (rng.random((B, N, 2)) * box).astype(np.float32)
+
+
+def make_taps(G, F, K, seed):
+    rng = np.random.default_rng(seed)
+    s = 1.0 / np.sqrt(G * K)   # reset_parameters law, graphML.py:2442-2447
+    return (rng.uniform(-s, s, (F, 1, K, G)).astype(np.float32), rng.uniform(-s, s, (F,)).astype(np.float32))
+
+
+# ----------------------------------------------------------------------------- our arm
+class HotPath:
+    """ring of resident batches + direct C-ABI calls (no autograd) for the device-timed loop"""
+
+    def __init__(self, w, dev, ring):
+        import torch
+        import gnnfc
+        self.torch, self.C, self.w, self.dev = torch, gnnfc._cabi, w, dev
+        C = self.C
+        B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        self.ring = ring
+        gen = torch.Generator(device=dev).manual_seed(w["seed"])
+        self.pos = [torch.from_numpy(make_positions(B, N, w["box"], w["seed"] + 17 * i)).to(dev) for i in range(ring)]
+        self.x = [torch.randn(B, G, N, device=dev, generator=gen) for _ in range(ring)]
+        self.y = [torch.empty(B, N, F, device=dev) for _ in range(ring)]
+        h, b = make_taps(G, F, K, w["seed"])
+        self.h, self.b = torch.from_numpy(h).to(dev), torch.from_numpy(b).to(dev)
+        self.mode = C.GSO_MODES[w["mode"]]
+        self.train = w["train"]
+        self.layers = w.get("layers", 1)
+        nbf = C.lib.gfc_filter_workspace_bytes(B, N, G, F, K, 1, 0)
+        self.wsf = torch.empty(max(nbf, 256), dtype=torch.uint8, device=dev); self.nbf = nbf
+        if self.train:
+            self.dY = [torch.randn(B, N, F, device=dev, generator=gen) for _ in range(ring)]
+            self.dX = [torch.empty(B, G, N, device=dev) for _ in range(ring)]
+            self.grads = torch.zeros(F * K * G + F, device=dev)       # flat bucket [dH | db]
+            self.dH, self.db = self.grads[:F * K * G], self.grads[F * K * G:]
+            nbb = C.lib.gfc_filter_workspace_bytes(B, N, G, F, K, 1, 1)
+            self.wsb = torch.empty(max(nbb, 256), dtype=torch.uint8, device=dev); self.nbb = nbb
+        if self.layers == 2:
+            self.h2, self.b2 = self.h.clone(), self.b.clone()
+            self.y2 = [torch.empty(B, N, F, device=dev) for _ in range(ring)]
+            self.xt = torch.empty(B, F, N, device=dev)
+        self.launches_per_step = 0
+
+    def stream(self):
+        return self.C.ct.c_void_p(self.torch.cuda.current_stream().cuda_stream)
+
+    def fwd(self, i, st):
+        C, w = self.C, self.w
+        B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        C.check(C.lib.gfc_filter_fwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
+                                         C.ptr(self.b), C.ptr(self.y[i]), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
+                                         C.PREC_FP32_3XTF32, C.ptr(self.wsf), self.nbf, st), "gfc_filter_fwd_pos")
+        n = C.last_launch_count()
+        if self.layers == 2:
+            # layer 2 consumes layer 1's node-major output; the reference permutes it back to
+            # [B,F,N] (suhaas_model.py:186) before the next GraphFilterBatch
+            self.xt.copy_(self.y[i].permute(0, 2, 1))
+            C.check(C.lib.gfc_filter_fwd_pos(C.ptr(self.xt), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h2),
+                                             C.ptr(self.b2), C.ptr(self.y2[i]), B, N, G, F, K, C.ACT_LEAKY_RELU,
+                                             SLOPE, C.PREC_FP32_3XTF32, C.ptr(self.wsf), self.nbf, st),
+                    "gfc_filter_fwd_pos")
+            n += C.last_launch_count()
+        return n
+
+    def bwd(self, i, st):
+        C, w = self.C, self.w
+        B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        C.check(C.lib.gfc_filter_bwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
+                                         C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.dH),
+                                         C.ptr(self.db), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
+                                         C.PREC_FP32_3XTF32, C.ptr(self.wsb), self.nbb, st), "gfc_filter_bwd_pos")
+        return C.last_launch_count()
+
+    def step(self, i):
+        st = self.stream()
+        n = self.fwd(i, st)
+        if self.train:
+            n += self.bwd(i, st)
+        self.launches_per_step = n
+        return n
+
+
+def ring_size(w):
+    per = w["B"] * bytes_per_graph(w)["total"]
+    if per >= 2 * L2_BYTES:
+        return 2 if per < 8e9 else 1
+    return int(min(64, max(2, -(-2 * L2_BYTES // per))))
+
+
+def timed_steps(torch, hp, steps, warmup, world, dist, use_graph):
+    """W warm-up + exactly K timed steps; returns ms for the K steps (this rank)."""
+    ring = hp.ring
+    allreduce = world > 1 and hp.train
+
+    def one(i):
+        hp.step(i % ring)
+        if allreduce:
+            dist.all_reduce(hp.grads)
+
+    for s in range(max(warmup, 1)):
+        one(s)
+    torch.cuda.synchronize()
+    graphs = None
+    if use_graph and not allreduce:
+        # capture the whole ring once (ring consecutive steps) + single-step graphs for the remainder
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for s in range(ring):
+                hp.step(s)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        gring = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gring):
+            for s in range(ring):
+                hp.step(s)
+        singles = []
+        for s in range(min(ring, steps % ring)):
+            g1 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                hp.step(s)
+            singles.append(g1)
+        graphs = (gring, singles)
+        gring.replay()
+        torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    if graphs is not None:
+        gring, singles = graphs
+        for _ in range(steps // ring):
+            gring.replay()
+        for g1 in singles:
+            g1.replay()
+    else:
+        for s in range(steps):
+            one(s)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    return e0.elapsed_time(e1)
+
+
+def kernel_alone_ms(torch, hp, which, reps):
+    """average duration of the dominant kernel launched back to back (graph of `ring` launches,
+    rotating batches) — second-stage reductions switched off so only that kernel runs."""
+    C = hp.C
+    ring = hp.ring
+    st_fn = hp.stream
+    if which == "bwd":
+        C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 1), "gfc_set_option")
+    try:
+        call = (lambda i: hp.bwd(i, st_fn())) if which == "bwd" else (lambda i: hp.fwd(i, st_fn()))
+        for i in range(ring):
+            call(i)
+        torch.cuda.synchronize()
+        n_launch = call(0)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(ring):
+                call(i)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (reps * ring), n_launch
+    finally:
+        if which == "bwd":
+            C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 0), "gfc_set_option")
+
+
+def e2e_steps(torch, w, dev, steps, warmup, world, dist):
+    """same metric through the public module API with HOST (pinned) inputs: every step copies
+    that step's positions + x host->device, runs addPositions + forward + loss + backward through
+    the drop-in nn.Module, and reads the loss back to the host."""
+    import gnnfc
+    B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+    nbuf = 4
+    hpos = [torch.from_numpy(make_positions(B, N, w["box"], 1000 + i)).pin_memory() for i in range(nbuf)]
+    hx = [torch.randn(B, G, N).pin_memory() for _ in range(nbuf)]
+    m = gnnfc.GraphFilterBatch(G, F, K, activation="leaky_relu").to(dev)
+    dpos = torch.empty(B, N, 2, device=dev)
+    dx = torch.empty(B, G, N, device=dev)
+    bucket = gnnfc.GradBucket(m.parameters(), average=True) if world > 1 else None
+    layers2 = w.get("layers", 1) == 2
+    m2 = gnnfc.GraphFilterBatch(F, F, K, activation="leaky_relu").to(dev) if layers2 else None
+    loss_host = 0.0
+
+    def one(s):
+        nonlocal loss_host
+        i = s % nbuf
+        dpos.copy_(hpos[i], non_blocking=True)
+        dx.copy_(hx[i], non_blocking=True)
+        m.addPositions(dpos, RADIUS, w["mode"])
+        if w["train"]:
+            xin = dx.detach().requires_grad_(True)
+            m.zero_grad(set_to_none=True)
+            y = m(xin)
+            loss = y.square().mean()
+            loss.backward()
+            if bucket is not None:
+                bucket.sync_grads()
+            loss_host = float(loss.item())
+        else:
+            with torch.no_grad():
+                y = m(dx)
+                if layers2:
+                    m2.addPositions(dpos, RADIUS, w["mode"])
+                    y = m2(y)
+                loss_host = float(y.mean().item())
+
+    for s in range(max(warmup, 1)):
+        one(s)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(steps):
+        one(s)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    h2d = hpos[0].numel() * 4 + hx[0].numel() * 4
+    return ms, h2d, 4, loss_host
+
+
+# ----------------------------------------------------------------------------- reference arm / cpu baseline
+def cpu_reference_step_fn(w, sample_B):
+    """the reference's CPU path for one batch: vectorised GSO builder restatement +
+    op-faithful GraphFilterBatch port (fp64 inside, as graphML.py:2350) + LeakyReLU + autograd backward."""
+    import torch
+    from oracle import gso as ogso
+    from oracle import lsigf
+    N, G, F, K = w["N"], w["G"], w["F"], w["K"]
+    pos = make_positions(sample_B, N, w["box"], w["seed"])
+    h, b = make_taps(G, F, K, w["seed"])
+    ht = torch.from_numpy(h).requires_grad_(True)
+    bt = torch.from_numpy(b.reshape(F, 1)).requires_grad_(True)
+    x = torch.randn(sample_B, G, N)
+    dY = torch.randn(sample_B, F, N, dtype=torch.float64)
+    omode = ogso.MODE_BINARY_LE if w["mode"] == "binary_le" else ogso.MODE_SYM_NORM_LT
+    layers = w.get("layers", 1)
+
+    def step():
+        S, _ = ogso.gso(pos, RADIUS, omode)
+        St = torch.from_numpy(S[:, None])
+        if w["train"]:
+            xt = x.clone().requires_grad_(True)
+            ht.grad = None; bt.grad = None
+            y = lsigf.activation_torch(lsigf.batch_lsigf_torch(ht, St, xt, bt), lsigf.ACT_LEAKY_RELU)
+            y.backward(dY)
+            return float(y[0, 0, 0])
+        with torch.no_grad():
+            y = lsigf.activation_torch(lsigf.batch_lsigf_torch(ht, St, x, bt), lsigf.ACT_LEAKY_RELU)
+            for _ in range(layers - 1):
+                y = lsigf.activation_torch(lsigf.batch_lsigf_torch(ht, St, y, bt), lsigf.ACT_LEAKY_RELU)
+            return float(y[0, 0, 0])
+    return step
+
+
+def cpu_sample_batch(w):
+    """bounded sample: the reference materialises fp64 z = B*K*G*N*8 bytes; keep it <= ~1 GB"""
+    z_bytes = w["K"] * w["G"] * w["N"] * 8
+    return int(max(1, min(w["B"], (1 << 30) // (8 * z_bytes))))
+
+
+def time_cpu(w, steps, warmup, budget_s):
+    import torch
+    sb = cpu_sample_batch(w)
+    best = None
+    ncores = os.cpu_count() or 1
+    for threads in sorted({1, ncores}):
+        torch.set_num_threads(threads)
+        fn = cpu_reference_step_fn(w, sb)
+        for _ in range(max(1, warmup)):
+            fn()
+        t0 = time.perf_counter()
+        done = 0
+        while done < steps:
+            fn(); done += 1
+            if time.perf_counter() - t0 > budget_s:
+                break
+        dt = (time.perf_counter() - t0) / done
+        if best is None or dt < best[0]:
+            best = (dt, threads, done)
+    dt, threads, done = best
+    return dict(value=sb / dt, unit="graphs/s", cores=threads, kind="port",
+                sample="%d graphs/step x %d steps (%s), best of 1 and %d threads; oracle port of "
+                       "graphML.py:2273-2367 + vectorised scene.py:140-154" % (sb, done, w["desc"].split(":")[0], ncores)), dt, sb
+
+
+# ----------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=None)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true", help="launch every step from Python (no CUDA graph)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of the other configs")
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
+    args = ap.parse_args()
+    w = WORKLOADS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        steps = args.steps or 20
+        warmup = args.warmup if args.warmup is not None else 3
+        cb, dt, sb = time_cpu(w, steps, warmup, budget_s=120.0)
+        line = dict(metric=METRIC, value=cb["value"], unit="graphs/s", n_gpus=args.gpus, steps=steps, warmup=warmup,
+                    ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
+                    data="synthetic", impl="reference",
+                    config=dict(workload=w["desc"], B=w["B"], N=w["N"], G=w["G"], F=w["F"], K=w["K"],
+                                sample_graphs_per_step=sb),
+                    cpu_baseline=cb, gpu_launches=0,
+                    e2e=dict(value=cb["value"], unit="graphs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    steps = args.steps or (4000 if w["B"] * bytes_per_graph(w)["total"] < L2_BYTES else 10)
+    warmup = args.warmup if args.warmup is not None else 5
+    warmup = max(warmup, 3)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ring = ring_size(w)
+    hp = HotPath(w, dev, ring)
+    use_graph = not args.no_graph
+    ms = timed_steps(torch, hp, steps, warmup, world, dist, use_graph)
+    launches = hp.launches_per_step * steps
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * w["B"] * steps / (ms_max * 1e-3)
+
+    # roofline of the dominant kernel, timed alone
+    bpg = bytes_per_graph(w)
+    which = "bwd" if w["train"] else "fwd"
+    reps = max(3, int(50e-3 / max(ms_max / steps * 1e-3, 1e-6) / ring))
+    reps = min(reps, 2000)
+    k_ms, k_launch = kernel_alone_ms(torch, hp, which, reps)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = w["B"] * bpg[which]
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("%s:%s" % (args.config, which))
+    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                    kernel="tile_%s_kernel<pos>" % which, kernel_ms=k_ms, algorithmic_bytes_per_launch=alg_bytes,
+                    launches_in_timed_call=k_launch, peak_source=peak_src,
+                    how="CUDA events around a graph of %d back-to-back launches over rotating batches x %d replays" % (ring, reps))
+
+    # end-to-end through the module API with host buffers
+    e2e_n = max(3, min(steps, 200 if w["B"] * bpg["total"] < L2_BYTES else 5))
+    e_ms, h2d, d2h, _ = e2e_steps(torch, w, dev, e2e_n, 3, world, dist)
+    te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = dict(value=world * w["B"] * e2e_n / (float(te.item()) * 1e-3), unit="graphs/s",
+               h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_n,
+               api="gnnfc.GraphFilterBatch.addPositions/forward + loss.backward, pinned host inputs, loss.item()")
+
+    extra = {}
+    if rank == 0 and world == 1 and not args.no_extra:
+        for name in ("cfg3", "cfg4", "cfg1"):
+            if name == args.config:
+                continue
+            try:
+                w2 = WORKLOADS[name]
+                hp2 = HotPath(w2, dev, ring_size(w2))
+                small = w2["B"] * bytes_per_graph(w2)["total"] < L2_BYTES
+                st2 = 400 if small else 4
+                ms2 = timed_steps(torch, hp2, st2, 3, 1, dist, True)
+                wk = "bwd" if w2["train"] else "fwd"
+                k2, _ = kernel_alone_ms(torch, hp2, wk, 20 if small else 2)
+                extra[name] = dict(workload=w2["desc"], value=w2["B"] * st2 / (ms2 * 1e-3), unit="graphs/s",
+                                   ms_per_step=ms2 / st2, steps=st2,
+                                   dominant_kernel_GBps=w2["B"] * bytes_per_graph(w2)[wk] / (k2 * 1e-3) / 1e9,
+                                   dominant_kernel_ms=k2)
+                del hp2
+                torch.cuda.empty_cache()
+            except Exception as ex:  # side measurement must never break the headline line
+                extra[name] = dict(error=str(ex)[:200])
+
+    clocks = sampler.stop() if rank == 0 else None
+    cpu = None
+    if rank == 0 and world == 1:
+        cpu, _, _ = time_cpu(w, 50, 1, budget_s=args.cpu_budget)
+    if rank == 0:
+        line = dict(metric=METRIC, value=value, unit="graphs/s", n_gpus=world, steps=steps, warmup=warmup,
+                    ms_per_step=ms_max / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="f32", data="synthetic",
+                    config=dict(workload=w["desc"], B_per_gpu=w["B"], N=w["N"], G=w["G"], F=w["F"], K=w["K"],
+                                gso="rebuilt on chip from positions, radius 2, " + w["mode"],
+                                activation="leaky_relu(0.01) fused", precision="3xTF32 tap contraction (fp32-equivalent)",
+                                upstream_gradient="resident synthetic dY",
+                                l2="inputs rotate through a ring of %d distinct batches = %.0f MB (> 126 MB L2)"
+                                   % (ring, ring * w["B"] * bpg["total"] / 1e6),
+                                launch="CUDA graph replay" if (use_graph and not (world > 1 and w["train"])) else "python loop",
+                                collective="none" if world == 1 else "NCCL all-reduce of the flat [dH|db] bucket every step"),
+                    roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, extra=extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

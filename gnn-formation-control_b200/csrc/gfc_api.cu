@@ -9,6 +9,7 @@ namespace gfc {
 
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
+static int g_skip_grad_reduce = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -213,6 +214,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       GFC_CUDA_TRY(cudaMemsetAsync(a.dHp, 0, (size_t)p.nparts * nH * sizeof(float), st));
     rc = launch_tile_bwd(a, gs.kind, st);
     if (rc) return rc;
+    if (g_skip_grad_reduce) return GFC_OK;  // profiling aid, see gfc_set_option
     if (dH) {
       rc = launch_reduce_parts(a.dHp, p.nparts, (int)nH, dH, st);
       if (rc) return rc;
@@ -287,6 +289,11 @@ using namespace gfc;
 extern "C" int gfc_version(void) { return GFC_VERSION; }
 extern "C" const char* gfc_last_error(void) { return g_err; }
 extern "C" int gfc_last_launch_count(void) { return g_launches; }
+extern "C" int gfc_set_option(int key, int value) {
+  if (key == GFC_OPT_SKIP_GRAD_REDUCE) { g_skip_grad_reduce = value ? 1 : 0; return GFC_OK; }
+  set_error("gfc_set_option: unknown key %d", key);
+  return GFC_ERR_BAD_ARG;
+}
 
 extern "C" int gfc_device_info(int* sm_count, int* cc_major, int* cc_minor, int* smem_optin_bytes) {
   DeviceInfo di;

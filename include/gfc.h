@@ -161,6 +161,11 @@ int gfc_filter_path(int B, int N, int G, int F, int K, int E, int backward);
 /* Tile plan of path A for a shape: out[12] = {ok, graphs_per_tile, rows, rows_padded,
  * ntiles, grid, smem_bytes, taps_in_smem, dH_in_registers, nb_dh, nparts, ldz}.  */
 int gfc_tile_plan_info(int B, int N, int G, int F, int K, int backward, int from_positions, int* out);
+/* Process-wide options.  GFC_OPT_SKIP_GRAD_REDUCE = 1 makes gfc_filter_bwd* leave the
+ * per-CTA dH / db partials unreduced (dH / db are then NOT written): a profiling aid that
+ * lets bench.py time the dominant backward kernel alone, back to back.  Default 0.      */
+enum { GFC_OPT_SKIP_GRAD_REDUCE = 1 };
+int gfc_set_option(int key, int value);
 /* number of kernel launches the last call on this thread enqueued */
 int gfc_last_launch_count(void);
 
