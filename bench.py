@@ -40,6 +40,8 @@ WORKLOADS = {
     "cfg2": dict(desc="cfg2: 8-robot formation policy, K=3, F=32->32, synthetic random-geometric graphs, "
                       "batch 4096 graphs", B=4096, N=8, G=32, F=32, K=3, box=5.0, seed=1,
                  mode="binary_le", train=True),
+    "cfg2_x64": dict(desc="cfg2 shapes, 64 batches of 4096 graphs per launch (steady-state rate of the same kernels)",
+                     B=262144, N=8, G=32, F=32, K=3, box=5.0, seed=1, mode="binary_le", train=True),
     "cfg3": dict(desc="cfg3: 64-agent synthetic swarm, K=4, F=128->128, batch 65536 graphs",
                  B=65536, N=64, G=128, F=128, K=4, box=10.0, seed=2, mode="binary_le", train=True),
     "cfg4": dict(desc="cfg4: rollout inference, 16384 parallel 12-robot swarms, per-step GSO rebuild + "
@@ -510,7 +512,7 @@ def main():
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        for name in ("cfg3", "cfg4", "cfg1"):
+        for name in ("cfg2_x64", "cfg3", "cfg4", "cfg1"):
             if name == args.config:
                 continue
             try:

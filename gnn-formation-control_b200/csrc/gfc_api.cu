@@ -4,6 +4,7 @@
 #include "gfc_tile.cuh"
 #include "gfc_generic.cuh"
 #include <string.h>
+#include <math.h>
 
 namespace gfc {
 
@@ -43,6 +44,17 @@ int get_device_info(DeviceInfo* out) {
 int gso_mode_threshold(int mode, double radius, double* thr, bool* norm);  // gfc_gso.cu
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// fp32 screening band around the fp64 threshold: the fp32 squared distance differs from the
+// fp64 one by < 2^-22 relative, the band is 4e-6 wide on each side; inside it the kernels
+// fall back to the exact fp64 rule.
+static void set_thresholds(TileArgs& a, double thr, bool norm) {
+  a.thr = thr;
+  a.norm = norm ? 1 : 0;
+  if (!(thr >= 0)) { a.thr_lo = -1.f; a.thr_hi = -1.f; return; }
+  a.thr_lo = nextafterf((float)(thr * (1.0 - 4e-6)), -INFINITY);
+  a.thr_hi = nextafterf((float)(thr * (1.0 + 4e-6)), INFINITY);
+}
 
 struct GsoSrc {
   int kind;  // GSRC_DENSE / GSRC_POS
@@ -126,7 +138,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = need_ws(fn, ws, ws_bytes, p.ws_bytes);
     if (rc) return rc;
     TileArgs a{};
-    a.S = gs.S; a.pos = gs.pos; a.thr = thr; a.norm = norm ? 1 : 0;
+    a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
     a.x = x; a.h = h; a.bias = bias; a.y = y;
     a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
     a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
@@ -196,7 +208,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     if (rc) return rc;
     char* wsb = static_cast<char*>(ws);
     TileArgs a{};
-    a.S = gs.S; a.pos = gs.pos; a.thr = thr; a.norm = norm ? 1 : 0;
+    a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
     a.x = x; a.h = h; a.yout = yout; a.dY = dY; a.dX = dX;
     a.dHp = dH ? reinterpret_cast<float*>(wsb + p.ws_dhp) : nullptr;
     a.dbp = db ? reinterpret_cast<float*>(wsb + p.ws_dbp) : nullptr;
@@ -215,15 +227,8 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_tile_bwd(a, gs.kind, st);
     if (rc) return rc;
     if (g_skip_grad_reduce) return GFC_OK;  // profiling aid, see gfc_set_option
-    if (dH) {
-      rc = launch_reduce_parts(a.dHp, p.nparts, (int)nH, dH, st);
-      if (rc) return rc;
-    }
-    if (db) {
-      rc = launch_reduce_parts(a.dbp, p.grid, F, db, st);
-      if (rc) return rc;
-    }
-    return GFC_OK;
+    return launch_reduce_parts(dH ? a.dHp : nullptr, p.nparts, (int)nH, dH,
+                               db ? a.dbp : nullptr, p.grid, F, db, st);
   }
   // path B
   GenericPlan g;
@@ -250,7 +255,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     float* part = reinterpret_cast<float*>(wsb + g.ws_dbp);
     rc = launch_colsum(Dw, rows, F, g.rows_per_chunk, g.nchunks, part, st);
     if (rc) return rc;
-    rc = launch_reduce_parts(part, g.nchunks, F, db, st);
+    rc = launch_reduce_parts(part, g.nchunks, F, db, nullptr, 0, 0, nullptr, st);
     if (rc) return rc;
   }
   if (dH) {
@@ -265,7 +270,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_sgemm(Dw, 1, F, Zw, C, 1, part, C, (long long)nH, F, (int)C, rows, g.nsplit, nullptr,
                       GFC_ACT_NONE, 0.f, st);
     if (rc) return rc;
-    rc = launch_reduce_parts(part, g.nsplit, (int)nH, dH, st);
+    rc = launch_reduce_parts(part, g.nsplit, (int)nH, dH, nullptr, 0, 0, nullptr, st);
     if (rc) return rc;
   }
   if (dX) {
@@ -447,7 +452,7 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
     float* part = reinterpret_cast<float*>(wsb + g.ws_dbp);
     rc = launch_colsum(Dw, rows, F, g.rows_per_chunk, g.nchunks, part, st);
     if (rc) return rc;
-    rc = launch_reduce_parts(part, g.nchunks, F, db, st);
+    rc = launch_reduce_parts(part, g.nchunks, F, db, nullptr, 0, 0, nullptr, st);
     if (rc) return rc;
   }
   if (dH) {
@@ -461,7 +466,7 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
     rc = launch_sgemm(Dw, 1, F, Zw, C, 1, part, C, (long long)nH, F, (int)C, rows, g.nsplit, nullptr,
                       GFC_ACT_NONE, 0.f, st);
     if (rc) return rc;
-    rc = launch_reduce_parts(part, g.nsplit, (int)nH, dH, st);
+    rc = launch_reduce_parts(part, g.nsplit, (int)nH, dH, nullptr, 0, 0, nullptr, st);
     if (rc) return rc;
   }
   if (dX) {

@@ -60,18 +60,20 @@ static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; 
 // ---- device helpers ----------------------------------------------------------
 #ifdef __CUDACC__
 
+// fp32 -> tf32 by "round half ulp, truncate": add half a tf32 ulp to the bit pattern and clear
+// the 13 low mantissa bits.  Two integer-pipe instructions; cvt.rna.tf32.f32 runs on the
+// quarter-rate conversion pipe and was the top stall of every MMA phase (profiles/r1).
 __device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
+  return (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
 }
 
-// x = hi + lo with hi the tf32 rounding of x; lo is rounded to tf32 as well so
-// that the three-term product hi*hi + hi*lo + lo*hi carries ~2^-21 relative
-// error per term (the "3xTF32" scheme).
+// x = hi + lo with hi the tf32 rounding of x; lo = x - hi is exact in fp32 and carries <= 13
+// significant bits, of which the tensor core keeps the top 11 (it ignores the low 13 mantissa
+// bits of a tf32 operand).  hi*hi + hi*lo + lo*hi then carries ~2^-21 relative error per term
+// (the "3xTF32" scheme).
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // D(16x8) += A(16x8, row) * B(8x8, col); fragment layout per PTX ISA:

@@ -1,59 +1,8 @@
-// gfc_tile.cu — kernels (b) and (c): fused K-hop graph filter forward / backward
-// for batches of small agent graphs (path A).
-//
-// What the reference does with ~8 ATen launches forward and ~20 backward
-// (utils/graphUtils/graphML.py:2342-2366 + autograd, all in fp64) is done here
-// in ONE persistent kernel per direction:
-//   * a tile = `gpc` whole graphs = rows r = (graph j, node n) of a row-packed
-//     matrix Z[r][k*G+g] kept in shared memory (z_k never touches HBM);
-//   * the GSO tile comes either from dense S or is rebuilt from positions on
-//     chip (fp64 compare, bit-identical to scene.py:140-154 /
-//     multirobotsim_dcenlocal.py:306-315);
-//   * the K-1 diffusion hops z_k = z_{k-1} S (graphML.py:2349-2352) run on the
-//     FP32 pipes straight out of shared memory, skipping zero weights;
-//   * the tap contraction y = Z H^T (graphML.py:2361-2362) runs on the tensor
-//     cores as a 3xTF32 split product (fp32-equivalent accuracy) with the taps
-//     pre-split and pre-swizzled into MMA B-fragment order;
-//   * bias + activation are fused in the epilogue; y is written node-major
-//     [B,N,F], which is the memory layout the reference returns.
-// Backward recomputes Z, then dH += D^T Z, U = D H, Horner acc = acc S^T + U_k,
-// dX = acc, db = colsum(D), with per-CTA partials reduced deterministically.
-#include "gfc_tile.cuh"
+// gfc_tile.cu — host side of path A: tile plan, variant dispatch, tap packing and the
+// deterministic second-stage gradient reduction.  Device code: gfc_tile_kernels.cuh.
+#include "gfc_tile_kernels.cuh"
 
 namespace gfc {
-
-struct __align__(16) F4 { float x, y, z, w; };
-
-// ---------------------------------------------------------------------------
-// tap packing: B-fragment order, hi/lo split.
-//   forward  (for_bwd=0): Bm[c][f] = h[f*KG+c], k-steps over c, n-tiles over f
-//   backward (for_bwd=1): Bm[f][c] = h[f*KG+c], k-steps over f, n-tiles over c
-// element p = (s*NT + nt)*32 + lane  ->  {hi(b0), hi(b1), lo(b0), lo(b1)}
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float4 pack_one(const float* __restrict__ h, int F, int KG,
-                                           int for_bwd, int p) {
-  const int lane = p & 31, q = p >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  float b0, b1;
-  if (!for_bwd) {
-    const int NT = F >> 3;
-    const int nt = q % NT, s = q / NT;
-    const float* src = h + (size_t)(nt * 8 + g) * KG + s * 8 + t;
-    b0 = src[0];
-    b1 = src[4];
-  } else {
-    const int NT = KG >> 3;
-    const int nt = q % NT, s = q / NT;
-    const float* src = h + (size_t)(s * 8 + t) * KG + nt * 8 + g;
-    b0 = src[0];
-    b1 = src[(size_t)4 * KG];
-  }
-  uint32_t h0, l0, h1, l1;
-  split_tf32(b0, h0, l0);
-  split_tf32(b1, h1, l1);
-  return make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(l0),
-                     __uint_as_float(l1));
-}
 
 __global__ void __launch_bounds__(256)
 pack_taps_kernel(const float* __restrict__ h, int F, int KG, int for_bwd, float4* __restrict__ out) {
@@ -62,500 +11,53 @@ pack_taps_kernel(const float* __restrict__ h, int F, int KG, int for_bwd, float4
     out[p] = pack_one(h, F, KG, for_bwd, p);
 }
 
-// out[i] = sum_p parts[p][i], fixed order => deterministic.
+// out[i] = sum_p parts[p][i] in a fixed order (deterministic).  A CTA reduces 32 outputs:
+// 8 partial-classes x 32 lanes, then a fixed-order combine through shared memory.  Two
+// independent segments (dH and db) share one launch.
 __global__ void __launch_bounds__(256)
-reduce_parts_kernel(const float* __restrict__ parts, int nparts, int n, float* __restrict__ out) {
-  __shared__ float red[4][64];
-  const int lane_i = threadIdx.x & 63, pg = threadIdx.x >> 6;
-  const int i = blockIdx.x * 64 + lane_i;
+reduce_parts_kernel(const float* __restrict__ pa, int npa, int na, float* __restrict__ oa, int blocks_a,
+                    const float* __restrict__ pb, int npb, int nb, float* __restrict__ ob) {
+  __shared__ float red[8][32];
+  const float* parts; int nparts, n; float* out; int blk;
+  if ((int)blockIdx.x < blocks_a) { parts = pa; nparts = npa; n = na; out = oa; blk = blockIdx.x; }
+  else { parts = pb; nparts = npb; n = nb; out = ob; blk = blockIdx.x - blocks_a; }
+  const int lane = threadIdx.x & 31, pg = threadIdx.x >> 5;
+  const int i = blk * 32 + lane;
   float s = 0.f;
   if (i < n) {
     int p = pg;
-    for (; p + 12 < nparts; p += 16) {
-      float v0 = parts[(size_t)p * n + i], v1 = parts[(size_t)(p + 4) * n + i];
-      float v2 = parts[(size_t)(p + 8) * n + i], v3 = parts[(size_t)(p + 12) * n + i];
-      s += v0; s += v1; s += v2; s += v3;
+    for (; p + 56 < nparts; p += 64) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = parts[(size_t)(p + 8 * u) * n + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
     }
-    for (; p < nparts; p += 4) s += parts[(size_t)p * n + i];
+    for (; p < nparts; p += 8) s += parts[(size_t)p * n + i];
   }
-  red[pg][lane_i] = s;
+  red[pg][lane] = s;
   __syncthreads();
-  if (pg == 0 && i < n) out[i] = (red[0][lane_i] + red[1][lane_i]) + (red[2][lane_i] + red[3][lane_i]);
-}
-
-// ---------------------------------------------------------------------------
-// tile loaders
-// ---------------------------------------------------------------------------
-// x[b0 .. b0+gcount) [G][N]  ->  Z[(j*N+n)*ldz + g]
-__device__ __forceinline__ void load_x_tile(float* __restrict__ Zs, const float* __restrict__ x,
-                                            int b0, int gcount, int N, int G, int ldz, int vec_ok) {
-  const int tid = threadIdx.x;
-  const int GN = G * N;
-  const int total = gcount * GN;
-  const float* src = x + (size_t)b0 * GN;
-  if (vec_ok && (N & 3) == 0) {
-    const float4* src4 = reinterpret_cast<const float4*>(src);
-    for (int i4 = tid; i4 < (total >> 2); i4 += kTileThreads) {
-      const float4 v = __ldg(src4 + i4);
-      const int i = i4 << 2;
-      const int j = i / GN, rem = i - j * GN;
-      const int g = rem / N, n = rem - g * N;
-      float* dst = Zs + (size_t)(j * N + n) * ldz + g;
-      dst[0] = v.x;
-      dst[ldz] = v.y;
-      dst[2 * ldz] = v.z;
-      dst[3 * ldz] = v.w;
-    }
-  } else {
-    for (int i = tid; i < total; i += kTileThreads) {
-      const int j = i / GN, rem = i - j * GN;
-      const int g = rem / N, n = rem - g * N;
-      Zs[(size_t)(j * N + n) * ldz + g] = __ldg(src + i);
-    }
-  }
-}
-
-// GSO tile Ss[j][m][n] from dense S (GSRC_DENSE) or rebuilt from positions.
-template <int GSRC>
-__device__ __forceinline__ void load_gso_tile(float* __restrict__ Ss, float* __restrict__ sp,
-                                              double* __restrict__ isd, const TileArgs& a,
-                                              int b0, int gcount) {
-  const int tid = threadIdx.x;
-  const int N = a.p.N;
-  const int NN = N * N;
-  if (GSRC == GSRC_DENSE) {
-    const int total = gcount * NN;
-    const float* src = a.S + (size_t)b0 * NN;
-    if (a.vec_ok && (NN & 3) == 0) {
-      const float4* src4 = reinterpret_cast<const float4*>(src);
-      float4* dst4 = reinterpret_cast<float4*>(Ss);
-      for (int i = tid; i < (total >> 2); i += kTileThreads) dst4[i] = __ldg(src4 + i);
-    } else {
-      for (int i = tid; i < total; i += kTileThreads) Ss[i] = __ldg(src + i);
-    }
-  } else {
-    const int nn = gcount * N;
-    const float* gp = a.pos + (size_t)b0 * N * 2;
-    for (int i = tid; i < nn * 2; i += kTileThreads) sp[i] = __ldg(gp + i);
-    __syncthreads();
-    if (a.norm) {
-      for (int r = tid; r < nn; r += kTileThreads) {
-        const int j = r / N, i = r - j * N;
-        const float xi = sp[2 * r], yi = sp[2 * r + 1];
-        int deg = 0;
-        for (int m = 0; m < N; ++m) {
-          const int q = j * N + m;
-          deg += (m != i) && (sqdist64(xi, yi, sp[2 * q], sp[2 * q + 1]) <= a.thr);
-        }
-        isd[r] = inv_sqrt_deg(deg);
-      }
-      __syncthreads();
-    }
-    const int total = nn * N;
-    for (int o = tid; o < total; o += kTileThreads) {
-      const int r = o / N, n2 = o - r * N;
-      const int j = r / N, i = r - j * N;
-      const int q = j * N + n2;
-      const bool adj = (i != n2) && (sqdist64(sp[2 * r], sp[2 * r + 1], sp[2 * q], sp[2 * q + 1]) <= a.thr);
-      float v = adj ? 1.f : 0.f;
-      if (a.norm) v = adj ? (float)__dmul_rn(isd[r], isd[q]) : 0.f;
-      Ss[o] = v;
-    }
-  }
-}
-
-// One diffusion hop in shared memory.
-//   TRANSPOSED = false: Z[r][dst] = sum_m S_j[m][n] Z[(j,m)][src]          (z_k = z_{k-1} S)
-//   TRANSPOSED = true : Z[r][dst] += sum_m S_j[n][m] Z[(j,m)][src]         (acc S^T + U_k)
-template <bool TRANSPOSED>
-__device__ __forceinline__ void hop_tile(float* __restrict__ Zs, const float* __restrict__ Ss,
-                                         int rows_used, int N, int G, int ldz, int src_col, int dst_col) {
-  const int G4 = G >> 2;
-  const int total = rows_used * G4;
-  for (int idx = threadIdx.x; idx < total; idx += kTileThreads) {
-    const int r = idx / G4, g4 = idx - r * G4;
-    const int j = r / N, n = r - j * N;
-    const float* sw = Ss + (size_t)j * N * N + (TRANSPOSED ? n * N : n);
-    const int sstride = TRANSPOSED ? 1 : N;
-    const float* zin = Zs + (size_t)(j * N) * ldz + src_col + (g4 << 2);
-    float* zout = Zs + (size_t)r * ldz + dst_col + (g4 << 2);
-    float4 acc = TRANSPOSED ? *reinterpret_cast<const float4*>(zout) : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int m = 0; m < N; ++m) {
-      const float w = sw[m * sstride];
-      if (w != 0.f) {
-        const float4 z = *reinterpret_cast<const float4*>(zin + (size_t)m * ldz);
-        acc.x = fmaf(w, z.x, acc.x);
-        acc.y = fmaf(w, z.y, acc.y);
-        acc.z = fmaf(w, z.z, acc.z);
-        acc.w = fmaf(w, z.w, acc.w);
-      }
-    }
-    *reinterpret_cast<float4*>(zout) = acc;
-  }
-}
-
-__device__ __forceinline__ void zero_floats(float* p, int n) {
-  for (int i = threadIdx.x; i < n; i += kTileThreads) p[i] = 0.f;
-}
-
-// three-term (or single-pass) tensor-core product accumulate
-__device__ __forceinline__ void mma3(float (&acc)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4],
-                                     uint32_t bh0, uint32_t bh1, uint32_t bl0, uint32_t bl1, bool single) {
-  if (!single) {
-    mma_tf32(acc, alo, bh0, bh1);
-    mma_tf32(acc, ahi, bl0, bl1);
-  }
-  mma_tf32(acc, ahi, bh0, bh1);
-}
-
-// ---------------------------------------------------------------------------
-// forward
-// ---------------------------------------------------------------------------
-template <int GSRC, bool HSMEM>
-__global__ void __launch_bounds__(kTileThreads)
-tile_fwd_kernel(const TileArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const TilePlan& p = a.p;
-  float* Zs = smem + p.off_z;
-  float* Ss = smem + p.off_s;
-  float* sp = smem + p.off_pos;
-  double* isd = reinterpret_cast<double*>(smem + p.off_isd);
-  float4* Hs = reinterpret_cast<float4*>(smem + p.off_h);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int N = p.N, G = p.G, F = p.F, K = p.K, KG = p.KG, ldz = p.ldz;
-  const bool single = a.single_pass != 0;
-
-  zero_floats(Zs, p.rpad * ldz);
-  if (HSMEM) {
-    const int total = (KG * F) >> 1;
-    for (int q = tid; q < total; q += kTileThreads) Hs[q] = pack_one(a.h, F, KG, 0, q);
-  }
-  const float4* HP = HSMEM ? Hs : a.hpack;
-  __syncthreads();
-
-  const int MT = p.rpad >> 4, NT = F >> 3, KS = KG >> 3;
-  const int ngroups = (NT + kNB - 1) / kNB;
-  const int ntasks = MT * ngroups;
-
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    const int b0 = tile * p.gpc;
-    const int gcount = min(p.gpc, p.B - b0);
-    const int rows_used = gcount * N;
-    if (gcount < p.gpc) {  // tail tile: clear the rows no graph maps to
-      for (int i = tid; i < (p.rows - rows_used) * ldz; i += kTileThreads) Zs[(size_t)rows_used * ldz + i] = 0.f;
-    }
-    load_x_tile(Zs, a.x, b0, gcount, N, G, ldz, a.vec_ok);
-    load_gso_tile<GSRC>(Ss, sp, isd, a, b0, gcount);
-    __syncthreads();
-    for (int k = 1; k < K; ++k) {
-      hop_tile<false>(Zs, Ss, rows_used, N, G, ldz, (k - 1) * G, k * G);
-      __syncthreads();
-    }
-    // ---- tap contraction on tensor cores: Y[rpad x F] = Z[rpad x KG] * Hm[KG x F]
-    for (int task = warp; task < ntasks; task += kTileWarps) {
-      const int mt = task / ngroups, ng = task - mt * ngroups;
-      const int nt0 = ng * kNB;
-      const int nbc = min(kNB, NT - nt0);
-      float acc[kNB][4];
+  if (pg == 0 && i < n) {
+    float r = red[0][lane];
 #pragma unroll
-      for (int i = 0; i < kNB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-      const float* za = Zs + (size_t)(mt * 16 + g) * ldz + t;
-      const float4* hp = HP + (size_t)nt0 * 32 + lane;
-#pragma unroll 2
-      for (int s = 0; s < KS; ++s) {
-        uint32_t ahi[4], alo[4];
-        split_tf32(za[s * 8], ahi[0], alo[0]);
-        split_tf32(za[8 * ldz + s * 8], ahi[1], alo[1]);
-        split_tf32(za[s * 8 + 4], ahi[2], alo[2]);
-        split_tf32(za[8 * ldz + s * 8 + 4], ahi[3], alo[3]);
-#pragma unroll
-        for (int nb = 0; nb < kNB; ++nb) {
-          if (nb < nbc) {
-            const float4 b = hp[((size_t)s * NT + nb) * 32];
-            mma3(acc[nb], ahi, alo, __float_as_uint(b.x), __float_as_uint(b.y),
-                 __float_as_uint(b.z), __float_as_uint(b.w), single);
-          }
-        }
-      }
-      // ---- epilogue: bias + activation, node-major store y[(b0*N + r)*F + f]
-      const int r0 = mt * 16 + g, r1 = r0 + 8;
-      float* yrow0 = a.y + ((size_t)b0 * N + r0) * F;
-      float* yrow1 = a.y + ((size_t)b0 * N + r1) * F;
-#pragma unroll
-      for (int nb = 0; nb < kNB; ++nb) {
-        if (nb < nbc) {
-          const int f0 = (nt0 + nb) * 8 + 2 * t;
-          const float bb0 = a.bias ? __ldg(a.bias + f0) : 0.f;
-          const float bb1 = a.bias ? __ldg(a.bias + f0 + 1) : 0.f;
-          if (r0 < rows_used) {
-            float2 v = make_float2(apply_act(acc[nb][0] + bb0, a.act, a.slope),
-                                   apply_act(acc[nb][1] + bb1, a.act, a.slope));
-            *reinterpret_cast<float2*>(yrow0 + f0) = v;
-          }
-          if (r1 < rows_used) {
-            float2 v = make_float2(apply_act(acc[nb][2] + bb0, a.act, a.slope),
-                                   apply_act(acc[nb][3] + bb1, a.act, a.slope));
-            *reinterpret_cast<float2*>(yrow1 + f0) = v;
-          }
-        }
-      }
-    }
-    __syncthreads();  // Z / S are overwritten by the next tile
+    for (int k = 1; k < 8; ++k) r += red[k][lane];
+    out[i] = r;
   }
 }
 
 // ---------------------------------------------------------------------------
-// backward
-// ---------------------------------------------------------------------------
-template <int GSRC, bool HSMEM, bool ACC>
-__global__ void __launch_bounds__(kTileThreads)
-tile_bwd_kernel(const TileArgs a) {
-  extern __shared__ __align__(16) float smem[];
-  const TilePlan& p = a.p;
-  float* Zs = smem + p.off_z;
-  float* Ss = smem + p.off_s;
-  float* Ds = smem + p.off_d;
-  float* sp = smem + p.off_pos;
-  double* isd = reinterpret_cast<double*>(smem + p.off_isd);
-  float4* Hs = reinterpret_cast<float4*>(smem + p.off_h);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int N = p.N, G = p.G, F = p.F, K = p.K, KG = p.KG, ldz = p.ldz, ldd = p.ldd;
-  const bool single = a.single_pass != 0;
-  const bool want_dx = a.dX != nullptr, want_dh = a.dHp != nullptr, want_db = a.dbp != nullptr;
-
-  zero_floats(Zs, p.rpad * ldz);
-  zero_floats(Ds, p.rpad * ldd);
-  if (HSMEM && want_dx) {
-    const int total = (KG * F) >> 1;
-    for (int q = tid; q < total; q += kTileThreads) Hs[q] = pack_one(a.h, F, KG, 1, q);
-  }
-  const float4* HP = HSMEM ? Hs : a.hpack;
-  __syncthreads();
-
-  // dH task geometry: M = F, N = KG, Kdim = rows
-  const int MTd = F >> 4, NTd = KG >> 3, KSd = p.rpad >> 3;
-  const int nbd = p.nb_dh;
-  const int ngroups_d = (NTd + nbd - 1) / nbd;
-  const int ntasks_d = MTd * ngroups_d;
-  // U task geometry: M = rows, N = KG, Kdim = F
-  const int MTu = p.rpad >> 4, NTu = KG >> 3, KSu = F >> 3;
-  const int ngroups_u = (NTu + kNB - 1) / kNB;
-  const int ntasks_u = MTu * ngroups_u;
-
-  float accH[kNB][4];
-#pragma unroll
-  for (int i = 0; i < kNB; ++i) accH[i][0] = accH[i][1] = accH[i][2] = accH[i][3] = 0.f;
-  float dbacc[4] = {0.f, 0.f, 0.f, 0.f};
-  float* dHpart = want_dh ? a.dHp + (size_t)(ACC ? blockIdx.x : (blockIdx.x % p.nparts)) * F * KG : nullptr;
-
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    const int b0 = tile * p.gpc;
-    const int gcount = min(p.gpc, p.B - b0);
-    const int rows_used = gcount * N;
-    if (gcount < p.gpc) {
-      for (int i = tid; i < (p.rows - rows_used) * ldz; i += kTileThreads) Zs[(size_t)rows_used * ldz + i] = 0.f;
-      for (int i = tid; i < (p.rows - rows_used) * ldd; i += kTileThreads) Ds[(size_t)rows_used * ldd + i] = 0.f;
-    }
-    // ---- loads: D = dY * act'(y), x -> Z_0, GSO tile
-    {
-      const int total = rows_used * F;
-      const float* dsrc = a.dY + (size_t)b0 * N * F;
-      const float* ysrc = (a.act != GFC_ACT_NONE) ? a.yout + (size_t)b0 * N * F : nullptr;
-      if (a.vec_ok) {
-        const float4* d4 = reinterpret_cast<const float4*>(dsrc);
-        const float4* y4 = reinterpret_cast<const float4*>(ysrc);
-        for (int i4 = tid; i4 < (total >> 2); i4 += kTileThreads) {
-          float4 v = __ldg(d4 + i4);
-          if (ysrc) {
-            const float4 yo = __ldg(y4 + i4);
-            v.x = act_grad(v.x, yo.x, a.act, a.slope);
-            v.y = act_grad(v.y, yo.y, a.act, a.slope);
-            v.z = act_grad(v.z, yo.z, a.act, a.slope);
-            v.w = act_grad(v.w, yo.w, a.act, a.slope);
-          }
-          const int i = i4 << 2;
-          const int r = i / F, f = i - r * F;
-          *reinterpret_cast<float4*>(Ds + (size_t)r * ldd + f) = v;
-        }
-      } else {
-        for (int i = tid; i < total; i += kTileThreads) {
-          float v = __ldg(dsrc + i);
-          if (ysrc) v = act_grad(v, __ldg(ysrc + i), a.act, a.slope);
-          const int r = i / F, f = i - r * F;
-          Ds[(size_t)r * ldd + f] = v;
-        }
-      }
-    }
-    if (want_dh) load_x_tile(Zs, a.x, b0, gcount, N, G, ldz, a.vec_ok);
-    load_gso_tile<GSRC>(Ss, sp, isd, a, b0, gcount);
-    __syncthreads();
-
-    // ---- db += column sums of D
-    if (want_db) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int f = tid + i * kTileThreads;
-        if (f < F) {
-          float s = 0.f;
-          for (int r = 0; r < rows_used; ++r) s += Ds[(size_t)r * ldd + f];
-          dbacc[i] += s;
-        }
-      }
-    }
-
-    if (want_dh) {
-      // ---- recompute the diffusion states (graphML.py:2349-2352)
-      for (int k = 1; k < K; ++k) {
-        hop_tile<false>(Zs, Ss, rows_used, N, G, ldz, (k - 1) * G, k * G);
-        __syncthreads();
-      }
-      // ---- dH[f][c] += sum_r D[r][f] Z[r][c]
-      for (int task = warp; task < ntasks_d; task += kTileWarps) {
-        const int mt = task / ngroups_d, ng = task - mt * ngroups_d;
-        const int nt0 = ng * nbd;
-        const int nbc = min(nbd, NTd - nt0);
-        if (!ACC) {
-#pragma unroll
-          for (int i = 0; i < kNB; ++i) accH[i][0] = accH[i][1] = accH[i][2] = accH[i][3] = 0.f;
-        }
-        const float* dcol = Ds + (size_t)t * ldd + mt * 16 + g;
-        const float* zb = Zs + (size_t)t * ldz + nt0 * 8 + g;
-#pragma unroll 2
-        for (int s = 0; s < KSd; ++s) {
-          const float* dc = dcol + (size_t)s * 8 * ldd;
-          uint32_t ahi[4], alo[4];
-          split_tf32(dc[0], ahi[0], alo[0]);
-          split_tf32(dc[8], ahi[1], alo[1]);
-          split_tf32(dc[4 * ldd], ahi[2], alo[2]);
-          split_tf32(dc[4 * ldd + 8], ahi[3], alo[3]);
-          const float* zr = zb + (size_t)s * 8 * ldz;
-#pragma unroll
-          for (int nb = 0; nb < kNB; ++nb) {
-            if (nb < nbc) {
-              uint32_t bh0, bl0, bh1, bl1;
-              split_tf32(zr[nb * 8], bh0, bl0);
-              split_tf32(zr[4 * ldz + nb * 8], bh1, bl1);
-              mma3(accH[nb], ahi, alo, bh0, bh1, bl0, bl1, single);
-            }
-          }
-        }
-        if (!ACC) {
-          float* row0 = dHpart + (size_t)(mt * 16 + g) * KG;
-          float* row1 = row0 + (size_t)8 * KG;
-#pragma unroll
-          for (int nb = 0; nb < kNB; ++nb) {
-            if (nb < nbc) {
-              const int c0 = (nt0 + nb) * 8 + 2 * t;
-              atomicAdd(row0 + c0, accH[nb][0]);
-              atomicAdd(row0 + c0 + 1, accH[nb][1]);
-              atomicAdd(row1 + c0, accH[nb][2]);
-              atomicAdd(row1 + c0 + 1, accH[nb][3]);
-            }
-          }
-        }
-      }
-      __syncthreads();  // all reads of Z done before U overwrites it
-    }
-
-    if (want_dx) {
-      // ---- U[r][c] = sum_f D[r][f] h[f][c]  -> Z
-      for (int task = warp; task < ntasks_u; task += kTileWarps) {
-        const int mt = task / ngroups_u, ng = task - mt * ngroups_u;
-        const int nt0 = ng * kNB;
-        const int nbc = min(kNB, NTu - nt0);
-        float acc[kNB][4];
-#pragma unroll
-        for (int i = 0; i < kNB; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-        const float* da = Ds + (size_t)(mt * 16 + g) * ldd + t;
-        const float4* hp = HP + (size_t)nt0 * 32 + lane;
-#pragma unroll 2
-        for (int s = 0; s < KSu; ++s) {
-          uint32_t ahi[4], alo[4];
-          split_tf32(da[s * 8], ahi[0], alo[0]);
-          split_tf32(da[8 * ldd + s * 8], ahi[1], alo[1]);
-          split_tf32(da[s * 8 + 4], ahi[2], alo[2]);
-          split_tf32(da[8 * ldd + s * 8 + 4], ahi[3], alo[3]);
-#pragma unroll
-          for (int nb = 0; nb < kNB; ++nb) {
-            if (nb < nbc) {
-              const float4 b = hp[((size_t)s * NTu + nb) * 32];
-              mma3(acc[nb], ahi, alo, __float_as_uint(b.x), __float_as_uint(b.y),
-                   __float_as_uint(b.z), __float_as_uint(b.w), single);
-            }
-          }
-        }
-        float* zr0 = Zs + (size_t)(mt * 16 + g) * ldz + nt0 * 8 + 2 * t;
-        float* zr1 = zr0 + (size_t)8 * ldz;
-#pragma unroll
-        for (int nb = 0; nb < kNB; ++nb) {
-          if (nb < nbc) {
-            *reinterpret_cast<float2*>(zr0 + nb * 8) = make_float2(acc[nb][0], acc[nb][1]);
-            *reinterpret_cast<float2*>(zr1 + nb * 8) = make_float2(acc[nb][2], acc[nb][3]);
-          }
-        }
-      }
-      __syncthreads();
-      // ---- Horner: acc = U_{K-1}; acc = acc S^T + U_k  (in place in slot k)
-      for (int k = K - 2; k >= 0; --k) {
-        hop_tile<true>(Zs, Ss, rows_used, N, G, ldz, (k + 1) * G, k * G);
-        __syncthreads();
-      }
-      // ---- dX[b][g][n] = Z[(j,n)][g]
-      {
-        const int GN = G * N;
-        const int total = gcount * GN;
-        float* dst = a.dX + (size_t)b0 * GN;
-        for (int i = tid; i < total; i += kTileThreads) {
-          const int j = i / GN, rem = i - j * GN;
-          const int gg = rem / N, n = rem - gg * N;
-          dst[i] = Zs[(size_t)(j * N + n) * ldz + gg];
-        }
-      }
-    }
-    __syncthreads();
-  }
-
-  if (want_dh && ACC) {
-    // each CTA owns one full partial; warps without a task have nothing to add,
-    // tasks cover the whole [F x KG] range.
-    const int task = warp;
-    if (task < ntasks_d) {
-      const int mt = task / ngroups_d, ng = task - mt * ngroups_d;
-      const int nt0 = ng * nbd;
-      const int nbc = min(nbd, NTd - nt0);
-      float* row0 = dHpart + (size_t)(mt * 16 + g) * KG;
-      float* row1 = row0 + (size_t)8 * KG;
-#pragma unroll
-      for (int nb = 0; nb < kNB; ++nb) {
-        if (nb < nbc) {
-          const int c0 = (nt0 + nb) * 8 + 2 * t;
-          *reinterpret_cast<float2*>(row0 + c0) = make_float2(accH[nb][0], accH[nb][1]);
-          *reinterpret_cast<float2*>(row1 + c0) = make_float2(accH[nb][2], accH[nb][3]);
-        }
-      }
-    }
-  }
-  if (want_db) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = tid + i * kTileThreads;
-      if (f < F) a.dbp[(size_t)blockIdx.x * F + f] = dbacc[i];
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------
-// host side: plan + launch
+// plan
 // ---------------------------------------------------------------------------
 static int tile_smem_floats(TilePlan* p, int gsrc, int with_h) {
   int off = 0;
   p->off_z = off; off += p->rpad * p->ldz;
   p->off_s = off; off += (p->gpc * p->N * p->N + 3) & ~3;
-  p->off_d = off; if (p->backward) off += p->rpad * p->ldd;
+  p->off_d = off; if (p->backward) off += p->rpad * p->ldd + ((p->F + 3) & ~3);
   p->off_pos = off; if (gsrc == GSRC_POS) off += (p->gpc * p->N * 2 + 3) & ~3;
   p->off_isd = off; if (gsrc == GSRC_POS) off += (p->gpc * p->N * 2 + 3) & ~3;  // doubles
+  p->off_nbr = off;
+  p->use_lists = (p->N > 16 && p->N <= 255) ? 1 : 0;
+  if (p->use_lists) off += (((p->rows * p->N + p->rows + 3) >> 2) + 3 & ~3) * (p->backward ? 2 : 1);
   p->off_h = off; if (with_h) off += p->KG * p->F * 2;
   return off;
 }
@@ -566,8 +68,13 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   if (B <= 0 || N <= 0 || G <= 0 || F <= 0 || K <= 0) return 0;
   if ((G & 7) || (F & 7)) return 0;
   if (backward && (F & 15)) return 0;
-  if (F > 4 * kTileThreads) return 0;
   if ((long long)K * G > 8192 || N > 4096) return 0;
+  // kernel variant
+  p->variant = VAR_GENERIC; p->threads = 256; p->nb = 4;
+  if (N == 8 && G == 32 && F == 32 && K == 3) { p->variant = VAR_N8_32_32_3; p->threads = 512; p->nb = 2; }
+  else if (N == 64 && G == 128 && F == 128 && K == 4) p->variant = VAR_N64_128_128_4;
+  else if (G == 128 && F == 128 && K == 3) p->variant = VAR_128_128_3;
+  if (F > p->threads) return 0;
   DeviceInfo di;
   if (get_device_info(&di)) return 0;
   const long long limit_floats = (di.smem_optin - 1024) / 4;
@@ -576,6 +83,13 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   int gpc = 128 / N;
   if (gpc < 1) gpc = 1;
   if (gpc > B) gpc = B;
+  {  // small batches: spread the graphs over the SMs instead of filling 128-row tiles
+    int spread = ceil_div(B, di.sm_count);
+    int gmin = 16 / N;  // keep at least one full MMA m-tile of rows
+    if (gmin < 1) gmin = 1;
+    if (spread < gmin) spread = gmin;
+    if (spread < gpc) gpc = spread;
+  }
   // prefer a footprint that lets two CTAs share an SM, as long as a tile keeps >= 64 rows
   const long long half_floats = limit_floats / 2 - 256;
   int chosen = 0, chosen_h = 0;
@@ -594,17 +108,18 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   p->h_smem = chosen_h;
   p->smem_bytes = (size_t)tile_smem_floats(p, gsrc, chosen_h) * sizeof(float);
   p->ntiles = ceil_div(B, p->gpc);
-  // dH accumulation mode
-  p->nb_dh = kNB; p->acc_regs = 0;
+  // dH accumulation mode: registers when the [F x KG] output fits one task per warp
+  p->nb_dh = p->nb; p->acc_regs = 0;
   if (backward) {
     const int MTd = F >> 4, NTd = p->KG >> 3;
-    for (int nb = 1; nb <= kNB; ++nb) {
-      if (MTd * ceil_div(NTd, nb) <= kTileWarps) { p->nb_dh = nb; p->acc_regs = 1; break; }
+    for (int nb = 1; nb <= p->nb; ++nb) {
+      if (MTd * ceil_div(NTd, nb) <= p->threads / 32) { p->nb_dh = nb; p->acc_regs = 1; break; }
     }
   }
   int per_sm = (int)((size_t)di.smem_optin / (p->smem_bytes + 1024));
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
+  const int cap = p->threads >= 512 ? 2 : 4;
+  if (per_sm > cap) per_sm = cap;
   p->grid = di.sm_count * per_sm;
   if (p->grid > p->ntiles) p->grid = p->ntiles;
   p->nparts = p->acc_regs ? p->grid : (p->grid < 8 ? p->grid : 8);
@@ -627,41 +142,33 @@ int launch_pack_taps(const float* h, int F, int KG, int for_bwd, float4* out, cu
   return GFC_OK;
 }
 
-int launch_reduce_parts(const float* parts, int nparts, int n, float* out, cudaStream_t st) {
-  reduce_parts_kernel<<<ceil_div(n, 64), 256, 0, st>>>(parts, nparts, n, out);
+int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_a,
+                        const float* parts_b, int nparts_b, int n_b, float* out_b, cudaStream_t st) {
+  const int blocks_a = parts_a ? ceil_div(n_a, 32) : 0;
+  const int blocks_b = parts_b ? ceil_div(n_b, 32) : 0;
+  if (blocks_a + blocks_b == 0) return GFC_OK;
+  reduce_parts_kernel<<<blocks_a + blocks_b, 256, 0, st>>>(parts_a, nparts_a, n_a, out_a, blocks_a,
+                                                           parts_b, nparts_b, n_b, out_b);
   GFC_LAUNCH_CHECK("reduce_parts_kernel");
   return GFC_OK;
 }
 
-template <typename Kern>
-static int launch_with_smem(Kern kern, const TileArgs& a, cudaStream_t st, const char* name) {
-  if (a.p.smem_bytes > 48 * 1024)
-    GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.p.smem_bytes));
-  kern<<<a.p.grid, kTileThreads, a.p.smem_bytes, st>>>(a);
-  GFC_LAUNCH_CHECK(name);
-  return GFC_OK;
-}
-
 int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st) {
-  if (gsrc == GSRC_DENSE) {
-    if (a.p.h_smem) return launch_with_smem(tile_fwd_kernel<GSRC_DENSE, true>, a, st, "tile_fwd_kernel<dense,hsmem>");
-    return launch_with_smem(tile_fwd_kernel<GSRC_DENSE, false>, a, st, "tile_fwd_kernel<dense,hglobal>");
+  switch (a.p.variant) {
+    case VAR_N8_32_32_3: return tile_fwd_n8_32_32_3(a, gsrc, st);
+    case VAR_128_128_3: return tile_fwd_128_128_3(a, gsrc, st);
+    case VAR_N64_128_128_4: return tile_fwd_n64_128_128_4(a, gsrc, st);
+    default: return tile_fwd_generic(a, gsrc, st);
   }
-  if (a.p.h_smem) return launch_with_smem(tile_fwd_kernel<GSRC_POS, true>, a, st, "tile_fwd_kernel<pos,hsmem>");
-  return launch_with_smem(tile_fwd_kernel<GSRC_POS, false>, a, st, "tile_fwd_kernel<pos,hglobal>");
 }
 
 int launch_tile_bwd(const TileArgs& a, int gsrc, cudaStream_t st) {
-#define GFC_BWD_CASE(SRC, HS, AC)                                                               \
-  return launch_with_smem(tile_bwd_kernel<SRC, HS, AC>, a, st, "tile_bwd_kernel<" #SRC "," #HS "," #AC ">")
-  if (gsrc == GSRC_DENSE) {
-    if (a.p.h_smem) { if (a.p.acc_regs) GFC_BWD_CASE(GSRC_DENSE, true, true); else GFC_BWD_CASE(GSRC_DENSE, true, false); }
-    else { if (a.p.acc_regs) GFC_BWD_CASE(GSRC_DENSE, false, true); else GFC_BWD_CASE(GSRC_DENSE, false, false); }
-  } else {
-    if (a.p.h_smem) { if (a.p.acc_regs) GFC_BWD_CASE(GSRC_POS, true, true); else GFC_BWD_CASE(GSRC_POS, true, false); }
-    else { if (a.p.acc_regs) GFC_BWD_CASE(GSRC_POS, false, true); else GFC_BWD_CASE(GSRC_POS, false, false); }
+  switch (a.p.variant) {
+    case VAR_N8_32_32_3: return tile_bwd_n8_32_32_3(a, gsrc, st);
+    case VAR_128_128_3: return tile_bwd_128_128_3(a, gsrc, st);
+    case VAR_N64_128_128_4: return tile_bwd_n64_128_128_4(a, gsrc, st);
+    default: return tile_bwd_generic(a, gsrc, st);
   }
-#undef GFC_BWD_CASE
 }
 
 }  // namespace gfc

@@ -4,16 +4,23 @@
 
 namespace gfc {
 
-constexpr int kTileThreads = 256;
-constexpr int kTileWarps = kTileThreads / 32;
-constexpr int kNB = 4;  // n-tiles (of 8 columns) a warp task covers at most
-
 enum { GSRC_DENSE = 0, GSRC_POS = 1 };
+
+// Kernel variants: compile-time shapes for the BASELINE configs, runtime shapes otherwise.
+enum {
+  VAR_GENERIC = 0,     // runtime N,G,F,K; 256 threads, 4 n-tiles per warp task
+  VAR_N8_32_32_3 = 1,  // cfg2: N=8, G=F=32, K=3; 512 threads, 2 n-tiles per warp task
+  VAR_128_128_3 = 2,   // the reference policy's layer (suhaas_model.py:33-42): G=F=128, K=3, any N
+  VAR_N64_128_128_4 = 3  // cfg3
+};
 
 // Host-computed plan: how a [B graphs] x [N nodes] batch is cut into tiles of
 // `gpc` graphs whose K diffusion states live in shared memory.
 struct TilePlan {
   int ok;          // 0 -> shape not covered by path A
+  int variant;
+  int threads;     // CTA size
+  int nb;          // n-tiles (8 columns each) per warp task
   int B, N, G, F, K, KG;
   int backward;
   int gpc;         // graphs per tile
@@ -28,7 +35,8 @@ struct TilePlan {
   int grid;        // persistent CTAs
   int nparts;      // dH partial buffers
   // shared-memory carve-up, float offsets
-  int off_z, off_s, off_d, off_h, off_pos, off_isd;
+  int off_z, off_s, off_d, off_h, off_pos, off_isd, off_nbr;
+  int use_lists;   // compact neighbour lists for the hops (16 < N <= 255)
   size_t smem_bytes;
   // workspace carve-up, byte offsets
   size_t ws_hpack, ws_dhp, ws_dbp, ws_bytes;
@@ -40,7 +48,8 @@ struct TileArgs {
   // graph source
   const float* S;      // [B,N,N] dense (E = 1)
   const float* pos;    // [B,N,2]
-  double thr;          // squared-distance threshold (GSRC_POS)
+  double thr;          // squared-distance threshold (GSRC_POS), fp64 rule
+  float thr_lo, thr_hi;  // fp32 band: s < thr_lo surely inside, s > thr_hi surely outside
   int norm;            // sym-norm weights (GSRC_POS)
   // tensors
   const float* x;      // [B,G,N]
@@ -63,6 +72,19 @@ struct TileArgs {
 int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st);
 int launch_tile_bwd(const TileArgs& a, int gsrc, cudaStream_t st);
 int launch_pack_taps(const float* h, int F, int KG, int for_bwd, float4* out, cudaStream_t st);
-int launch_reduce_parts(const float* parts, int nparts, int n, float* out, cudaStream_t st);
+// out_a[i] = sum_p parts_a[p][i] (i < n_a) and, in the same launch, out_b likewise (n_b may be 0)
+int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_a,
+                        const float* parts_b, int nparts_b, int n_b, float* out_b, cudaStream_t st);
+
+// per-variant launchers (one translation unit each, see gfc_tile_inst_*.cu)
+typedef int (*tile_launch_fn)(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_fwd_generic(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_bwd_generic(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_fwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_bwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_fwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_bwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_fwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_bwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
 
 }  // namespace gfc
