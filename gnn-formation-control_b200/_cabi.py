@@ -17,6 +17,7 @@ GSO_BINARY_LE, GSO_SYM_NORM_LT, GSO_BINARY_LT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
 PREC_FP32_3XTF32, PREC_TF32 = 0, 1
 OPT_SKIP_GRAD_REDUCE = 1
+OPT_DISABLE_TCGEN05 = 2
 
 GSO_MODES = {"binary_le": GSO_BINARY_LE, "sym_norm_lt": GSO_SYM_NORM_LT, "binary_lt": GSO_BINARY_LT}
 ACTIVATIONS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU}
@@ -30,6 +31,7 @@ SIGNATURES = {
     "gfc_last_error": (ct.c_char_p, []),
     "gfc_last_launch_count": (_i, []),
     "gfc_set_option": (_i, [_i, _i]),
+    "gfc_set_debug_clock_buffer": (_i, [_p, _sz]),
     "gfc_device_info": (_i, [ct.POINTER(_i)] * 4),
     "gfc_gso_build": (_i, [_p, _i, _i, _d, _i, _p, _p, _p]),
     "gfc_filter_workspace_bytes": (_sz, [_i] * 7),

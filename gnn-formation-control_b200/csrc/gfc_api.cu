@@ -11,6 +11,7 @@ namespace gfc {
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static int g_skip_grad_reduce = 0;
+static long long* g_dbg_clk = nullptr;  // device buffer [>= grid][16], see gfc_set_debug_clock_buffer
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -143,6 +144,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
     a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
+    a.dbg_clk = g_dbg_clk;
     if (!p.h_smem) {
       float4* hp = reinterpret_cast<float4*>(static_cast<char*>(ws) + p.ws_hpack);
       rc = launch_pack_taps(h, F, p.KG, 0, hp, st);
@@ -216,6 +218,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     a.vec_ok = aligned16(dY) && (!x || aligned16(x)) && (!yout || aligned16(yout)) &&
                (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
+    a.dbg_clk = g_dbg_clk;
     if (!p.h_smem && dX) {
       float4* hp = reinterpret_cast<float4*>(wsb + p.ws_hpack);
       rc = launch_pack_taps(h, F, p.KG, 1, hp, st);
@@ -294,8 +297,13 @@ using namespace gfc;
 extern "C" int gfc_version(void) { return GFC_VERSION; }
 extern "C" const char* gfc_last_error(void) { return g_err; }
 extern "C" int gfc_last_launch_count(void) { return g_launches; }
+extern "C" int gfc_set_debug_clock_buffer(void* device_i64, size_t bytes) {
+  g_dbg_clk = (bytes >= 16 * sizeof(long long) * 1184) ? static_cast<long long*>(device_i64) : nullptr;
+  return (device_i64 && !g_dbg_clk) ? GFC_ERR_BAD_ARG : GFC_OK;
+}
 extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_SKIP_GRAD_REDUCE) { g_skip_grad_reduce = value ? 1 : 0; return GFC_OK; }
+  if (key == GFC_OPT_DISABLE_TCGEN05) { g_disable_tcgen05 = value ? 1 : 0; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
   return GFC_ERR_BAD_ARG;
 }

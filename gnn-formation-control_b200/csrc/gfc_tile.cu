@@ -153,9 +153,13 @@ int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_
   return GFC_OK;
 }
 
+int g_disable_tcgen05 = 0;
+
 int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st) {
   switch (a.p.variant) {
-    case VAR_N8_32_32_3: return tile_fwd_n8_32_32_3(a, gsrc, st);
+    case VAR_N8_32_32_3:
+      if (!g_disable_tcgen05 && a.vec_ok) return tc5_fwd_n8_32_32_3(a, gsrc, st);
+      return tile_fwd_n8_32_32_3(a, gsrc, st);
     case VAR_128_128_3: return tile_fwd_128_128_3(a, gsrc, st);
     case VAR_N64_128_128_4: return tile_fwd_n64_128_128_4(a, gsrc, st);
     default: return tile_fwd_generic(a, gsrc, st);

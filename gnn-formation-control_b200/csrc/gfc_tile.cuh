@@ -66,6 +66,7 @@ struct TileArgs {
   float slope;
   int single_pass;     // GFC_PREC_TF32
   int vec_ok;          // all global bases 16-byte aligned
+  long long* dbg_clk;  // optional [grid][16] phase time stamps (gfc_set_debug_clock_buffer), else null
   TilePlan p;
 };
 
@@ -86,5 +87,8 @@ int tile_fwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_bwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_fwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_bwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
+// tcgen05 / TMEM kernels (gfc_tc5_small.cu)
+int tc5_fwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);
+extern int g_disable_tcgen05;  // gfc_set_option(GFC_OPT_DISABLE_TCGEN05)
 
 }  // namespace gfc

@@ -344,8 +344,19 @@ __device__ __forceinline__ void hops_from_column(float (&z)[CFG::sN > 0 ? CFG::s
 #pragma unroll
     for (int m = 0; m < N; ++m) {
       const float zm = z[m];
+      if ((N & 3) == 0) {  // 128-bit broadcast loads of row m of S_j
 #pragma unroll
-      for (int n = 0; n < N; ++n) zn[n] = fmaf(Sj[m * N + n], zm, zn[n]);
+        for (int q = 0; q < N / 4; ++q) {
+          const float4 sv = *reinterpret_cast<const float4*>(Sj + m * N + 4 * q);
+          zn[4 * q] = fmaf(sv.x, zm, zn[4 * q]);
+          zn[4 * q + 1] = fmaf(sv.y, zm, zn[4 * q + 1]);
+          zn[4 * q + 2] = fmaf(sv.z, zm, zn[4 * q + 2]);
+          zn[4 * q + 3] = fmaf(sv.w, zm, zn[4 * q + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int n = 0; n < N; ++n) zn[n] = fmaf(Sj[m * N + n], zm, zn[n]);
+      }
     }
 #pragma unroll
     for (int n = 0; n < N; ++n) { z[n] = zn[n]; zc[(size_t)n * ldz + k * G] = zn[n]; }
@@ -366,10 +377,22 @@ __device__ __forceinline__ void horner_from_column(float (&acc)[CFG::sN > 0 ? CF
 #pragma unroll
     for (int n = 0; n < N; ++n) an[n] = zc[(size_t)n * ldz + k * G];
 #pragma unroll
-    for (int m = 0; m < N; ++m) {
-      const float am = acc[m];
+    for (int n = 0; n < N; ++n) {   // an[n] += sum_m S[n][m] acc[m], row n of S_j as 128-bit broadcasts
+      float sacc = an[n];
+      if ((N & 3) == 0) {
 #pragma unroll
-      for (int n = 0; n < N; ++n) an[n] = fmaf(Sj[n * N + m], am, an[n]);
+        for (int q = 0; q < N / 4; ++q) {
+          const float4 sv = *reinterpret_cast<const float4*>(Sj + n * N + 4 * q);
+          sacc = fmaf(sv.x, acc[4 * q], sacc);
+          sacc = fmaf(sv.y, acc[4 * q + 1], sacc);
+          sacc = fmaf(sv.z, acc[4 * q + 2], sacc);
+          sacc = fmaf(sv.w, acc[4 * q + 3], sacc);
+        }
+      } else {
+#pragma unroll
+        for (int m = 0; m < N; ++m) sacc = fmaf(Sj[n * N + m], acc[m], sacc);
+      }
+      an[n] = sacc;
     }
 #pragma unroll
     for (int n = 0; n < N; ++n) acc[n] = an[n];
@@ -414,6 +437,22 @@ __device__ __forceinline__ void gso_tile_from_global(float* __restrict__ Ss, dou
   }
 }
 
+// debug: thread 0 stamps the SM clock at phase boundaries of the CTA's first tile
+#define GFC_STAMP(a, slot)                                                                 \
+  do {                                                                                     \
+    if ((a).dbg_clk && threadIdx.x == 0 && (slot) < 16) (a).dbg_clk[(size_t)blockIdx.x * 16 + (slot)] = clock64(); \
+  } while (0)
+
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GFC_STAMP_NS(a, slot)                                                              \
+  do {                                                                                     \
+    if ((a).dbg_clk && threadIdx.x == 0) (a).dbg_clk[(size_t)blockIdx.x * 16 + (slot)] = global_ns(); \
+  } while (0)
+
 template <int THREADS>
 __device__ __forceinline__ void zero_floats(float* p, int n) {
   for (int i = threadIdx.x; i < n; i += THREADS) p[i] = 0.f;
@@ -437,6 +476,8 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kThreads >= 512 ? 2 : 1)
 tile_fwd_kernel(const TileArgs a) {
   extern __shared__ __align__(16) float smem[];
   const TilePlan& p = a.p;
+  GFC_STAMP(a, 7);
+  GFC_STAMP_NS(a, 8);
   GFC_TILE_DIMS(CFG, p);
   constexpr int NB = CFG::kNB;
   float* Zs = smem + p.off_z;
@@ -457,6 +498,7 @@ tile_fwd_kernel(const TileArgs a) {
     for (int q = tid; q < total; q += CFG::kThreads) Hs[q] = pack_one(a.h, F, KG, 0, q);
   }
   const float4* HP = HSMEM ? Hs : a.hpack;
+  GFC_STAMP(a, 0);
 
   const int MT = p.rpad >> 4, NT = F >> 3, KS = KG >> 3;
   const int ngroups = (NT + NB - 1) / NB;
@@ -478,8 +520,10 @@ tile_fwd_kernel(const TileArgs a) {
       if (GSRC == GSRC_POS) gso_tile_from_global<CFG>(Ss, isd, a, b0, gcount);
       else load_gso_tile<CFG, GSRC>(Ss, sp, isd, a, b0, gcount);
       __syncthreads();
+      if (tile == (int)blockIdx.x) GFC_STAMP(a, 1);
       if (has_col) hops_from_column<CFG>(zcol, Zs, Ss + (size_t)j * N * N, j, gcol, ldz);
       __syncthreads();
+      if (tile == (int)blockIdx.x) GFC_STAMP(a, 2);
     } else {
       load_x_tile<CFG>(Zs, a.x, p, b0, gcount, ldz, a.vec_ok);
       load_gso_tile<CFG, GSRC>(Ss, sp, isd, a, b0, gcount);
@@ -544,7 +588,9 @@ tile_fwd_kernel(const TileArgs a) {
       }
     }
     __syncthreads();  // Z / S are overwritten by the next tile
+    if (tile == (int)blockIdx.x) GFC_STAMP(a, 3);
   }
+  GFC_STAMP_NS(a, 9);
 }
 
 // ---------------------------------------------------------------------------
@@ -555,6 +601,8 @@ __global__ void __launch_bounds__(CFG::kThreads, CFG::kThreads >= 512 ? 2 : 1)
 tile_bwd_kernel(const TileArgs a) {
   extern __shared__ __align__(16) float smem[];
   const TilePlan& p = a.p;
+  GFC_STAMP(a, 7);
+  GFC_STAMP_NS(a, 8);
   GFC_TILE_DIMS(CFG, p);
   constexpr int NB = CFG::kNB;
   float* Zs = smem + p.off_z;
@@ -583,6 +631,7 @@ tile_bwd_kernel(const TileArgs a) {
   }
   const float4* HP = HSMEM ? Hs : a.hpack;
   __syncthreads();
+  GFC_STAMP(a, 0);
 
   // dH task geometry: M = F, N = KG, Kdim = rows
   const int MTd = F >> 4, NTd = KG >> 3, KSd = p.rpad >> 3;
@@ -646,6 +695,7 @@ tile_bwd_kernel(const TileArgs a) {
       if (GSRC == GSRC_POS) gso_tile_from_global<CFG>(Ss, isd, a, b0, gcount);
       else load_gso_tile<CFG, GSRC>(Ss, sp, isd, a, b0, gcount);
       __syncthreads();
+      if (tile == (int)blockIdx.x) GFC_STAMP(a, 1);
     } else {
       if (want_dh) load_x_tile<CFG>(Zs, a.x, p, b0, gcount, ldz, a.vec_ok);
       load_gso_tile<CFG, GSRC>(Ss, sp, isd, a, b0, gcount);
@@ -675,6 +725,7 @@ tile_bwd_kernel(const TileArgs a) {
       if constexpr (kFast) {
         if (has_col) hops_from_column<CFG>(zcol, Zs, Ss + (size_t)jcol * N * N, jcol, gcol, ldz);
         __syncthreads();
+        if (tile == (int)blockIdx.x) GFC_STAMP(a, 2);
       } else {
         for (int k = 1; k < K; ++k) {
           if (p.use_lists) hop_tile_lists<CFG, false>(Zs, Ss, lst_c, p, rows_used, ldz, (k - 1) * G, k * G);
@@ -726,6 +777,7 @@ tile_bwd_kernel(const TileArgs a) {
         }
       }
       __syncthreads();  // all reads of Z done before U overwrites it
+      if (tile == (int)blockIdx.x) GFC_STAMP(a, 3);
     }
 
     if (want_dx) {
@@ -766,6 +818,7 @@ tile_bwd_kernel(const TileArgs a) {
         }
       }
       __syncthreads();
+      if (tile == (int)blockIdx.x) GFC_STAMP(a, 4);
       // ---- Horner: acc = U_{K-1}; acc = acc S^T + U_k  (in place in slot k)
       if constexpr (kFast) {
         if (has_col) {   // Horner in registers, dX column stored straight to global
@@ -790,6 +843,7 @@ tile_bwd_kernel(const TileArgs a) {
       }
     }
     __syncthreads();
+    if (tile == (int)blockIdx.x) GFC_STAMP(a, 5);
   }
 
   if (want_dh && ACC) {
@@ -814,6 +868,8 @@ tile_bwd_kernel(const TileArgs a) {
   if (want_db) {
     for (int f = tid; f < F; f += CFG::kThreads) a.dbp[(size_t)blockIdx.x * F + f] = dbs[f];
   }
+  GFC_STAMP(a, 6);
+  GFC_STAMP_NS(a, 9);
 }
 
 // ---------------------------------------------------------------------------

@@ -164,8 +164,14 @@ int gfc_tile_plan_info(int B, int N, int G, int F, int K, int backward, int from
 /* Process-wide options.  GFC_OPT_SKIP_GRAD_REDUCE = 1 makes gfc_filter_bwd* leave the
  * per-CTA dH / db partials unreduced (dH / db are then NOT written): a profiling aid that
  * lets bench.py time the dominant backward kernel alone, back to back.  Default 0.      */
-enum { GFC_OPT_SKIP_GRAD_REDUCE = 1 };
+enum {
+  GFC_OPT_SKIP_GRAD_REDUCE = 1,
+  GFC_OPT_DISABLE_TCGEN05 = 2 /* 1: use the mma.sync tile kernels where a tcgen05 kernel exists (A/B comparison) */
+};
 int gfc_set_option(int key, int value);
+/* Debug aid: a device buffer of >= 1184*16 int64 in which the fused tile kernels stamp the SM
+ * clock at their phase boundaries (first tile of every CTA).  NULL switches it off (default). */
+int gfc_set_debug_clock_buffer(void* device_i64, size_t bytes);
 /* number of kernel launches the last call on this thread enqueued */
 int gfc_last_launch_count(void);
 

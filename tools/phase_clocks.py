@@ -1,0 +1,43 @@
+#!/usr/bin/env python
+"""Phase breakdown of the fused tile kernels (SM clock stamps of every CTA's first tile)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, gnnfc
+from bench import WORKLOADS, HotPath, ring_size
+C = gnnfc._cabi
+name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
+w = WORKLOADS[name]; dev = torch.device("cuda", 0)
+hp = HotPath(w, dev, 2)
+buf = torch.zeros(1184 * 16, dtype=torch.int64, device=dev)
+for which, labels in (("fwd", ["setup", "load+gso", "hops", "mma+store"]),
+                      ("bwd", ["setup", "load+gso", "hops", "dH mma", "U mma", "horner+dX", "final"])):
+    if which == "bwd" and not w["train"]:
+        continue
+    for _ in range(3):
+        hp.step(0)
+    torch.cuda.synchronize()
+    buf.zero_()
+    C.check(C.lib.gfc_set_debug_clock_buffer(C.ptr(buf), buf.numel() * 8), "dbg")
+    st = hp.stream()
+    (hp.fwd if which == "fwd" else hp.bwd)(1, st)
+    torch.cuda.synchronize()
+    C.lib.gfc_set_debug_clock_buffer(None, 0)
+    t = buf.cpu().numpy().reshape(-1, 16)
+    t = t[t[:, 0] != 0]
+    n = len(labels)
+    d = np.diff(t[:, :n], axis=1).astype(np.float64)
+    print("%s %s: %d CTAs; per-phase cycles median [p10, p90]; total median %.0f" % (name, which, len(t), np.median(t[:, n - 1] - t[:, 0])))
+    for i in range(n - 1):
+        col = d[:, i]
+        print("   %-12s %8.0f [%6.0f, %6.0f]" % (labels[i + 1], np.median(col), np.percentile(col, 10), np.percentile(col, 90)))
+    print("   setup (entry -> stamp 0): %.0f cycles median" % np.median(t[:, 0] - t[:, 7]))
+    if which == "fwd" and t[:, 10].any():
+        seq = [("entry", 7), ("setup done", 0), ("x+gso issued", 10), ("tap0 A written", 11), ("fence.proxy", 12),
+               ("barrier k0", 1), ("tap0 MMAs issued", 13), ("barrier k1", 14), ("mbar wait k2", 15),
+               ("tap loop done", 2), ("epilogue done", 3)]
+        base = t[:, 7]
+        print("   tcgen05 fwd timeline (median cycles since entry): " +
+              ", ".join("%s=%.0f" % (nm, np.median(t[:, sl] - base)) for nm, sl in seq))
+    ns0, ns1 = t[:, 8], t[:, 9]
+    print("   globaltimer: CTA starts spread %.2f us, CTA duration median %.2f us, first start -> last end %.2f us"
+          % ((ns0.max() - ns0.min()) / 1e3, np.median(ns1 - ns0) / 1e3, (ns1.max() - ns0.min()) / 1e3))
