@@ -3,6 +3,7 @@
 // (path B, incl. the CSR variant), second-stage gradient reductions.
 #include "gfc_tile.cuh"
 #include "gfc_generic.cuh"
+#include "gfc_tc5_wide.cuh"
 #include <string.h>
 #include <math.h>
 
@@ -118,6 +119,15 @@ static int need_ws(const char* fn, const void* ws, size_t have, size_t need) {
   return GFC_OK;
 }
 
+// ---- tcgen05 wide path eligibility -------------------------------------------------
+static bool use_wide(const GsoSrc& gs, bool norm, int N, int G, int F, int K, int mode, int prec) {
+  return !g_disable_tcgen05 && gs.kind == GSRC_POS && !norm && prec == GFC_PREC_FP32_3XTF32 &&
+         wide_supported(N, G, F, K, mode);
+}
+static size_t wide_ws_extra(int N, int G, int F, int K) {
+  return (wide_supported(N, G, F, K, 0) || wide_supported(N, G, F, K, 1)) ? wide_pack_bytes(G, F, K) : 0;
+}
+
 // ---- forward ------------------------------------------------------------------
 static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, const float* h, const float* bias,
                            float* y, int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
@@ -136,7 +146,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   }
   TilePlan p;
   if (E == 1 && plan_tile(B, N, G, F, K, 0, gs.kind, &p)) {
-    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes);
+    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(N, G, F, K));
     if (rc) return rc;
     TileArgs a{};
     a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
@@ -145,6 +155,17 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
+    if (use_wide(gs, norm, N, G, F, K, 0, prec) && a.vec_ok && aligned16(gs.pos)) {
+      // tcgen05 / TMEM path: bf16x3 planes, hops and taps on the tensor cores
+      uint16_t* hp = reinterpret_cast<uint16_t*>(static_cast<char*>(ws) + p.ws_bytes);
+      rc = launch_wide_pack(h, G, F, K, 0, hp, st);
+      if (rc) return rc;
+      WideArgs wa{};
+      wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
+      wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K;
+      wa.act = act; wa.slope = slope;
+      return launch_wide(wa, G, F, 0, st);
+    }
     if (!p.h_smem) {
       float4* hp = reinterpret_cast<float4*>(static_cast<char*>(ws) + p.ws_hpack);
       rc = launch_pack_taps(h, F, p.KG, 0, hp, st);
@@ -206,7 +227,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   }
   TilePlan p;
   if (E == 1 && plan_tile(B, N, G, F, K, 1, gs.kind, &p)) {
-    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes);
+    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(N, G, F, K));
     if (rc) return rc;
     char* wsb = static_cast<char*>(ws);
     TileArgs a{};
@@ -219,7 +240,21 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
-    if (!p.h_smem && dX) {
+    if (dX && use_wide(gs, norm, N, G, F, K, 1, prec) && a.vec_ok && aligned16(gs.pos) && aligned16(dX)) {
+      // dX on the tcgen05 path (V_k = P^k (dY o act'), dX = sum_k V_k H_k); dH / db below
+      uint16_t* hp = reinterpret_cast<uint16_t*>(wsb + p.ws_bytes);
+      rc = launch_wide_pack(h, G, F, K, 1, hp, st);
+      if (rc) return rc;
+      WideArgs wa{};
+      wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
+      wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
+      wa.B = B; wa.N = N; wa.K = K; wa.act = act; wa.slope = slope;
+      rc = launch_wide(wa, G, F, 1, st);
+      if (rc) return rc;
+      a.dX = nullptr;
+      if (!dH && !db) return GFC_OK;
+    }
+    if (!p.h_smem && a.dX) {
       float4* hp = reinterpret_cast<float4*>(wsb + p.ws_hpack);
       rc = launch_pack_taps(h, F, p.KG, 1, hp, st);
       if (rc) return rc;
@@ -342,7 +377,10 @@ extern "C" size_t gfc_filter_workspace_bytes(int B, int N, int G, int F, int K, 
   TilePlan p;
   bool all_tile = (E == 1);
   for (int src = 0; src < 2 && E == 1; ++src) {
-    if (plan_tile(B, N, G, F, K, backward, src, &p)) { if (p.ws_bytes > need) need = p.ws_bytes; }
+    if (plan_tile(B, N, G, F, K, backward, src, &p)) {
+      const size_t nb = p.ws_bytes + wide_ws_extra(N, G, F, K);
+      if (nb > need) need = nb;
+    }
     else all_tile = false;
   }
   if (!all_tile) {

@@ -1,0 +1,28 @@
+// gfc_tc5_wide.cuh — host interface of the warp-specialised tcgen05 kernels (gfc_tc5_wide.cu).
+#pragma once
+#include "gfc_common.cuh"
+
+namespace gfc {
+
+struct WideArgs {
+  const float* pos;        // [B,N,2]
+  double thr;              // squared-distance threshold, fp64 rule (gfc_gso.cu)
+  float thr_lo, thr_hi;    // fp32 screening band
+  const float* in;         // MODE 0: x [B,G,N];  MODE 1: dY [B,N,F]
+  const float* yout;       // MODE 1: forward output [B,N,F] (activation mask) or null
+  const uint16_t* hpack;   // taps as bf16x3 planes in ring-stage order (wide_pack_taps_kernel)
+  const float* bias;       // MODE 0: [F] or null
+  float* out;              // MODE 0: y [B,N,F];  MODE 1: dX [B,G,N]
+  int B, N, K;
+  int gpc, ntiles;         // filled by launch_wide
+  int act;
+  float slope;
+};
+
+// mode 0 = forward, 1 = backward dX
+bool wide_supported(int N, int G, int F, int K, int mode);
+size_t wide_pack_bytes(int G, int F, int K);
+int launch_wide_pack(const float* h, int G, int F, int K, int mode, uint16_t* out, cudaStream_t st);
+int launch_wide(const WideArgs& a, int G, int F, int mode, cudaStream_t st);
+
+}  // namespace gfc
