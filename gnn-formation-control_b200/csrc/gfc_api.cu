@@ -124,8 +124,13 @@ static bool use_wide(const GsoSrc& gs, bool norm, int N, int G, int F, int K, in
   return !g_disable_tcgen05 && gs.kind == GSRC_POS && !norm && prec == GFC_PREC_FP32_3XTF32 &&
          wide_supported(N, G, F, K, mode);
 }
-static size_t wide_ws_extra(int N, int G, int F, int K) {
-  return (wide_supported(N, G, F, K, 0) || wide_supported(N, G, F, K, 1)) ? wide_pack_bytes(G, F, K) : 0;
+static size_t wide_ws_extra(int B, int N, int G, int F, int K, int backward) {
+  size_t n = (wide_supported(N, G, F, K, 0) || wide_supported(N, G, F, K, 1)) ? wide_pack_bytes(G, F, K) : 0;
+  if (backward && wide_dh_supported(N, G, F, K)) {
+    const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
+    n += align_up(np * F * K * G * sizeof(float), 256) + align_up(np * F * sizeof(float), 256);
+  }
+  return n;
 }
 
 // ---- forward ------------------------------------------------------------------
@@ -146,7 +151,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   }
   TilePlan p;
   if (E == 1 && plan_tile(B, N, G, F, K, 0, gs.kind, &p)) {
-    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(N, G, F, K));
+    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(B, N, G, F, K, 0));
     if (rc) return rc;
     TileArgs a{};
     a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
@@ -163,7 +168,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       WideArgs wa{};
       wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
       wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K;
-      wa.act = act; wa.slope = slope;
+      wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
       return launch_wide(wa, G, F, 0, st);
     }
     if (!p.h_smem) {
@@ -227,7 +232,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   }
   TilePlan p;
   if (E == 1 && plan_tile(B, N, G, F, K, 1, gs.kind, &p)) {
-    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(N, G, F, K));
+    rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(B, N, G, F, K, 1));
     if (rc) return rc;
     char* wsb = static_cast<char*>(ws);
     TileArgs a{};
@@ -248,11 +253,28 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       WideArgs wa{};
       wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
       wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
-      wa.B = B; wa.N = N; wa.K = K; wa.act = act; wa.slope = slope;
+      wa.B = B; wa.N = N; wa.K = K; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
       rc = launch_wide(wa, G, F, 1, st);
       if (rc) return rc;
       a.dX = nullptr;
       if (!dH && !db) return GFC_OK;
+    }
+    if (dH && use_wide(gs, norm, N, G, F, K, 1, prec) && wide_dh_supported(N, G, F, K) && a.vec_ok &&
+        aligned16(gs.pos) && !a.dX) {
+      // dH / db on the tcgen05 path: accumulators stay in tensor memory across all tiles of a CTA
+      const int np = wide_dh_nparts(B, N, F, K);
+      char* base = wsb + p.ws_bytes + wide_pack_bytes(G, F, K);
+      float* dhp = reinterpret_cast<float*>(base);
+      float* dbp = reinterpret_cast<float*>(base + align_up((size_t)np * nH * sizeof(float), 256));
+      WideDhArgs da{};
+      da.pos = gs.pos; da.thr = a.thr; da.thr_lo = a.thr_lo; da.thr_hi = a.thr_hi;
+      da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr;
+      da.dHp = dhp; da.dbp = db ? dbp : nullptr;
+      da.B = B; da.N = N; da.K = K; da.act = act; da.slope = slope;
+      rc = launch_wide_dh(da, G, F, st);
+      if (rc) return rc;
+      if (g_skip_grad_reduce) return GFC_OK;
+      return launch_reduce_parts(dhp, np, (int)nH, dH, db ? dbp : nullptr, np, F, db, st);
     }
     if (!p.h_smem && a.dX) {
       float4* hp = reinterpret_cast<float4*>(wsb + p.ws_hpack);
@@ -339,6 +361,7 @@ extern "C" int gfc_set_debug_clock_buffer(void* device_i64, size_t bytes) {
 extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_SKIP_GRAD_REDUCE) { g_skip_grad_reduce = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_DISABLE_TCGEN05) { g_disable_tcgen05 = value ? 1 : 0; return GFC_OK; }
+  if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 2; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
   return GFC_ERR_BAD_ARG;
 }
@@ -378,7 +401,7 @@ extern "C" size_t gfc_filter_workspace_bytes(int B, int N, int G, int F, int K, 
   bool all_tile = (E == 1);
   for (int src = 0; src < 2 && E == 1; ++src) {
     if (plan_tile(B, N, G, F, K, backward, src, &p)) {
-      const size_t nb = p.ws_bytes + wide_ws_extra(N, G, F, K);
+      const size_t nb = p.ws_bytes + wide_ws_extra(B, N, G, F, K, backward);
       if (nb > need) need = nb;
     }
     else all_tile = false;

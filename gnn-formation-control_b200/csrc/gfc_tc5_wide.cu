@@ -20,9 +20,13 @@
 // MODE 1: backward dX: V_0 = dY o act'(y), V_k = P V_{k-1}, dX = sum_k V_k H_k^T-contraction
 //         (IN = dY [B,N,F], OUT = dX [B,G,N]; CIN = F, COUT = G) — the closed form of the autograd
 //         graph of graphML.py:2342-2366 for a symmetric 0/1 GSO.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <type_traits>
 #include "gfc_common.cuh"
 #include "gfc_tc5.cuh"
 #include "gfc_tc5_wide.cuh"
+#include <string.h>
 
 namespace gfc {
 
@@ -35,20 +39,21 @@ struct WideLayout {
   static constexpr int PW = ROWS * 16;               // bytes between chunks (one chunk column of all rows)
   static constexpr int PLANE = NCH * PW;             // one bf16 plane of a slab
   static constexpr int SLAB = 3 * PLANE;
-  static constexpr int P_BYTES = (ROWS / 8) * PW;    // block-diagonal hop matrix, bf16 [128 x 128]
   static constexpr int STAGE = COUT * 96;            // taps of 16 channels: 3 planes x 2 chunks x COUT x 16 B
   static constexpr int NSTAGE = 6;
   static constexpr int KSTEPS = CS / 16;             // tap MMA k-steps (= ring stages) per phase
   static constexpr int OFF_W = 0;
-  static constexpr int OFF_P = OFF_W + 2 * SLAB;
-  static constexpr int OFF_RING = OFF_P + P_BYTES;
-  static constexpr int OFF_SP = OFF_RING + NSTAGE * STAGE;   // float2 positions of the tile rows
-  static constexpr int OFF_BAR = OFF_SP + ROWS * 8;
+  static constexpr int OFF_RING = OFF_W + 2 * SLAB;
+  static constexpr int OFF_STAGE = (OFF_RING + NSTAGE * STAGE + 1023) / 1024 * 1024;   // 2 TMA store staging buffers [128 rows x 32 cols] fp32, 128B swizzle
+  static constexpr int OFF_BIAS = OFF_STAGE + 2 * ROWS * 128;
+  static constexpr int OFF_SP = OFF_BIAS + COUT * 4;         // float2 positions of the tile rows
+  static constexpr int OFF_BAR = OFF_SP + 2 * ROWS * 8;     // (two position buffers, alternating per tile)
   static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 1 + 2 + 2;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr int TM_OUT = 0;                   // two output accumulators [128 x COUT]
   static constexpr int TM_HOP = 2 * COUT;            // two hop accumulators   [128 x CS]
-  static constexpr int TM_USED = 2 * COUT + 2 * CS;
+  static constexpr int TM_P = 2 * COUT + 2 * CS;     // two buffers of the block-diagonal 0/1 hop matrix P, bf16 [128 lanes x 128 k] = 64 columns each
+  static constexpr int TM_USED = 2 * COUT + 2 * CS + 128;
   static constexpr int TM_COLS = TM_USED <= 32 ? 32 : TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
   static_assert(CIN % 32 == 0 && CIN >= 32 && CIN <= 128, "CIN in {32,64,96,128}");
   static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "COUT multiple of 16, <= 128");
@@ -58,6 +63,7 @@ struct WideLayout {
 
 constexpr int kWideThreads = 320;   // warp 0: MMA issuer, warp 1: TMA producer + TMEM owner, warps 2..9: workers
 constexpr int kWorkerWarps = 8;
+int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16);
@@ -65,12 +71,74 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
   return ((uint64_t)hi << 32) | lo;
 }
 
-__device__ __forceinline__ bool wide_adjacent(float2 a, float2 b, const WideArgs& w) {
+// exact fp64 rule, kept out of line so the (rare) rounding-band case is a real branch and the fp64 /
+// conversion instructions are not if-converted into every pair test
+__device__ __noinline__ bool wide_adjacent_exact(float ax, float ay, float bx, float by, double thr) {
+  return sqdist64(ax, ay, bx, by) <= thr;
+}
+__device__ __forceinline__ bool wide_adjacent(float2 a, float2 b, double thr, float thr_lo, float thr_hi) {
   const float dx = a.x - b.x, dy = a.y - b.y;
   const float s = fmaf(dx, dx, dy * dy);
-  if (s < w.thr_lo) return true;
-  if (s > w.thr_hi) return false;
-  return sqdist64(a.x, a.y, b.x, b.y) <= w.thr;
+  if (s < thr_lo) return true;
+  if (s > thr_hi) return false;
+  return wide_adjacent_exact(a.x, a.y, b.x, b.y, thr);
+}
+
+// adjacency of tile row `pr` (position `me`) with the 8 tile rows c0..c0+7: fp32 bit patterns 1.0f / 0.
+// All 8 squared distances are formed first (8 independent shared-memory loads); the exact fp64 rule only
+// runs for the rare pairs inside the fp32 rounding band.
+__device__ __forceinline__ void adjacency8(uint32_t (&e)[8], const float2* __restrict__ sp, float2 me, int pr,
+                                           int c0, int c_lo, int c_hi, int rows_used, double thr, float thr_lo,
+                                           float thr_hi) {
+  float sv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float2 o = sp[c0 + i];
+    const float dx = me.x - o.x, dy = me.y - o.y;
+    sv[i] = fmaf(dx, dx, dy * dy);
+  }
+  uint32_t band = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int c = c0 + i;
+    const bool ok = (c >= c_lo) && (c < c_hi) && (c != pr) && (pr < rows_used) && (c < rows_used);
+    e[i] = (ok && sv[i] < thr_lo) ? 0x3f800000u : 0u;
+    if (ok && sv[i] >= thr_lo && sv[i] <= thr_hi) band |= 1u << i;
+  }
+  if (band) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (band & (1u << i)) {
+        const float2 o = sp[c0 + i];
+        e[i] = wide_adjacent_exact(me.x, me.y, o.x, o.y, thr) ? 0x3f800000u : 0u;
+      }
+    }
+  }
+}
+
+// Predicated read-only loads as volatile asm: issued exactly where written (never sunk to the first use)
+// and with the predicate inside the statement, so no select / move depends on the value right after it.
+__device__ __forceinline__ float ldg_f32(const float* p, bool pred) {
+  float v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\t"
+      "@q ld.global.nc.f32 %0, [%1];\n\t}"
+      : "=f"(v)
+      : "l"(p), "r"((int)pred));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_f32x4(const float* p, bool pred) {
+  float4 v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "@q ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];\n\t}"
+      : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+      : "l"(p), "r"((int)pred));
+  return v;
 }
 
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -92,13 +160,14 @@ __device__ __forceinline__ void store_chunk3(unsigned char* plane0, int plane_by
 
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(kWideThreads, 1)
-tc5_wide_kernel(const WideArgs w) {
+tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUtensorMap tmap_out) {
   using L = WideLayout<CIN, COUT>;
   extern __shared__ __align__(128) unsigned char wsmem[];
   unsigned char* Wb = wsmem + L::OFF_W;
-  unsigned char* Pb = wsmem + L::OFF_P;
   unsigned char* Rb = wsmem + L::OFF_RING;
-  float2* sp = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
+  float2* sp_all = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
+  unsigned char* stage_out = wsmem + L::OFF_STAGE;
+  float* sbias = reinterpret_cast<float*>(wsmem + L::OFF_BIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsmem + L::OFF_BAR);
   uint64_t* h_full = bars;                      // [NSTAGE]
   uint64_t* h_empty = bars + L::NSTAGE;         // [NSTAGE]
@@ -113,7 +182,7 @@ tc5_wide_kernel(const WideArgs w) {
   const int N = w.N, K = w.K;
 
   // ---- one-time setup -------------------------------------------------------------------------
-  for (int i = tid; i < L::P_BYTES / 16; i += kWideThreads) reinterpret_cast<uint4*>(Pb)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < COUT; i += kWideThreads) sbias[i] = (MODE == 0 && w.bias) ? __ldg(w.bias + i) : 0.f;
   if (tid == 0) {
     for (int i = 0; i < L::NSTAGE; ++i) { tc5::mbar_init(&h_full[i], 1); tc5::mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -132,79 +201,92 @@ tc5_wide_kernel(const WideArgs w) {
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
 
+  // NOTE on code size: every role's per-tile code is executed once per ~15 us while the other roles run
+  // their own loops, so the instruction caches only hold it if it is small.  Loops are deliberately kept
+  // rolled (one copy of the plane-split / pair-test / MMA-issue code each) unless a register array forces
+  // unrolling; barrier parities are bit masks so that they can be indexed at run time.
   if (warp == 0) {
-    // =========================== MMA issuer (one thread) ======================================
-    if (lane == 0) {
+    // =========================== MMA issuer (one elected thread) ===============================
+    if (tc5::elect_one()) {
       constexpr uint32_t kIdescTap = tc5::idesc_bf16(128, COUT, 0, 0);
       constexpr uint32_t kIdescHop = tc5::idesc_bf16(128, L::CS, 0, 1);
-      const uint32_t w_addr = tc5::smem_u32(Wb), p_addr = tc5::smem_u32(Pb), r_addr = tc5::smem_u32(Rb);
-      uint32_t par_wr[2] = {0, 0}, par_of[2] = {0, 0}, par_pr = 0, par_hf = 0;
+      const uint32_t w_addr = tc5::smem_u32(Wb), r_addr = tc5::smem_u32(Rb);
+      uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0;
       int st = 0;
+      int nstamp = 0;
+      const bool dbg = w.dbg != nullptr && blockIdx.x == 0;
+#define GFC_WSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
       const int hop_ksteps = (w.gpc * N + 15) >> 4;
       int it = 0;
       for (int tile = blockIdx.x; tile < w.ntiles; tile += gridDim.x, ++it) {
         const int ob = it & 1;
-        if (it >= 2) { tc5::mbar_wait(&out_free[ob], par_of[ob]); par_of[ob] ^= 1; }
+        if (it >= 2) { tc5::mbar_wait(&out_free[ob], (par_of >> ob) & 1); par_of ^= 1u << ob; }
         tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
         const uint32_t d_out = tmem + L::TM_OUT + ob * COUT;
-        for (int k = 0; k < K; ++k) {
+#pragma unroll 1
+        for (int ph = 0; ph < 2 * K; ++ph) {
+          const int k = ph >> 1, s = ph & 1;
+          GFC_WSTAMP(100 + s);
+          tc5::mbar_wait(&w_ready[s], (par_wr >> s) & 1); par_wr ^= 1u << s;
+          tc5::fence_after_sync();
+          GFC_WSTAMP(110 + s);
+          const uint32_t ws = w_addr + s * L::SLAB;
+          if (k + 1 < K) {
+            // hop: D_hop[s] = P * W_k[slab s]   (A = P from tensor memory, B = state planes MN-major)
+            const uint32_t d_hop = tmem + L::TM_HOP + s * L::CS;
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int j = 0; j < hop_ksteps; ++j) {
+              const uint32_t pa = tmem + L::TM_P + ob * 64 + j * 8;   // 16 source rows = 8 columns of bf16 pairs
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            tc5::mbar_wait(&w_ready[s], par_wr[s]); par_wr[s] ^= 1;
-            tc5::fence_after_sync();
-            const uint32_t ws = w_addr + s * L::SLAB;
-            if (k + 1 < K) {
-              // hop: D_hop[s] = P * W_k[slab s]   (A = P K-major, B = state planes MN-major)
-              const uint32_t d_hop = tmem + L::TM_HOP + s * L::CS;
-              uint32_t acc = 0;
-              for (int j = 0; j < hop_ksteps; ++j) {
-                const uint64_t da = make_desc(p_addr + j * 2 * L::PW, L::PW, 128);
-#pragma unroll
-                for (int pl = 0; pl < 3; ++pl) {
-                  const uint64_t db = make_desc(ws + pl * L::PLANE + j * 256, 128, L::PW);
-                  tc5::mma_bf16_ss(d_hop, da, db, kIdescHop, acc);
-                  acc = 1;
-                }
+              for (int pl = 0; pl < 3; ++pl) {
+                tc5::mma_bf16_ts(d_hop, pa, make_desc(ws + pl * L::PLANE + j * 256, 128, L::PW), kIdescHop, acc);
+                acc = 1;
               }
             }
-            // taps: D_out += W_k[slab s] * H_k[slab s]   (6-term bf16x3 product)
-#pragma unroll 1
-            for (int i = 0; i < L::KSTEPS; ++i) {
-              tc5::mbar_wait(&h_full[st], par_hf);
-              tc5::fence_after_sync();
-              const uint32_t hs = r_addr + st * L::STAGE;
-              const uint32_t wa = ws + i * 2 * L::PW;
-              const uint64_t a0 = make_desc(wa, L::PW, 128);
-              const uint64_t a1 = make_desc(wa + L::PLANE, L::PW, 128);
-              const uint64_t a2 = make_desc(wa + 2 * L::PLANE, L::PW, 128);
-              const uint64_t b0 = make_desc(hs, COUT * 16, 128);
-              const uint64_t b1 = make_desc(hs + COUT * 32, COUT * 16, 128);
-              const uint64_t b2 = make_desc(hs + COUT * 64, COUT * 16, 128);
-              const uint32_t first = (k == 0 && s == 0 && i == 0) ? 0u : 1u;
-              tc5::mma_bf16_ss(d_out, a0, b0, kIdescTap, first);
-              tc5::mma_bf16_ss(d_out, a0, b1, kIdescTap, 1u);
-              tc5::mma_bf16_ss(d_out, a1, b0, kIdescTap, 1u);
-              tc5::mma_bf16_ss(d_out, a1, b1, kIdescTap, 1u);
-              tc5::mma_bf16_ss(d_out, a0, b2, kIdescTap, 1u);
-              tc5::mma_bf16_ss(d_out, a2, b0, kIdescTap, 1u);
-              tc5::mma_commit(&h_empty[st]);
-              if (++st == L::NSTAGE) { st = 0; par_hf ^= 1; }
-            }
-            tc5::mma_commit(&mma_done[s]);
           }
+          // taps: D_out += W_k[slab s] * H_k[slab s]   (6-term bf16x3 product)
+#pragma unroll 1
+          for (int i = 0; i < L::KSTEPS; ++i) {
+            if (i == 0) GFC_WSTAMP(120 + s);
+            tc5::mbar_wait(&h_full[st], par_hf);
+            tc5::fence_after_sync();
+            GFC_WSTAMP(130 + i);
+            const uint32_t hs = r_addr + st * L::STAGE;
+            const uint32_t wa = ws + i * 2 * L::PW;
+            const uint64_t a0 = make_desc(wa, L::PW, 128);
+            const uint64_t a1 = make_desc(wa + L::PLANE, L::PW, 128);
+            const uint64_t a2 = make_desc(wa + 2 * L::PLANE, L::PW, 128);
+            const uint64_t b0 = make_desc(hs, COUT * 16, 128);
+            const uint64_t b1 = make_desc(hs + COUT * 32, COUT * 16, 128);
+            const uint64_t b2 = make_desc(hs + COUT * 64, COUT * 16, 128);
+            const uint32_t first = (ph == 0 && i == 0) ? 0u : 1u;
+            tc5::mma_bf16_ss(d_out, a0, b0, kIdescTap, first);
+            tc5::mma_bf16_ss(d_out, a0, b1, kIdescTap, 1u);
+            tc5::mma_bf16_ss(d_out, a1, b0, kIdescTap, 1u);
+            tc5::mma_bf16_ss(d_out, a1, b1, kIdescTap, 1u);
+            tc5::mma_bf16_ss(d_out, a0, b2, kIdescTap, 1u);
+            tc5::mma_bf16_ss(d_out, a2, b0, kIdescTap, 1u);
+            tc5::mma_commit(&h_empty[st]);
+            if (++st == L::NSTAGE) { st = 0; par_hf ^= 1; }
+          }
+          tc5::mma_commit(&mma_done[s]);
+          GFC_WSTAMP(140 + s);
         }
         tc5::mma_commit(&out_full[ob]);
       }
     }
+    __syncwarp();
   } else if (warp == 1) {
     // =========================== tap producer (TMA bulk copies) ===============================
-    if (lane == 0) {
+    if (tc5::elect_one()) {
       int st = 0;
       uint32_t par_he = 0;
       bool primed = false;   // the first NSTAGE fills need no wait
       int filled = 0;
       const int stages_per_tile = K * (CIN / 16);
       for (int tile = blockIdx.x; tile < w.ntiles; tile += gridDim.x) {
+#pragma unroll 1
         for (int u = 0; u < stages_per_tile; ++u) {
           if (primed) { tc5::mbar_wait(&h_empty[st], par_he); }
           tc5::mbar_arrive_expect_tx(&h_full[st], L::STAGE);
@@ -215,61 +297,106 @@ tc5_wide_kernel(const WideArgs w) {
         }
       }
     }
+    __syncwarp();
   } else {
     // =========================== workers ======================================================
     const int wt = tid - 64;                 // 0..255
-    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;        // which half of a slab's columns
-    const int r = q * 32 + lane;             // tile row owned by this thread
+    const int r = q * 32 + lane;             // tile row owned by this thread (= its TMEM lane)
     const int jr = r / N, nr = r - jr * N;   // (graph, node) of the row
-    float xin[2][L::CPT];
+    const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
+    float xin[L::CPT];
     float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_md[2] = {0, 0}, par_ofl[2] = {0, 0};
+    uint32_t par_md = 0, par_ofl = 0;
+    int nstamp = 0;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2048 + 2 * nstamp] = clock64(); w.dbg[2048 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
 
-    auto load_inputs = [&](int tile) {
+    // Operands of the next tile.  Early in the current tile one thread asks the TMA engine to pull the
+    // (contiguous) input tile into L2; the register loads then happen slab by slab right before the slab is
+    // written (short live ranges, L2-hit latency hidden behind the P build / the wait for the slab).
+    auto prefetch_tile = [&](int tile) {
+      const int b0 = tile * w.gpc;
+      const int gcount = min(w.gpc, w.B - b0);
+      const uint32_t bytes = (uint32_t)gcount * (uint32_t)N * CIN * 4u;   // multiple of 16 (CIN % 32 == 0)
+      const size_t off = (size_t)b0 * N * CIN;
+      tc5::bulk_prefetch_l2(w.in + off, bytes);
+      if (MODE == 1 && w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + off, bytes);
+    };
+    auto load_pos = [&](int tile) {
+      const int b0 = tile * w.gpc;
+      const int gcount = min(w.gpc, w.B - b0);
+      if (wt < 128)   // rows 0..127 in thread order wt: position of row wt
+        mypos = (wt < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + wt)
+                                  : make_float2(0.f, 0.f);
+    };
+    auto load_slab = [&](int tile, int s) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
       const bool valid = r < gcount * N;
-      if (wt < 128) {   // rows 0..127 in thread order wt: position of row wt
-        const int rr = wt;
-        mypos = (rr < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + rr)
-                                  : make_float2(0.f, 0.f);
-      }
+      const int c0 = s * L::CS + half * L::CPT;
+      if (MODE == 0) {
+        const float* src = w.in + ((size_t)(b0 + jr) * CIN + c0) * N + nr;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const int c0 = s * L::CS + half * L::CPT;
-        if (MODE == 0) {
-          const float* src = w.in + ((size_t)(b0 + jr) * CIN + c0) * N + nr;
+        for (int i = 0; i < L::CPT; ++i) xin[i] = ldg_f32(src + (size_t)i * N, valid);
+      } else {
+        // dY / y are row-major [rows x CIN]: a warp instruction reads whole 16-byte pieces of RPI consecutive rows
+        // (4 full lines) instead of 32 scattered ones; the halves of a bf16 chunk meet by a lane-pair shuffle
+        // at store time.  Warp ww owns rows 16 ww .. 16 ww + 15, lane = (row offset, piece).
+        constexpr int PPR = L::CS / 4, RPI = 32 / PPR;
+        const int ww = warp - 2;
+        const int rows_used = gcount * N;
 #pragma unroll
-          for (int i = 0; i < L::CPT; ++i) xin[s][i] = valid ? __ldg(src + (size_t)i * N) : 0.f;
-        } else {
-          const size_t off = ((size_t)b0 * N + r) * CIN + c0;
-#pragma unroll
-          for (int i4 = 0; i4 < L::CPT / 4; ++i4) {
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (valid) {
-              v = __ldg(reinterpret_cast<const float4*>(w.in + off) + i4);
-              if (w.act != GFC_ACT_NONE) {
-                const float4 yo = __ldg(reinterpret_cast<const float4*>(w.yout + off) + i4);
-                v.x = act_grad(v.x, yo.x, w.act, w.slope);
-                v.y = act_grad(v.y, yo.y, w.act, w.slope);
-                v.z = act_grad(v.z, yo.z, w.act, w.slope);
-                v.w = act_grad(v.w, yo.w, w.act, w.slope);
-              }
-            }
-            xin[s][4 * i4] = v.x; xin[s][4 * i4 + 1] = v.y; xin[s][4 * i4 + 2] = v.z; xin[s][4 * i4 + 3] = v.w;
+        for (int i = 0; i < L::CPT / 4; ++i) {
+          const int row = 16 * ww + RPI * i + lane / PPR;
+          const bool ok = row < rows_used;
+          const size_t off = ((size_t)b0 * N + row) * CIN + s * L::CS + 4 * (lane % PPR);
+          float4 v = ldg_f32x4(w.in + off, ok);
+          if (w.act != GFC_ACT_NONE) {
+            const float4 yo = ldg_f32x4(w.yout + off, ok);
+            v.x = act_grad(v.x, yo.x, w.act, w.slope);
+            v.y = act_grad(v.y, yo.y, w.act, w.slope);
+            v.z = act_grad(v.z, yo.z, w.act, w.slope);
+            v.w = act_grad(v.w, yo.w, w.act, w.slope);
           }
+          xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
         }
       }
     };
-    auto store_w0 = [&](int s) {
-      unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
+    // registers of load_slab -> the three bf16 planes of W_0[slab s]
+    auto store_slab = [&](int s) {
+      if (MODE == 0) {
+        unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
 #pragma unroll
-      for (int c = 0; c < L::CPT / 8; ++c) {
-        float v[8];
+        for (int c = 0; c < L::CPT / 8; ++c) {
+          float v[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = xin[s][c * 8 + i];
-        store_chunk3(base + c * L::PW, L::PLANE, v);
+          for (int i = 0; i < 8; ++i) v[i] = xin[c * 8 + i];
+          store_chunk3(base + c * L::PW, L::PLANE, v);
+        }
+      } else {
+        constexpr int PPR = L::CS / 4, RPI = 32 / PPR;
+        const int ww = warp - 2;
+        const int pi = lane % PPR;
+        const bool odd = pi & 1;
+#pragma unroll
+        for (int i = 0; i < L::CPT / 4; i += 2) {
+          // even lane keeps its piece of row(i) and receives the partner's; odd lane does the same for row(i+1)
+          float snd[4], rcv[4], own[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            snd[e] = odd ? xin[4 * i + e] : xin[4 * (i + 1) + e];
+            own[e] = odd ? xin[4 * (i + 1) + e] : xin[4 * i + e];
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { v[e] = odd ? rcv[e] : own[e]; v[4 + e] = odd ? own[e] : rcv[e]; }
+          const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+          store_chunk3(Wb + s * L::SLAB + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
+        }
       }
     };
     auto publish = [&](uint64_t* bar) {   // this warp's shared-memory writes -> tensor core, then arrive
@@ -278,15 +405,411 @@ tc5_wide_kernel(const WideArgs w) {
       __syncwarp();
       if (lane == 0) tc5::mbar_arrive(bar);
     };
+
+    // P[r][c] = 1 iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
+    // TMEM lane r; the two warps of a quadrant interleave 4-chunk groups of source rows.  Chunks t0..t1-1 of 8.
+    auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
+      const float2* sp = sp_all + pbuf * L::ROWS;
+      const int gcount = min(w.gpc, w.B - tile * w.gpc);
+      const int rows_used = gcount * N;
+      const int c_lo = jr * N, c_hi = c_lo + N;
+      const float2 me = sp[r];
+      const bool row_ok = r < w.gpc * N;
+#pragma unroll 1
+      for (int t = t0; t < t1; ++t) {
+        const int qc = (t >> 2) * 8 + half * 4 + (t & 3);   // chunk of 8 source rows = 4 TMEM columns
+        uint32_t e[8];
+        if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
+          adjacency8(e, sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.thr, w.thr_lo, w.thr_hi);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) e[i] = 0u;
+        }
+        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, tc5::pack_bf16_hi(e[0], e[1]), tc5::pack_bf16_hi(e[2], e[3]),
+                      tc5::pack_bf16_hi(e[4], e[5]), tc5::pack_bf16_hi(e[6], e[7]));
+      }
+    };
+    auto publish_p = [&]() {
+      tc5::tmem_st_wait();
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(p_ready);
+    };
+
+    // The loop runs once per tile plus one leading iteration (it == -1) that only prepares the first tile's
+    // operands, so that the per-tile code exists exactly once.  P of the next tile is double-buffered in TMEM and
+    // built in two halves right after the first two write-backs of the live tile (where the workers have slack).
+    int tile = blockIdx.x;            // tile whose MMAs run during this iteration (none when it == -1)
+    int it = -1;
+    int next = blockIdx.x;
+    if (next < w.ntiles) load_pos(next);
+    while (true) {
+      const bool live = it >= 0;
+      const bool has_next = next < w.ntiles;
+      if (!live && !has_next) break;
+      const int pbuf = (it + 1) & 1;
+      if (has_next) {
+        if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;   // positions of `next` (loaded one tile ahead)
+        worker_bar();
+        if (next + (int)gridDim.x < w.ntiles) load_pos(next + gridDim.x);
+        if (wt == 0) prefetch_tile(next);
+        if (!live || K == 1) {
+          if (K > 1) build_p_part(next, pbuf, 0, 8);
+          publish_p();
+        }
+      }
+      // ---- write-backs of the K-1 hops ------------------------------------------------------------------
+      const int nwb = live ? 2 * (K - 1) : 0;
+#pragma unroll 1
+      for (int ph = 0; ph < nwb; ++ph) {
+        {
+          const int s = ph & 1;
+          GFC_KSTAMP(200 + s);
+          tc5::mbar_wait(&mma_done[s], (par_md >> s) & 1); par_md ^= 1u << s;
+          tc5::fence_after_sync();
+          GFC_KSTAMP(210 + s);
+          // hop result (exact fp32) -> three bf16 planes of W_{k+1}[slab s], 8 columns at a time
+          const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + half * L::CPT;
+          unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
+#pragma unroll 1
+          for (int c = 0; c < L::CPT / 8; ++c) {
+            uint32_t v[8];
+            tc5::tmem_ld8u(taddr + c * 8, v);
+            tc5::tmem_ld_wait();
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+            store_chunk3(base + c * L::PW, L::PLANE, f);
+          }
+          GFC_KSTAMP(220 + s);
+          publish(&w_ready[s]);
+          GFC_KSTAMP(230 + s);
+        }
+        if (has_next && ph < 2) {   // K > 1 here
+          build_p_part(next, pbuf, 4 * ph, 4 * ph + 4);
+          if (ph == 1) publish_p();
+        }
+      }
+      // ---- the live tile's slabs become free one by one: next tile's state W_0 ---------------------------
+      GFC_KSTAMP(240);
+      if (has_next) load_slab(next, 0);     // L2 hits (prefetched)
+#pragma unroll 1
+      for (int s = 0; s < 2; ++s) {
+        if (has_next && s == 1) load_slab(next, 1);   // in flight while the last tap of slab 1 finishes
+        if (live) { tc5::mbar_wait(&mma_done[s], (par_md >> s) & 1); par_md ^= 1u << s; }
+        GFC_KSTAMP(250 + s);
+        if (has_next) {
+          store_slab(s);
+          publish(&w_ready[s]);
+        }
+        GFC_KSTAMP(260 + s);
+      }
+      // ---- epilogue of the live tile (the issuer is already working on the next one) -------------------
+      if (live) {
+        const int b0 = tile * w.gpc;
+        const int rows_used = min(w.gpc, w.B - b0) * N;
+        const int ob = it & 1;
+        tc5::mbar_wait(&out_full[ob], (par_ofl >> ob) & 1); par_ofl ^= 1u << ob;
+        tc5::fence_after_sync();
+        GFC_KSTAMP(271);
+        if constexpr (MODE == 0) {
+          // y tile through swizzled staging buffers and the TMA store engine: full 128-byte lines
+#pragma unroll 1
+          for (int pc = 0; pc < COUT / 32; ++pc) {
+            const int col = pc * 32 + half * 16;
+            uint32_t v[16];
+            tc5::tmem_ld16(tm_lane + L::TM_OUT + ob * COUT + col, v);
+            tc5::tmem_ld_wait();
+            unsigned char* sbuf = stage_out + (pc & 1) * (L::ROWS * 128);
+            unsigned char* srow = sbuf + r * 128;
+            // the TMA store that last used this buffer (two pieces ago) has finished reading it
+            if (wt == 0) tc5::tma_store_wait_read1();
+            worker_bar();
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i4 * 4);
+              float4 o;
+              o.x = apply_act(__uint_as_float(v[i4 * 4 + 0]) + bb.x, w.act, w.slope);
+              o.y = apply_act(__uint_as_float(v[i4 * 4 + 1]) + bb.y, w.act, w.slope);
+              o.z = apply_act(__uint_as_float(v[i4 * 4 + 2]) + bb.z, w.act, w.slope);
+              o.w = apply_act(__uint_as_float(v[i4 * 4 + 3]) + bb.w, w.act, w.slope);
+              const int cc = half * 4 + i4;
+              *reinterpret_cast<float4*>(srow + ((cc ^ (r & 7)) << 4)) = o;
+            }
+            tc5::fence_proxy_async();
+            worker_bar();
+            if (wt == 0) {
+              tc5::tma_store_2d(&tmap_out, sbuf, pc * 32, b0 * N);
+              tc5::tma_store_commit();
+            }
+          }
+        } else {
+          // dX[(b0 + j), g, n]: lanes = consecutive nodes n, one coalesced store per channel
+          const bool valid = r < rows_used;
+#pragma unroll 1
+          for (int cb = 0; cb < COUT / 2; cb += 16) {
+            const int col = half * (COUT / 2) + cb;
+            uint32_t v[16];
+            tc5::tmem_ld16(tm_lane + L::TM_OUT + ob * COUT + col, v);
+            tc5::tmem_ld_wait();
+            if (valid) {
+              float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]);
+            }
+          }
+        }
+        tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(&out_free[ob]);
+        GFC_KSTAMP(270);
+      }
+      if (!has_next) break;
+      tile = next;
+      next += gridDim.x;
+      ++it;
+    }
+  }
+  if (tid == 64) tc5::tma_store_wait_all();
+  tc5::fence_before_sync();
+  __syncthreads();
+  if (warp == 1) tc5::tmem_dealloc(tmem, L::TM_COLS);
+}
+
+// =====================================================================================================
+// backward dH / db:  dH[f][k*G+g] = sum_rows V_k[r][f] X[r][g],  V_0 = dY o act'(y),  V_k = P V_{k-1}
+// (the same gradient as sum_rows D[r][f] Z_k[r][g] with Z_k = P^k X, because P is symmetric; it needs no
+// recomputation of the diffusion states).  A CTA owns the feature slice fh (FH columns of f) for the
+// whole kernel and keeps its K x [G x FH] accumulators in tensor memory across all its tiles:
+//   * X^T (lanes = g, columns = tile rows, bf16x3 planes) is the A operand, stored into TMEM by the
+//     workers straight from x's native [B,G,N] layout (tcgen05.st);
+//   * V_k sub-slabs (two independent chains of FH/2 columns) live in shared memory as bf16x3 planes and
+//     serve as MN-major B operand of both the dH product and the hop.
+// =====================================================================================================
+template <int G, int F, int FH>
+struct DhLayout {
+  static constexpr int ROWS = 128;
+  static constexpr int NFH = F / FH;
+  static constexpr int SS = FH / 2;                  // columns per sub-slab (one chain)
+  static constexpr int CPT = SS / 2;                 // V columns per worker thread and sub-slab
+  static constexpr int NCH = SS / 8;
+  static constexpr int PW = ROWS * 16;
+  static constexpr int PLANE = NCH * PW;
+  static constexpr int SLAB = 3 * PLANE;
+  static constexpr int P_BYTES = (ROWS / 8) * PW;
+  static constexpr int OFF_V = 0;
+  static constexpr int OFF_P = OFF_V + 2 * SLAB;
+  static constexpr int OFF_SP = OFF_P + P_BYTES;
+  static constexpr int OFF_DB = OFF_SP + ROWS * 8;
+  static constexpr int OFF_BAR = OFF_DB + FH * 4;
+  static constexpr int NBAR = 2 + 2 + 1 + 1;
+  static constexpr int BYTES_MIN = OFF_BAR + NBAR * 8 + 16;
+  static constexpr int BYTES = BYTES_MIN < 120 * 1024 ? 120 * 1024 : BYTES_MIN;   // one CTA per SM (TMEM is taken whole)
+  static constexpr int TM_X = 0;                     // 3 planes x 64 columns (128 rows, two per column)
+  static constexpr int TM_ACC = 192;                 // acc(k, s) at TM_ACC + k*FH + s*SS
+  static_assert(FH % 32 == 0 && F % FH == 0 && CPT % 8 == 0, "feature slice");
+  static_assert(G == 128 || G == 64 || G == 32, "G");
+};
+
+template <int G, int F, int FH>
+__global__ void __launch_bounds__(kWideThreads, 1)
+tc5_wide_dh_kernel(const WideDhArgs w) {
+  using L = DhLayout<G, F, FH>;
+  extern __shared__ __align__(128) unsigned char wsmem[];
+  unsigned char* Vb = wsmem + L::OFF_V;
+  unsigned char* Pb = wsmem + L::OFF_P;
+  float2* sp = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
+  float* dbs = reinterpret_cast<float*>(wsmem + L::OFF_DB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsmem + L::OFF_BAR);
+  uint64_t* v_ready = bars;          // [2]
+  uint64_t* mma_done = bars + 2;     // [2]
+  uint64_t* p_ready = bars + 4;
+  uint64_t* x_ready = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = w.N, K = w.K;
+  const int fh = blockIdx.x % L::NFH, part = blockIdx.x / L::NFH, nparts = gridDim.x / L::NFH;
+  const int TM_HOP = L::TM_ACC + K * FH;
+
+  for (int i = tid; i < L::P_BYTES / 16; i += kWideThreads) reinterpret_cast<uint4*>(Pb)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < FH; i += kWideThreads) dbs[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { tc5::mbar_init(&v_ready[i], kWorkerWarps); tc5::mbar_init(&mma_done[i], 1); }
+    tc5::mbar_init(p_ready, kWorkerWarps);
+    tc5::mbar_init(x_ready, kWorkerWarps);
+    tc5::fence_mbar_init();
+  }
+  if (warp == 1) tc5::tmem_alloc(tmem_ptr, 512);
+  tc5::fence_proxy_async();
+  tc5::fence_before_sync();
+  __syncthreads();
+  tc5::fence_after_sync();
+  const uint32_t tmem = *tmem_ptr;
+
+  if (warp == 0) {
+    if (tc5::elect_one()) {
+      constexpr uint32_t kIdescHop = tc5::idesc_bf16(128, L::SS, 0, 1);
+      constexpr uint32_t kIdescDh = tc5::idesc_bf16(128, L::SS, 0, 1);
+      const uint32_t v_addr = tc5::smem_u32(Vb), p_addr = tc5::smem_u32(Pb);
+      uint32_t par_vr[2] = {0, 0}, par_pr = 0, par_xr = 0;
+      const int ksteps = (w.gpc * N + 15) >> 4;
+      int it = 0;
+      for (int tile = part; tile < w.ntiles; tile += nparts, ++it) {
+        tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
+        tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1;
+        tc5::fence_after_sync();
+        const bool fresh = (it % w.flush_every) == 0;   // the workers drained the accumulators before x_ready
+        for (int k = 0; k < K; ++k) {
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            tc5::mbar_wait(&v_ready[s], par_vr[s]); par_vr[s] ^= 1;
+            tc5::fence_after_sync();
+            const uint32_t vs = v_addr + s * L::SLAB;
+            if (k + 1 < K) {
+              const uint32_t d_hop = tmem + TM_HOP + s * L::SS;
+              uint32_t acc = 0;
+              for (int j = 0; j < ksteps; ++j) {
+                const uint64_t da = make_desc(p_addr + j * 2 * L::PW, L::PW, 128);
+#pragma unroll
+                for (int pl = 0; pl < 3; ++pl) {
+                  tc5::mma_bf16_ss(d_hop, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdescHop, acc);
+                  acc = 1;
+                }
+              }
+            }
+            const uint32_t d_acc = tmem + L::TM_ACC + k * FH + s * L::SS;
+            for (int j = 0; j < ksteps; ++j) {
+              const uint32_t xa = tmem + L::TM_X + j * 8;
+              const uint64_t b0 = make_desc(vs + j * 256, 128, L::PW);
+              const uint64_t b1 = make_desc(vs + L::PLANE + j * 256, 128, L::PW);
+              const uint64_t b2 = make_desc(vs + 2 * L::PLANE + j * 256, 128, L::PW);
+              const uint32_t first = (fresh && j == 0) ? 0u : 1u;
+              tc5::mma_bf16_ts(d_acc, xa, b0, kIdescDh, first);
+              tc5::mma_bf16_ts(d_acc, xa, b1, kIdescDh, 1u);
+              tc5::mma_bf16_ts(d_acc, xa + 64, b0, kIdescDh, 1u);
+              tc5::mma_bf16_ts(d_acc, xa + 64, b1, kIdescDh, 1u);
+              tc5::mma_bf16_ts(d_acc, xa, b2, kIdescDh, 1u);
+              tc5::mma_bf16_ts(d_acc, xa + 128, b0, kIdescDh, 1u);
+            }
+            tc5::mma_commit(&mma_done[s]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 2) {
+    const int wt = tid - 64;
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
+    const int r = q * 32 + lane;               // tile row (V loads / write-back) and feature lane g (X^T, readout)
+    const bool g_ok = r < G;
+    float xin[2][L::CPT];                      // V_0 columns of this row, next tile
+    float dbacc[2][L::CPT];
+    float xt[64];                              // x[g = r][rows 64 hf .. 64 hf + 63], next tile
+    float2 mypos = make_float2(0.f, 0.f);
+    uint32_t par_md[2] = {0, 0};
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int i = 0; i < L::CPT; ++i) dbacc[s][i] = 0.f;
+
+    auto load_inputs = [&](int tile) {
+      const int b0 = tile * w.gpc;
+      const int gcount = min(w.gpc, w.B - b0);
+      const int rows_used = gcount * N;
+      const bool valid = r < rows_used;
+      if (wt < 128) mypos = (wt < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + wt)
+                                             : make_float2(0.f, 0.f);
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const size_t off = ((size_t)b0 * N + r) * F + fh * FH + s * L::SS + hf * L::CPT;
+#pragma unroll
+        for (int i4 = 0; i4 < L::CPT / 4; ++i4) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) {
+            v = __ldg(reinterpret_cast<const float4*>(w.dY + off) + i4);
+            if (w.act != GFC_ACT_NONE) {
+              const float4 yo = __ldg(reinterpret_cast<const float4*>(w.yout + off) + i4);
+              v.x = act_grad(v.x, yo.x, w.act, w.slope);
+              v.y = act_grad(v.y, yo.y, w.act, w.slope);
+              v.z = act_grad(v.z, yo.z, w.act, w.slope);
+              v.w = act_grad(v.w, yo.w, w.act, w.slope);
+            }
+          }
+          xin[s][4 * i4] = v.x; xin[s][4 * i4 + 1] = v.y; xin[s][4 * i4 + 2] = v.z; xin[s][4 * i4 + 3] = v.w;
+        }
+      }
+      if (g_ok) {
+        // x[(b0 + j), g, n] for the 64 tile rows (j, n) of this thread's half
+        if ((N & 3) == 0) {
+#pragma unroll
+          for (int i4 = 0; i4 < 16; ++i4) {
+            const int rr = hf * 64 + i4 * 4;
+            const int j = rr / N, n = rr - j * N;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rr < rows_used) v = __ldg(reinterpret_cast<const float4*>(w.x + ((size_t)(b0 + j) * G + r) * N + n));
+            xt[4 * i4] = v.x; xt[4 * i4 + 1] = v.y; xt[4 * i4 + 2] = v.z; xt[4 * i4 + 3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) {
+            const int rr = hf * 64 + i;
+            const int j = rr / N, n = rr - j * N;
+            xt[i] = (rr < rows_used) ? __ldg(w.x + ((size_t)(b0 + j) * G + r) * N + n) : 0.f;
+          }
+        }
+      }
+    };
+    auto store_v0 = [&](int s) {
+      unsigned char* base = Vb + s * L::SLAB + (hf * (L::CPT / 8)) * L::PW + r * 16;
+#pragma unroll
+      for (int c = 0; c < L::CPT / 8; ++c) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[i] = xin[s][c * 8 + i]; dbacc[s][c * 8 + i] += v[i]; }
+        store_chunk3(base + c * L::PW, L::PLANE, v);
+      }
+    };
+    auto store_xt = [&]() {
+      if (q * 32 < G) {   // warp-uniform: this quadrant holds real feature lanes
+        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + L::TM_X + hf * 32;
+#pragma unroll
+        for (int c8 = 0; c8 < 4; ++c8) {   // 8 columns (16 tile rows) at a time keeps the live registers low
+          uint32_t p0[8], p1[8], p2[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint32_t a0, a1, a2, b0, b1, b2;
+            tc5::split_bf16x3(xt[16 * c8 + 2 * i], a0, a1, a2);
+            tc5::split_bf16x3(xt[16 * c8 + 2 * i + 1], b0, b1, b2);
+            p0[i] = tc5::pack_bf16_hi(a0, b0);
+            p1[i] = tc5::pack_bf16_hi(a1, b1);
+            p2[i] = tc5::pack_bf16_hi(a2, b2);
+          }
+          tc5::tmem_st8(ta + c8 * 8, p0);
+          tc5::tmem_st8(ta + 64 + c8 * 8, p1);
+          tc5::tmem_st8(ta + 128 + c8 * 8, p2);
+        }
+        tc5::tmem_st_wait();
+      }
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(x_ready);
+    };
+    auto publish = [&](uint64_t* bar) {
+      tc5::fence_proxy_async();
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(bar);
+    };
     auto build_p = [&](int tile) {
-      // P[r][c] = 1 iff rows r and c belong to the same graph and are adjacent (symmetric rule)
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
       const int rows_used = gcount * N;
       const int pr = wt & 127, hsel = wt >> 7;
       if (pr < w.gpc * N) {
         const int pj = pr / N;
-        const int c_lo = pj * N, c_hi = c_lo + N;        // block columns [c_lo, c_hi)
+        const int c_lo = pj * N, c_hi = c_lo + N;
         const float2 me = sp[pr];
         for (int qc = (c_lo >> 3); qc <= ((c_hi - 1) >> 3); ++qc) {
           if ((qc & 1) != hsel) continue;
@@ -295,7 +818,8 @@ tc5_wide_kernel(const WideArgs w) {
           for (int i = 0; i < 8; ++i) {
             const int c = qc * 8 + i;
             bool on = false;
-            if (c >= c_lo && c < c_hi && c != pr && pr < rows_used && c < rows_used) on = wide_adjacent(me, sp[c], w);
+            if (c >= c_lo && c < c_hi && c != pr && pr < rows_used && c < rows_used)
+              on = wide_adjacent(me, sp[c], w.thr, w.thr_lo, w.thr_hi);
             e[i] = on ? 0x3f800000u : 0u;
           }
           *reinterpret_cast<uint4*>(Pb + qc * L::PW + pr * 16) =
@@ -305,45 +829,70 @@ tc5_wide_kernel(const WideArgs w) {
       }
     };
 
-    // ---- prologue: first tile's operands -----------------------------------------------------
-    int tile = blockIdx.x;
+    // Drain the TMEM accumulators into this CTA group's partial buffer (L2-resident, owned by this CTA:
+    // plain read-modify-write).  The tensor core's fp32 accumulation truncates, so the error grows with the
+    // number of MMAs chained into one accumulator; draining every `flush_every` tiles bounds it.
+    float* dst = w.dHp + (size_t)part * F * K * G;
+    int n_flush = 0;
+    auto flush = [&](bool have_acc) {
+      tc5::fence_after_sync();
+      if (q * 32 < G) {
+        for (int k = 0; k < K; ++k) {
+#pragma unroll 1
+          for (int cb = 0; cb < L::SS; cb += 8) {
+            const int col = hf * L::SS + cb;
+            uint32_t v[8];
+            if (have_acc) {
+              tc5::tmem_ld8u(tmem + ((uint32_t)(q * 32) << 16) + L::TM_ACC + k * FH + col, v);
+              tc5::tmem_ld_wait();
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = 0u;
+            }
+            if (g_ok) {
+              float* d0 = dst + (size_t)(fh * FH + col) * K * G + k * G + r;
+              if (n_flush == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d0[(size_t)i * K * G] = __uint_as_float(v[i]);
+              } else {
+                float old[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) old[i] = d0[(size_t)i * K * G];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d0[(size_t)i * K * G] = old[i] + __uint_as_float(v[i]);
+              }
+            }
+          }
+        }
+      }
+      ++n_flush;
+      tc5::fence_before_sync();
+    };
+
+    int tile = part;
     if (tile < w.ntiles) {
       load_inputs(tile);
       if (wt < 128) sp[wt] = mypos;
       worker_bar();
       if (K > 1) build_p(tile);
       publish(p_ready);
-      store_w0(0); publish(&w_ready[0]);
-      store_w0(1); publish(&w_ready[1]);
+      store_v0(0); publish(&v_ready[0]);
+      store_v0(1); publish(&v_ready[1]);
+      store_xt();
     }
-    int it = 0;
-    for (; tile < w.ntiles; tile += gridDim.x, ++it) {
-      const int next = tile + gridDim.x;
+    int n_items = 0;
+    for (; tile < w.ntiles; tile += nparts, ++n_items) {
+      const int next = tile + nparts;
       const bool has_next = next < w.ntiles;
-      const int b0 = tile * w.gpc;
-      const int gcount = min(w.gpc, w.B - b0);
-      const int rows_used = gcount * N;
-      if (has_next) load_inputs(next);       // in flight during this tile's tensor-core phases
+      if (has_next) load_inputs(next);
       for (int k = 0; k + 1 < K; ++k) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           tc5::mbar_wait(&mma_done[s], par_md[s]); par_md[s] ^= 1;
           tc5::fence_after_sync();
-          // hop result (exact fp32) -> three bf16 planes of W_{k+1}[slab s]
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + L::TM_HOP + s * L::CS + half * L::CPT;
-          unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
-          if constexpr (L::CPT == 32) {
-            uint32_t v[32];
-            tc5::tmem_ld32(taddr, v);
-            tc5::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c * 8 + i]);
-              store_chunk3(base + c * L::PW, L::PLANE, f);
-            }
-          } else {
+          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_HOP + s * L::SS + hf * L::CPT;
+          unsigned char* base = Vb + s * L::SLAB + (hf * (L::CPT / 8)) * L::PW + r * 16;
+          if constexpr (L::CPT == 16) {
             uint32_t v[16];
             tc5::tmem_ld16(taddr, v);
             tc5::tmem_ld_wait();
@@ -354,11 +903,18 @@ tc5_wide_kernel(const WideArgs w) {
               for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c * 8 + i]);
               store_chunk3(base + c * L::PW, L::PLANE, f);
             }
+          } else {
+            uint32_t v[8];
+            tc5::tmem_ld8u(taddr, v);
+            tc5::tmem_ld_wait();
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+            store_chunk3(base, L::PLANE, f);
           }
-          publish(&w_ready[s]);
+          publish(&v_ready[s]);
         }
       }
-      // ---- tail: all hops of this tile are done -> next tile's P; slabs free one by one --------
       if (has_next) {
         if (wt < 128) sp[wt] = mypos;
         worker_bar();
@@ -368,47 +924,25 @@ tc5_wide_kernel(const WideArgs w) {
 #pragma unroll
       for (int s = 0; s < 2; ++s) {
         tc5::mbar_wait(&mma_done[s], par_md[s]); par_md[s] ^= 1;
-        if (has_next) { store_w0(s); publish(&w_ready[s]); }
+        if (has_next) { store_v0(s); publish(&v_ready[s]); }
       }
-      // ---- epilogue of this tile (the issuer is already working on the next one) ---------------
-      const int ob = it & 1;
-      tc5::mbar_wait(&out_full[ob], par_ofl[ob]); par_ofl[ob] ^= 1;
-      tc5::fence_after_sync();
-      const bool valid = r < rows_used;
-#pragma unroll 1
-      for (int cb = 0; cb < COUT / 2; cb += 16) {
-        const int col = half * (COUT / 2) + cb;
-        uint32_t v[16];
-        tc5::tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + L::TM_OUT + ob * COUT + col, v);
-        tc5::tmem_ld_wait();
-        if (valid) {
-          if (MODE == 0) {
-            float* dst = w.out + ((size_t)b0 * N + r) * COUT + col;
+      // every dH product of this tile has completed (mma_done[1] of the last tap)
+      if (!has_next || ((n_items + 1) % w.flush_every) == 0) flush(true);
+      if (has_next) store_xt();
+    }
+    if (n_items == 0) flush(false);
+    if (w.dbp) {
 #pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              float o[4];
+      for (int s = 0; s < 2; ++s)
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float bb = w.bias ? __ldg(w.bias + col + i4 * 4 + i) : 0.f;
-                o[i] = apply_act(__uint_as_float(v[i4 * 4 + i]) + bb, w.act, w.slope);
-              }
-              reinterpret_cast<float4*>(dst)[i4] = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          } else {
-            float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]);
-          }
-        }
-      }
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(&out_free[ob]);
+        for (int i = 0; i < L::CPT; ++i) atomicAdd(dbs + s * L::SS + hf * L::CPT + i, dbacc[s][i]);
+      worker_bar();
+      if (wt < FH) w.dbp[(size_t)part * F + fh * FH + wt] = dbs[wt];
     }
   }
   tc5::fence_before_sync();
   __syncthreads();
-  if (warp == 1) tc5::tmem_dealloc(tmem, L::TM_COLS);
+  if (warp == 1) tc5::tmem_dealloc(tmem, 512);
 }
 
 // ---- tap packing: bf16x3 planes in ring-stage order ----------------------------------------------
@@ -452,16 +986,47 @@ bool wide_supported(int N, int G, int F, int K, int mode) {
 
 size_t wide_pack_bytes(int G, int F, int K) { return align_up((size_t)K * G * F * 6, 256); }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+static int encode_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
+                          uint32_t box_outer) {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    GFC_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres));
+    GFC_REQUIRE(p && qres == cudaDriverEntryPointSuccess, GFC_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {inner * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  GFC_REQUIRE(r == CUDA_SUCCESS, GFC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return GFC_OK;
+}
+
 template <int CIN, int COUT, int MODE>
-static int launch_wide_t(const WideArgs& a, cudaStream_t st) {
+static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   using L = WideLayout<CIN, COUT>;
+  WideArgs a = a0;
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  a.tma_out = 0;
+  if (MODE == 0) {   // y viewed as [B*N rows, COUT cols]; one box = [gpc*N rows x 32 cols]
+    int rc = encode_tmap_2d(&tmap, a.out, COUT, (uint64_t)a.B * a.N, 32, (uint32_t)(a.gpc * a.N));
+    if (rc) return rc;
+    a.tma_out = 1;
+  }
   auto kern = tc5_wide_kernel<CIN, COUT, MODE>;
   GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
   const int grid = a.ntiles < di.sm_count ? a.ntiles : di.sm_count;
-  kern<<<grid, kWideThreads, L::BYTES, st>>>(a);
+  kern<<<grid, kWideThreads, L::BYTES, st>>>(a, tmap);
   GFC_LAUNCH_CHECK(MODE == 0 ? "tc5_wide_kernel<fwd>" : "tc5_wide_kernel<dX>");
   return GFC_OK;
 }
@@ -481,6 +1046,69 @@ int launch_wide(const WideArgs& a0, int G, int F, int mode, cudaStream_t st) {
   GFC_WIDE_CASE(64, 128)
 #undef GFC_WIDE_CASE
   set_error("launch_wide: unsupported channel counts %d -> %d", CIN, COUT);
+  return GFC_ERR_UNSUPPORTED;
+}
+
+
+template <int G, int F, int FH>
+static int launch_wide_dh_t(const WideDhArgs& a0, int* nparts_out, cudaStream_t st) {
+  using L = DhLayout<G, F, FH>;
+  WideDhArgs a = a0;
+  auto kern = tc5_wide_dh_kernel<G, F, FH>;
+  GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+  kern<<<a.nparts * L::NFH, kWideThreads, L::BYTES, st>>>(a);
+  GFC_LAUNCH_CHECK("tc5_wide_dh_kernel");
+  if (nparts_out) *nparts_out = a.nparts;
+  return GFC_OK;
+}
+
+// feature slice: the K+1 [128 x FH] fp32 regions (K accumulators + the hop result) share 320 TMEM columns
+static int dh_slice(int F, int K) {
+  if ((K + 1) * F <= 320) return F;
+  if ((K + 1) * (F / 2) <= 320 && (F / 2) % 32 == 0) return F / 2;
+  return 0;
+}
+
+bool wide_dh_supported(int N, int G, int F, int K) {
+  if (N < 1 || N > 128 || K < 1) return false;
+  if (!(G == 128 || G == 64)) return false;
+  if (!(F == 128 || F == 64)) return false;
+  return dh_slice(F, K) != 0;
+}
+
+int wide_dh_nparts(int B, int N, int F, int K) {
+  DeviceInfo di;
+  if (get_device_info(&di)) return 0;
+  const int fhs = dh_slice(F, K);
+  if (!fhs) return 0;
+  const int nfh = F / fhs;
+  int gpc = 128 / N; if (gpc > B) gpc = B;
+  const int ntiles = ceil_div(B, gpc);
+  int np = di.sm_count / nfh;
+  if (np > ntiles) np = ntiles;
+  if (np < 1) np = 1;
+  return np;
+}
+
+int launch_wide_dh(const WideDhArgs& a0, int G, int F, cudaStream_t st) {
+  WideDhArgs a = a0;
+  a.gpc = 128 / a.N;
+  if (a.gpc > a.B) a.gpc = a.B;
+  a.ntiles = ceil_div(a.B, a.gpc);
+  a.nparts = wide_dh_nparts(a.B, a.N, F, a.K);
+  if (a.flush_every <= 0) a.flush_every = g_wide_flush_every;
+  const int fhs = dh_slice(F, a.K);
+#define GFC_DH_CASE(g, f, s) if (G == g && F == f && fhs == s) return launch_wide_dh_t<g, f, s>(a, nullptr, st);
+  GFC_DH_CASE(128, 128, 64)
+  GFC_DH_CASE(128, 128, 128)
+  GFC_DH_CASE(64, 64, 64)
+  GFC_DH_CASE(64, 64, 32)
+  GFC_DH_CASE(128, 64, 64)
+  GFC_DH_CASE(128, 64, 32)
+  GFC_DH_CASE(64, 128, 64)
+  GFC_DH_CASE(64, 128, 128)
+#undef GFC_DH_CASE
+  set_error("launch_wide_dh: unsupported shape G=%d F=%d K=%d", G, F, a.K);
   return GFC_ERR_UNSUPPORTED;
 }
 

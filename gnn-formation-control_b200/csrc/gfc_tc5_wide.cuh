@@ -17,7 +17,29 @@ struct WideArgs {
   int gpc, ntiles;         // filled by launch_wide
   int act;
   float slope;
+  int tma_out;             // filled by launch_wide: the y tile leaves through the TMA store engine
+  long long* dbg;          // optional clock stamps of CTA 0 (issuer at [0..), worker warp 2 at [2048..)), else null
 };
+
+struct WideDhArgs {
+  const float* pos;
+  double thr;
+  float thr_lo, thr_hi;
+  const float* x;          // [B,G,N]
+  const float* dY;         // [B,N,F]
+  const float* yout;       // [B,N,F] forward output (activation mask) or null
+  float* dHp;              // [nparts][F*K*G] per-CTA-group partial gradients (every element written)
+  float* dbp;              // [nparts][F] or null
+  int B, N, K;
+  int gpc, ntiles, nparts; // filled by launch_wide_dh
+  int flush_every;         // tiles chained into the TMEM accumulators between drains (0 = default)
+  int act;
+  float slope;
+};
+extern int g_wide_flush_every;
+bool wide_dh_supported(int N, int G, int F, int K);
+int wide_dh_nparts(int B, int N, int F, int K);   // number of partial buffers launch_wide_dh writes
+int launch_wide_dh(const WideDhArgs& a, int G, int F, cudaStream_t st);
 
 // mode 0 = forward, 1 = backward dX
 bool wide_supported(int N, int G, int F, int K, int mode);
