@@ -270,7 +270,8 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       da.pos = gs.pos; da.thr = a.thr; da.thr_lo = a.thr_lo; da.thr_hi = a.thr_hi;
       da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr;
       da.dHp = dhp; da.dbp = db ? dbp : nullptr;
-      da.B = B; da.N = N; da.K = K; da.act = act; da.slope = slope;
+      da.B = B; da.N = N; da.K = K; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
+      GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)np * nH * sizeof(float), st));   // partials are accumulated with red.add
       rc = launch_wide_dh(da, G, F, st);
       if (rc) return rc;
       if (g_skip_grad_reduce) return GFC_OK;
@@ -361,6 +362,7 @@ extern "C" int gfc_set_debug_clock_buffer(void* device_i64, size_t bytes) {
 extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_SKIP_GRAD_REDUCE) { g_skip_grad_reduce = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_DISABLE_TCGEN05) { g_disable_tcgen05 = value ? 1 : 0; return GFC_OK; }
+  if (key == 99) { g_wide_no_prefetch = value; return GFC_OK; }
   if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 2; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
   return GFC_ERR_BAD_ARG;

@@ -64,6 +64,7 @@ struct WideLayout {
 constexpr int kWideThreads = 320;   // warp 0: MMA issuer, warp 1: TMA producer + TMEM owner, warps 2..9: workers
 constexpr int kWorkerWarps = 8;
 int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
+int g_wide_no_prefetch = 0;    // experiment switch
 
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16);
@@ -141,6 +142,14 @@ __device__ __forceinline__ float4 ldg_f32x4(const float* p, bool pred) {
   return v;
 }
 
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ldg_cg(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // 8 consecutive channels of one row -> one 16-byte chunk in each of the three planes
@@ -180,6 +189,11 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
+  // a CTA owns a CONTIGUOUS range of tiles: its streams stay inside a few 2 MB pages for many tiles (strided
+  // assignment made every CTA touch new pages of every array at every tile: TLB-miss storms at tile boundaries)
+  const int tiles_per_cta = (w.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int t_begin = min(w.ntiles, (int)blockIdx.x * tiles_per_cta);
+  const int t_end = min(w.ntiles, t_begin + tiles_per_cta);
 
   // ---- one-time setup -------------------------------------------------------------------------
   for (int i = tid; i < COUT; i += kWideThreads) sbias[i] = (MODE == 0 && w.bias) ? __ldg(w.bias + i) : 0.f;
@@ -218,7 +232,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 #define GFC_WSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
       const int hop_ksteps = (w.gpc * N + 15) >> 4;
       int it = 0;
-      for (int tile = blockIdx.x; tile < w.ntiles; tile += gridDim.x, ++it) {
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const int ob = it & 1;
         if (it >= 2) { tc5::mbar_wait(&out_free[ob], (par_of >> ob) & 1); par_of ^= 1u << ob; }
         tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
@@ -285,7 +299,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       bool primed = false;   // the first NSTAGE fills need no wait
       int filled = 0;
       const int stages_per_tile = K * (CIN / 16);
-      for (int tile = blockIdx.x; tile < w.ntiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; ++tile) {
 #pragma unroll 1
         for (int u = 0; u < stages_per_tile; ++u) {
           if (primed) { tc5::mbar_wait(&h_empty[st], par_he); }
@@ -439,20 +453,23 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
     // The loop runs once per tile plus one leading iteration (it == -1) that only prepares the first tile's
     // operands, so that the per-tile code exists exactly once.  P of the next tile is double-buffered in TMEM and
     // built in two halves right after the first two write-backs of the live tile (where the workers have slack).
-    int tile = blockIdx.x;            // tile whose MMAs run during this iteration (none when it == -1)
+    int tile = t_begin;               // tile whose MMAs run during this iteration (none when it == -1)
     int it = -1;
-    int next = blockIdx.x;
-    if (next < w.ntiles) load_pos(next);
+    int next = t_begin;
+    if (next < t_end) load_pos(next);
     while (true) {
       const bool live = it >= 0;
-      const bool has_next = next < w.ntiles;
+      const bool has_next = next < t_end;
       if (!live && !has_next) break;
       const int pbuf = (it + 1) & 1;
       if (has_next) {
         if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;   // positions of `next` (loaded one tile ahead)
         worker_bar();
-        if (next + (int)gridDim.x < w.ntiles) load_pos(next + gridDim.x);
-        if (wt == 0) prefetch_tile(next);
+        if (next + 1 < t_end) load_pos(next + 1);
+        if (wt == 0 && !w.no_prefetch) {   // L2 prefetch runs two tiles ahead
+          if (!live) prefetch_tile(next);
+          if (next + 1 < t_end) prefetch_tile(next + 1);
+        }
         if (!live || K == 1) {
           if (K > 1) build_p_part(next, pbuf, 0, 8);
           publish_p();
@@ -460,8 +477,11 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       }
       // ---- write-backs of the K-1 hops ------------------------------------------------------------------
       const int nwb = live ? 2 * (K - 1) : 0;
+      bool slab0_loaded = false;
 #pragma unroll 1
       for (int ph = 0; ph < nwb; ++ph) {
+        // next tile's slab 0: requested two write-backs ahead of its use (memory latency behind the last taps)
+        if (has_next && !slab0_loaded && ph + 2 >= nwb) { load_slab(next, 0); slab0_loaded = true; }
         {
           const int s = ph & 1;
           GFC_KSTAMP(200 + s);
@@ -492,7 +512,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       }
       // ---- the live tile's slabs become free one by one: next tile's state W_0 ---------------------------
       GFC_KSTAMP(240);
-      if (has_next) load_slab(next, 0);     // L2 hits (prefetched)
+      if (has_next && !slab0_loaded) load_slab(next, 0);
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
         if (has_next && s == 1) load_slab(next, 1);   // in flight while the last tap of slab 1 finishes
@@ -566,7 +586,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       }
       if (!has_next) break;
       tile = next;
-      next += gridDim.x;
+      next += 1;
       ++it;
     }
   }
@@ -580,62 +600,72 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 // backward dH / db:  dH[f][k*G+g] = sum_rows V_k[r][f] X[r][g],  V_0 = dY o act'(y),  V_k = P V_{k-1}
 // (the same gradient as sum_rows D[r][f] Z_k[r][g] with Z_k = P^k X, because P is symmetric; it needs no
 // recomputation of the diffusion states).  A CTA owns the feature slice fh (FH columns of f) for the
-// whole kernel and keeps its K x [G x FH] accumulators in tensor memory across all its tiles:
-//   * X^T (lanes = g, columns = tile rows, bf16x3 planes) is the A operand, stored into TMEM by the
-//     workers straight from x's native [B,G,N] layout (tcgen05.st);
-//   * V_k sub-slabs (two independent chains of FH/2 columns) live in shared memory as bf16x3 planes and
-//     serve as MN-major B operand of both the dH product and the hop.
+// whole kernel and keeps its K x [G x FH] accumulators in tensor memory across its tiles:
+//   * X^T (lanes = g, columns = tile rows, bf16x3 planes) is the A operand, stored into TMEM by the workers
+//     straight from x's native [B,G,N] layout (tcgen05.st);
+//   * V_k lives in shared memory as bf16x3 planes, in a ring of three buffers (tap k of a tile uses buffer
+//     (base + k) % 3, so the next tile's V_0 can be written while the last taps still run); it is the MN-major
+//     B operand of both the dH product and the hop;
+//   * P (block-diagonal 0/1, exact in bf16) is double-buffered in shared memory (K-major A operand of the hop).
+// One chain per tile: hop(k) -> [write-back(k) by the workers || dH(k) on the tensor core] -> hop(k+1) ...
 // =====================================================================================================
 template <int G, int F, int FH>
 struct DhLayout {
   static constexpr int ROWS = 128;
   static constexpr int NFH = F / FH;
-  static constexpr int SS = FH / 2;                  // columns per sub-slab (one chain)
-  static constexpr int CPT = SS / 2;                 // V columns per worker thread and sub-slab
-  static constexpr int NCH = SS / 8;
+  static constexpr int CPT = FH / 2;                 // V columns per worker thread in a write-back
+  static constexpr int NCH = FH / 8;
   static constexpr int PW = ROWS * 16;
   static constexpr int PLANE = NCH * PW;
-  static constexpr int SLAB = 3 * PLANE;
+  static constexpr int VBUF = 3 * PLANE;
   static constexpr int P_BYTES = (ROWS / 8) * PW;
   static constexpr int OFF_V = 0;
-  static constexpr int OFF_P = OFF_V + 2 * SLAB;
-  static constexpr int OFF_SP = OFF_P + P_BYTES;
-  static constexpr int OFF_DB = OFF_SP + ROWS * 8;
+  static constexpr int OFF_P = OFF_V + 3 * VBUF;
+  static constexpr int OFF_SP = OFF_P + 2 * P_BYTES;
+  static constexpr int OFF_DB = OFF_SP + 2 * ROWS * 8;
   static constexpr int OFF_BAR = OFF_DB + FH * 4;
-  static constexpr int NBAR = 2 + 2 + 1 + 1;
+  static constexpr int NBAR = 5;
   static constexpr int BYTES_MIN = OFF_BAR + NBAR * 8 + 16;
   static constexpr int BYTES = BYTES_MIN < 120 * 1024 ? 120 * 1024 : BYTES_MIN;   // one CTA per SM (TMEM is taken whole)
   static constexpr int TM_X = 0;                     // 3 planes x 64 columns (128 rows, two per column)
-  static constexpr int TM_ACC = 192;                 // acc(k, s) at TM_ACC + k*FH + s*SS
+  static constexpr int TM_ACC = 192;                 // acc(k) at TM_ACC + k*FH, hop result at TM_ACC + K*FH
   static_assert(FH % 32 == 0 && F % FH == 0 && CPT % 8 == 0, "feature slice");
   static_assert(G == 128 || G == 64 || G == 32, "G");
+  static_assert(BYTES <= 227 * 1024, "shared memory");
 };
 
 template <int G, int F, int FH>
 __global__ void __launch_bounds__(kWideThreads, 1)
-tc5_wide_dh_kernel(const WideDhArgs w) {
+tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   using L = DhLayout<G, F, FH>;
   extern __shared__ __align__(128) unsigned char wsmem[];
   unsigned char* Vb = wsmem + L::OFF_V;
   unsigned char* Pb = wsmem + L::OFF_P;
-  float2* sp = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
+  float2* sp_all = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
   float* dbs = reinterpret_cast<float*>(wsmem + L::OFF_DB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsmem + L::OFF_BAR);
-  uint64_t* v_ready = bars;          // [2]
-  uint64_t* mma_done = bars + 2;     // [2]
-  uint64_t* p_ready = bars + 4;
-  uint64_t* x_ready = bars + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* v_ready = bars;          // workers -> issuer: the next V buffer is written
+  uint64_t* hop_done = bars + 1;     // issuer (commit) -> workers: hop result in TMEM, older MMAs complete
+  uint64_t* item_done = bars + 2;    // issuer (commit) -> workers: every MMA of the tile complete
+  uint64_t* p_ready = bars + 3;
+  uint64_t* x_ready = bars + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
   const int fh = blockIdx.x % L::NFH, part = blockIdx.x / L::NFH, nparts = gridDim.x / L::NFH;
   const int TM_HOP = L::TM_ACC + K * FH;
+  // contiguous tile range per CTA group (see tc5_wide_kernel)
+  const int tiles_per_part = (w.ntiles + nparts - 1) / nparts;
+  const int t_begin = min(w.ntiles, part * tiles_per_part);
+  const int t_end = min(w.ntiles, t_begin + tiles_per_part);
 
-  for (int i = tid; i < L::P_BYTES / 16; i += kWideThreads) reinterpret_cast<uint4*>(Pb)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * L::P_BYTES / 16; i += kWideThreads) reinterpret_cast<uint4*>(Pb)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < FH; i += kWideThreads) dbs[i] = 0.f;
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { tc5::mbar_init(&v_ready[i], kWorkerWarps); tc5::mbar_init(&mma_done[i], 1); }
+    tc5::mbar_init(v_ready, kWorkerWarps);
+    tc5::mbar_init(hop_done, 1);
+    tc5::mbar_init(item_done, 1);
     tc5::mbar_init(p_ready, kWorkerWarps);
     tc5::mbar_init(x_ready, kWorkerWarps);
     tc5::fence_mbar_init();
@@ -648,147 +678,167 @@ tc5_wide_dh_kernel(const WideDhArgs w) {
   const uint32_t tmem = *tmem_ptr;
 
   if (warp == 0) {
+    // =========================== MMA issuer (one elected thread) ===============================
     if (tc5::elect_one()) {
-      constexpr uint32_t kIdescHop = tc5::idesc_bf16(128, L::SS, 0, 1);
-      constexpr uint32_t kIdescDh = tc5::idesc_bf16(128, L::SS, 0, 1);
+      constexpr uint32_t kIdesc = tc5::idesc_bf16(128, FH, 0, 1);   // B = V planes, MN-major
       const uint32_t v_addr = tc5::smem_u32(Vb), p_addr = tc5::smem_u32(Pb);
-      uint32_t par_vr[2] = {0, 0}, par_pr = 0, par_xr = 0;
+      uint32_t par_vr = 0, par_pr = 0, par_xr = 0;
       const int ksteps = (w.gpc * N + 15) >> 4;
-      int it = 0;
-      for (int tile = part; tile < w.ntiles; tile += nparts, ++it) {
+      int it = 0, vbase = 0;
+      int nstamp = 0;
+      const bool dbg = w.dbg != nullptr && blockIdx.x == 0;
+#define GFC_DSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        GFC_DSTAMP(300);
         tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
-        tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1;
-        tc5::fence_after_sync();
+        GFC_DSTAMP(301);
         const bool fresh = (it % w.flush_every) == 0;   // the workers drained the accumulators before x_ready
+        const uint32_t pa = p_addr + (it & 1) * L::P_BYTES;
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
+          GFC_DSTAMP(310);
+          tc5::mbar_wait(v_ready, par_vr); par_vr ^= 1;
+          tc5::fence_after_sync();
+          GFC_DSTAMP(311);
+          const uint32_t vs = v_addr + ((vbase + k) % 3) * L::VBUF;
+          if (k + 1 < K) {
+            // hop: D_hop = P * V_k
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t da = make_desc(pa + j * 2 * L::PW, L::PW, 128);
 #pragma unroll
-          for (int s = 0; s < 2; ++s) {
-            tc5::mbar_wait(&v_ready[s], par_vr[s]); par_vr[s] ^= 1;
-            tc5::fence_after_sync();
-            const uint32_t vs = v_addr + s * L::SLAB;
-            if (k + 1 < K) {
-              const uint32_t d_hop = tmem + TM_HOP + s * L::SS;
-              uint32_t acc = 0;
-              for (int j = 0; j < ksteps; ++j) {
-                const uint64_t da = make_desc(p_addr + j * 2 * L::PW, L::PW, 128);
-#pragma unroll
-                for (int pl = 0; pl < 3; ++pl) {
-                  tc5::mma_bf16_ss(d_hop, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdescHop, acc);
-                  acc = 1;
-                }
+              for (int pl = 0; pl < 3; ++pl) {
+                tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdesc, acc);
+                acc = 1;
               }
             }
-            const uint32_t d_acc = tmem + L::TM_ACC + k * FH + s * L::SS;
-            for (int j = 0; j < ksteps; ++j) {
-              const uint32_t xa = tmem + L::TM_X + j * 8;
-              const uint64_t b0 = make_desc(vs + j * 256, 128, L::PW);
-              const uint64_t b1 = make_desc(vs + L::PLANE + j * 256, 128, L::PW);
-              const uint64_t b2 = make_desc(vs + 2 * L::PLANE + j * 256, 128, L::PW);
-              const uint32_t first = (fresh && j == 0) ? 0u : 1u;
-              tc5::mma_bf16_ts(d_acc, xa, b0, kIdescDh, first);
-              tc5::mma_bf16_ts(d_acc, xa, b1, kIdescDh, 1u);
-              tc5::mma_bf16_ts(d_acc, xa + 64, b0, kIdescDh, 1u);
-              tc5::mma_bf16_ts(d_acc, xa + 64, b1, kIdescDh, 1u);
-              tc5::mma_bf16_ts(d_acc, xa, b2, kIdescDh, 1u);
-              tc5::mma_bf16_ts(d_acc, xa + 128, b0, kIdescDh, 1u);
-            }
-            tc5::mma_commit(&mma_done[s]);
+            tc5::mma_commit(hop_done);
+            GFC_DSTAMP(312);
           }
+          if (k == 0) { tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1; tc5::fence_after_sync(); GFC_DSTAMP(313); }
+          // dH: acc(k)[g][f] += X^T[g][rows] * V_k[rows][f]   (6-term bf16x3 product, A from tensor memory)
+          const uint32_t d_acc = tmem + L::TM_ACC + k * FH;
+#pragma unroll 1
+          for (int j = 0; j < ksteps; ++j) {
+            const uint32_t xa = tmem + L::TM_X + j * 8;
+            const uint64_t b0 = make_desc(vs + j * 256, 128, L::PW);
+            const uint64_t b1 = make_desc(vs + L::PLANE + j * 256, 128, L::PW);
+            const uint64_t b2 = make_desc(vs + 2 * L::PLANE + j * 256, 128, L::PW);
+            const uint32_t first = (fresh && j == 0) ? 0u : 1u;
+            tc5::mma_bf16_ts(d_acc, xa, b0, kIdesc, first);
+            tc5::mma_bf16_ts(d_acc, xa, b1, kIdesc, 1u);
+            tc5::mma_bf16_ts(d_acc, xa + 64, b0, kIdesc, 1u);
+            tc5::mma_bf16_ts(d_acc, xa + 64, b1, kIdesc, 1u);
+            tc5::mma_bf16_ts(d_acc, xa, b2, kIdesc, 1u);
+            tc5::mma_bf16_ts(d_acc, xa + 128, b0, kIdesc, 1u);
+          }
+          GFC_DSTAMP(314);
         }
+        tc5::mma_commit(item_done);
+        vbase = (vbase + K) % 3;
       }
     }
     __syncwarp();
   } else if (warp >= 2) {
+    // =========================== workers ======================================================
     const int wt = tid - 64;
+    const int ww = warp - 2;
     const int q = warp & 3;
-    const int hf = (warp - 2) >> 2;
-    const int r = q * 32 + lane;               // tile row (V loads / write-back) and feature lane g (X^T, readout)
+    const int hf = ww >> 2;
+    const int r = q * 32 + lane;               // tile row (write-back) and feature lane g (X^T, drain)
+    const int jr = r / N;
     const bool g_ok = r < G;
-    float xin[2][L::CPT];                      // V_0 columns of this row, next tile
-    float dbacc[2][L::CPT];
-    float xt[64];                              // x[g = r][rows 64 hf .. 64 hf + 63], next tile
+    const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr int PPR = FH / 4, RPI = 32 / PPR;   // V_0 loads: 16-byte pieces per row, rows per warp instruction
+    float xt[64];                              // x[g = r][rows 64 hf .. 64 hf + 63] of the next tile
+    float xin[FH / 2];                         // V_0 pieces of the next tile (short-lived)
+    float dbacc[4] = {0.f, 0.f, 0.f, 0.f};     // column sums of V_0 (columns 4*(lane % PPR) .. +3)
     float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_md[2] = {0, 0};
-#pragma unroll
-    for (int s = 0; s < 2; ++s)
-#pragma unroll
-      for (int i = 0; i < L::CPT; ++i) dbacc[s][i] = 0.f;
+    uint32_t par_hd = 0, par_id = 0;
+    int nstamp = 0;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+#define GFC_ESTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2048 + 2 * nstamp] = clock64(); w.dbg[2048 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
 
-    auto load_inputs = [&](int tile) {
+    auto publish = [&](uint64_t* bar) {
+      tc5::fence_proxy_async();
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(bar);
+    };
+    auto load_pos = [&](int tile) {
+      const int b0 = tile * w.gpc;
+      const int rows_used = min(w.gpc, w.B - b0) * N;
+      if (wt < 128)
+        mypos = (wt < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + wt) : make_float2(0.f, 0.f);
+    };
+    auto prefetch_tile = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
-      const int rows_used = gcount * N;
-      const bool valid = r < rows_used;
-      if (wt < 128) mypos = (wt < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + wt)
-                                             : make_float2(0.f, 0.f);
+      tc5::bulk_prefetch_l2(w.dY + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+      if (w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+      if (fh == 0) tc5::bulk_prefetch_l2(w.x + (size_t)b0 * G * N, (uint32_t)gcount * G * N * 4u);
+    };
+    // X^T operand: x[(b0 + j), g, n] -> TMEM lane g, column (tile row / 2).  The 16x256b store shape lets a
+    // thread own 4 consecutive tile rows (one float4 of x) of the feature lanes  16 h + t/4  and  16 h + t/4 + 8:
+    // a warp load instruction then touches 8 lines instead of 32.  xt[16 P + 8 e + 4 u + i]: part P = 2 h + e
+    // (e selects rho in {2e, 2e+1}), u = rho & 1 ... see store_xt for the register order of the store.
+    auto load_xt_part = [&](int tile, auto part_c) {
+      constexpr int PART = decltype(part_c)::value;
+      constexpr int h16 = PART >> 1, e = PART & 1;
+      const int b0 = tile * w.gpc;
+      const int rows_used = min(w.gpc, w.B - b0) * N;
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const size_t off = ((size_t)b0 * N + r) * F + fh * FH + s * L::SS + hf * L::CPT;
+      for (int u = 0; u < 2; ++u) {          // rho = 2 e + u
 #pragma unroll
-        for (int i4 = 0; i4 < L::CPT / 4; ++i4) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (valid) {
-            v = __ldg(reinterpret_cast<const float4*>(w.dY + off) + i4);
-            if (w.act != GFC_ACT_NONE) {
-              const float4 yo = __ldg(reinterpret_cast<const float4*>(w.yout + off) + i4);
-              v.x = act_grad(v.x, yo.x, w.act, w.slope);
-              v.y = act_grad(v.y, yo.y, w.act, w.slope);
-              v.z = act_grad(v.z, yo.z, w.act, w.slope);
-              v.w = act_grad(v.w, yo.w, w.act, w.slope);
+        for (int gs = 0; gs < 2; ++gs) {     // feature lane t/4 (+ 8)
+          const int g = q * 32 + 16 * h16 + 8 * gs + (lane >> 2);
+          const int rr = hf * 64 + 16 * (2 * e + u) + 4 * (lane & 3);
+          float* dst = &xt[16 * PART + 8 * u + 4 * gs];
+          if ((N & 3) == 0) {
+            const int j = rr / N, n = rr - j * N;
+            const float4 v = ldg_f32x4(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr < rows_used);
+            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int j = (rr + i) / N, n = (rr + i) - j * N;
+              dst[i] = ldg_f32(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr + i < rows_used);
             }
-          }
-          xin[s][4 * i4] = v.x; xin[s][4 * i4 + 1] = v.y; xin[s][4 * i4 + 2] = v.z; xin[s][4 * i4 + 3] = v.w;
-        }
-      }
-      if (g_ok) {
-        // x[(b0 + j), g, n] for the 64 tile rows (j, n) of this thread's half
-        if ((N & 3) == 0) {
-#pragma unroll
-          for (int i4 = 0; i4 < 16; ++i4) {
-            const int rr = hf * 64 + i4 * 4;
-            const int j = rr / N, n = rr - j * N;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rr < rows_used) v = __ldg(reinterpret_cast<const float4*>(w.x + ((size_t)(b0 + j) * G + r) * N + n));
-            xt[4 * i4] = v.x; xt[4 * i4 + 1] = v.y; xt[4 * i4 + 2] = v.z; xt[4 * i4 + 3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 64; ++i) {
-            const int rr = hf * 64 + i;
-            const int j = rr / N, n = rr - j * N;
-            xt[i] = (rr < rows_used) ? __ldg(w.x + ((size_t)(b0 + j) * G + r) * N + n) : 0.f;
           }
         }
       }
     };
-    auto store_v0 = [&](int s) {
-      unsigned char* base = Vb + s * L::SLAB + (hf * (L::CPT / 8)) * L::PW + r * 16;
-#pragma unroll
-      for (int c = 0; c < L::CPT / 8; ++c) {
-        float v[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { v[i] = xin[s][c * 8 + i]; dbacc[s][c * 8 + i] += v[i]; }
-        store_chunk3(base + c * L::PW, L::PLANE, v);
-      }
+    auto load_xt_slot = [&](int tile, int slot) {
+      if (slot == 0) load_xt_part(tile, std::integral_constant<int, 0>{});
+      else if (slot == 1) load_xt_part(tile, std::integral_constant<int, 1>{});
+      else if (slot == 2) load_xt_part(tile, std::integral_constant<int, 2>{});
+      else load_xt_part(tile, std::integral_constant<int, 3>{});
     };
     auto store_xt = [&]() {
       if (q * 32 < G) {   // warp-uniform: this quadrant holds real feature lanes
-        const uint32_t ta = tmem + ((uint32_t)(q * 32) << 16) + L::TM_X + hf * 32;
 #pragma unroll
-        for (int c8 = 0; c8 < 4; ++c8) {   // 8 columns (16 tile rows) at a time keeps the live registers low
-          uint32_t p0[8], p1[8], p2[8];
+        for (int h16 = 0; h16 < 2; ++h16) {
+          uint32_t p0[16], p1[16], p2[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint32_t a0, a1, a2, b0, b1, b2;
-            tc5::split_bf16x3(xt[16 * c8 + 2 * i], a0, a1, a2);
-            tc5::split_bf16x3(xt[16 * c8 + 2 * i + 1], b0, b1, b2);
-            p0[i] = tc5::pack_bf16_hi(a0, b0);
-            p1[i] = tc5::pack_bf16_hi(a1, b1);
-            p2[i] = tc5::pack_bf16_hi(a2, b2);
+          for (int rho = 0; rho < 4; ++rho) {
+#pragma unroll
+            for (int gs = 0; gs < 2; ++gs) {
+              const float* src = &xt[16 * (2 * h16 + (rho >> 1)) + 8 * (rho & 1) + 4 * gs];
+              uint32_t a0, a1, a2, b0, b1, b2, c0, c1, c2, d0, d1, d2;
+              tc5::split_bf16x3(src[0], a0, a1, a2);
+              tc5::split_bf16x3(src[1], b0, b1, b2);
+              tc5::split_bf16x3(src[2], c0, c1, c2);
+              tc5::split_bf16x3(src[3], d0, d1, d2);
+              p0[4 * rho + 2 * gs] = tc5::pack_bf16_hi(a0, b0); p0[4 * rho + 2 * gs + 1] = tc5::pack_bf16_hi(c0, d0);
+              p1[4 * rho + 2 * gs] = tc5::pack_bf16_hi(a1, b1); p1[4 * rho + 2 * gs + 1] = tc5::pack_bf16_hi(c1, d1);
+              p2[4 * rho + 2 * gs] = tc5::pack_bf16_hi(a2, b2); p2[4 * rho + 2 * gs + 1] = tc5::pack_bf16_hi(c2, d2);
+            }
           }
-          tc5::tmem_st8(ta + c8 * 8, p0);
-          tc5::tmem_st8(ta + 64 + c8 * 8, p1);
-          tc5::tmem_st8(ta + 128 + c8 * 8, p2);
+          const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * h16) << 16) + L::TM_X + hf * 32;
+          tc5::tmem_st_16x256b_x4(ta, p0);
+          tc5::tmem_st_16x256b_x4(ta + 64, p1);
+          tc5::tmem_st_16x256b_x4(ta + 128, p2);
         }
         tc5::tmem_st_wait();
       }
@@ -796,146 +846,185 @@ tc5_wide_dh_kernel(const WideDhArgs w) {
       __syncwarp();
       if (lane == 0) tc5::mbar_arrive(x_ready);
     };
-    auto publish = [&](uint64_t* bar) {
-      tc5::fence_proxy_async();
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(bar);
-    };
-    auto build_p = [&](int tile) {
+    // V_0 = dY o act'(y) of this CTA's feature slice: coalesced pieces -> registers (+ db), then planes
+    auto load_v0 = [&](int tile) {
       const int b0 = tile * w.gpc;
-      const int gcount = min(w.gpc, w.B - b0);
-      const int rows_used = gcount * N;
-      const int pr = wt & 127, hsel = wt >> 7;
-      if (pr < w.gpc * N) {
-        const int pj = pr / N;
-        const int c_lo = pj * N, c_hi = c_lo + N;
-        const float2 me = sp[pr];
-        for (int qc = (c_lo >> 3); qc <= ((c_hi - 1) >> 3); ++qc) {
-          if ((qc & 1) != hsel) continue;
-          uint32_t e[8];
+      const int rows_used = min(w.gpc, w.B - b0) * N;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int c = qc * 8 + i;
-            bool on = false;
-            if (c >= c_lo && c < c_hi && c != pr && pr < rows_used && c < rows_used)
-              on = wide_adjacent(me, sp[c], w.thr, w.thr_lo, w.thr_hi);
-            e[i] = on ? 0x3f800000u : 0u;
+      for (int i = 0; i < FH / 8; ++i) {
+        const int row = 16 * ww + RPI * i + lane / PPR;
+        const bool ok = row < rows_used;
+        const size_t off = ((size_t)b0 * N + row) * F + fh * FH + 4 * (lane % PPR);
+        float4 v = ldg_f32x4(w.dY + off, ok);
+        if (w.act != GFC_ACT_NONE) {
+          const float4 yo = ldg_f32x4(w.yout + off, ok);
+          v.x = act_grad(v.x, yo.x, w.act, w.slope);
+          v.y = act_grad(v.y, yo.y, w.act, w.slope);
+          v.z = act_grad(v.z, yo.z, w.act, w.slope);
+          v.w = act_grad(v.w, yo.w, w.act, w.slope);
+        }
+        xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+        dbacc[0] += v.x; dbacc[1] += v.y; dbacc[2] += v.z; dbacc[3] += v.w;
+      }
+    };
+    auto store_v0 = [&](unsigned char* vbuf) {
+      const int pi = lane % PPR;
+      const bool odd = pi & 1;
+#pragma unroll
+      for (int i = 0; i < FH / 8; i += 2) {
+        float snd[4], rcv[4], own[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          snd[e] = odd ? xin[4 * i + e] : xin[4 * (i + 1) + e];
+          own[e] = odd ? xin[4 * (i + 1) + e] : xin[4 * i + e];
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { v[e] = odd ? rcv[e] : own[e]; v[4 + e] = odd ? own[e] : rcv[e]; }
+        const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+        store_chunk3(vbuf + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
+      }
+    };
+    // P[r][c] (smem, K-major A operand): chunks t0..t1-1 of the 8 this thread owns
+    auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
+      const float2* sp = sp_all + pbuf * L::ROWS;
+      unsigned char* pb = Pb + pbuf * L::P_BYTES;
+      const int rows_used = min(w.gpc, w.B - tile * w.gpc) * N;
+      const int c_lo = jr * N, c_hi = c_lo + N;
+      const float2 me = sp[r];
+      if (r < w.gpc * N) {
+#pragma unroll 1
+        for (int t = t0; t < t1; ++t) {
+          const int qc = 2 * t + hf;
+          if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
+            uint32_t e[8];
+            adjacency8(e, sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.thr, w.thr_lo, w.thr_hi);
+            *reinterpret_cast<uint4*>(pb + qc * L::PW + r * 16) =
+                make_uint4(tc5::pack_bf16_hi(e[0], e[1]), tc5::pack_bf16_hi(e[2], e[3]), tc5::pack_bf16_hi(e[4], e[5]),
+                           tc5::pack_bf16_hi(e[6], e[7]));
           }
-          *reinterpret_cast<uint4*>(Pb + qc * L::PW + pr * 16) =
-              make_uint4(tc5::pack_bf16_hi(e[0], e[1]), tc5::pack_bf16_hi(e[2], e[3]), tc5::pack_bf16_hi(e[4], e[5]),
-                         tc5::pack_bf16_hi(e[6], e[7]));
         }
       }
     };
-
-    // Drain the TMEM accumulators into this CTA group's partial buffer (L2-resident, owned by this CTA:
-    // plain read-modify-write).  The tensor core's fp32 accumulation truncates, so the error grows with the
-    // number of MMAs chained into one accumulator; draining every `flush_every` tiles bounds it.
+    // Drain the TMEM accumulators into this CTA group's partial buffer (zeroed by the host, L2-resident, every
+    // address owned by exactly one thread of one CTA) with fire-and-forget reductions: no read latency, and the
+    // per-address order is this thread's program order, so the result is deterministic.  The tensor core's fp32
+    // accumulation truncates, so the error grows with the number of MMAs chained into one accumulator;
+    // draining every `flush_every` tiles bounds it.
     float* dst = w.dHp + (size_t)part * F * K * G;
-    int n_flush = 0;
-    auto flush = [&](bool have_acc) {
+    auto flush = [&]() {
       tc5::fence_after_sync();
       if (q * 32 < G) {
+#pragma unroll 1
         for (int k = 0; k < K; ++k) {
 #pragma unroll 1
-          for (int cb = 0; cb < L::SS; cb += 8) {
-            const int col = hf * L::SS + cb;
+          for (int cb = 0; cb < FH / 2; cb += 8) {
+            const int col = hf * (FH / 2) + cb;
             uint32_t v[8];
-            if (have_acc) {
-              tc5::tmem_ld8u(tmem + ((uint32_t)(q * 32) << 16) + L::TM_ACC + k * FH + col, v);
-              tc5::tmem_ld_wait();
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) v[i] = 0u;
-            }
+            tc5::tmem_ld8u(tm_lane + L::TM_ACC + k * FH + col, v);
+            tc5::tmem_ld_wait();
             if (g_ok) {
               float* d0 = dst + (size_t)(fh * FH + col) * K * G + k * G + r;
-              if (n_flush == 0) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) d0[(size_t)i * K * G] = __uint_as_float(v[i]);
-              } else {
-                float old[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) old[i] = d0[(size_t)i * K * G];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) d0[(size_t)i * K * G] = old[i] + __uint_as_float(v[i]);
-              }
+              for (int i = 0; i < 8; ++i) red_add_f32(d0 + (size_t)i * K * G, __uint_as_float(v[i]));
             }
           }
         }
       }
-      ++n_flush;
       tc5::fence_before_sync();
     };
 
-    int tile = part;
-    if (tile < w.ntiles) {
-      load_inputs(tile);
-      if (wt < 128) sp[wt] = mypos;
-      worker_bar();
-      if (K > 1) build_p(tile);
-      publish(p_ready);
-      store_v0(0); publish(&v_ready[0]);
-      store_v0(1); publish(&v_ready[1]);
-      store_xt();
-    }
-    int n_items = 0;
-    for (; tile < w.ntiles; tile += nparts, ++n_items) {
-      const int next = tile + nparts;
-      const bool has_next = next < w.ntiles;
-      if (has_next) load_inputs(next);
-      for (int k = 0; k + 1 < K; ++k) {
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          tc5::mbar_wait(&mma_done[s], par_md[s]); par_md[s] ^= 1;
-          tc5::fence_after_sync();
-          const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + TM_HOP + s * L::SS + hf * L::CPT;
-          unsigned char* base = Vb + s * L::SLAB + (hf * (L::CPT / 8)) * L::PW + r * 16;
-          if constexpr (L::CPT == 16) {
-            uint32_t v[16];
-            tc5::tmem_ld16(taddr, v);
-            tc5::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 2; ++c) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[c * 8 + i]);
-              store_chunk3(base + c * L::PW, L::PLANE, f);
-            }
-          } else {
-            uint32_t v[8];
-            tc5::tmem_ld8u(taddr, v);
-            tc5::tmem_ld_wait();
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
-            store_chunk3(base, L::PLANE, f);
-          }
-          publish(&v_ready[s]);
+    // One leading iteration (it == -1) prepares the first tile; afterwards iteration `it` serves tile `tile`
+    // (write-backs) and prepares `next`.
+    int tile = t_begin, next = t_begin, it = -1, vbase = 0, n_items = 0;
+    if (next < t_end) load_pos(next);
+    while (true) {
+      const bool live = it >= 0;
+      const bool has_next = next < t_end;
+      if (!live && !has_next) break;
+      const int pbuf = (it + 1) & 1;
+      int xt_slot = 0;
+      bool p_done = false;
+      if (has_next) {
+        if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;
+        worker_bar();
+        if (next + 1 < t_end) load_pos(next + 1);
+        if (wt == 0 && !w.no_prefetch) {   // L2 prefetch runs two tiles ahead
+          if (!live) prefetch_tile(next);
+          if (next + 1 < t_end) prefetch_tile(next + 1);
         }
       }
-      if (has_next) {
-        if (wt < 128) sp[wt] = mypos;
-        worker_bar();
-        if (K > 1) build_p(next);
-        publish(p_ready);
-      }
+      // ---- write-backs of the K-1 hops; the next tile's x columns and P are prepared in the gaps ----------
+      const int nwb = live ? K - 1 : 0;
+      bool v0_loaded = false;
+#pragma unroll 1
+      for (int k = 0; k < nwb; ++k) {
+        // next tile's V_0 pieces: requested two write-backs ahead of their use so that the (long) memory latency
+        // overlaps the remaining taps of the live tile
+        if (has_next && !v0_loaded && k + 2 >= nwb) { load_v0(next); v0_loaded = true; }
+        GFC_ESTAMP(400);
+        tc5::mbar_wait(hop_done, par_hd); par_hd ^= 1;
+        tc5::fence_after_sync();
+        GFC_ESTAMP(401);
+        unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (hf * (L::CPT / 8)) * L::PW + r * 16;
+        const uint32_t taddr = tm_lane + TM_HOP + hf * L::CPT;
+#pragma unroll 1
+        for (int c = 0; c < L::CPT / 8; ++c) {
+          uint32_t v[8];
+          tc5::tmem_ld8u(taddr + c * 8, v);
+          tc5::tmem_ld_wait();
+          float f[8];
 #pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        tc5::mbar_wait(&mma_done[s], par_md[s]); par_md[s] ^= 1;
-        if (has_next) { store_v0(s); publish(&v_ready[s]); }
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
+          store_chunk3(base + c * L::PW, L::PLANE, f);
+        }
+        publish(v_ready);
+        GFC_ESTAMP(402);
+        if (has_next) {
+          if (K > 1 && k < 2) {
+            build_p_part(next, pbuf, 4 * k, 4 * k + 4);
+            if (k == 1 || nwb == 1) {
+              if (nwb == 1) build_p_part(next, pbuf, 4, 8);
+              publish(p_ready); p_done = true;
+            }
+          }
+          if (xt_slot < 4) load_xt_slot(next, xt_slot++);
+          if (k == nwb - 1) { while (xt_slot < 4) load_xt_slot(next, xt_slot++); }
+        }
+        GFC_ESTAMP(403);
       }
-      // every dH product of this tile has completed (mma_done[1] of the last tap)
-      if (!has_next || ((n_items + 1) % w.flush_every) == 0) flush(true);
+      if (has_next) {
+        if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 8); publish(p_ready); }
+        while (xt_slot < 4) load_xt_slot(next, xt_slot++);
+        // V_0 of the next tile goes into the ring buffer after the live tile's last one (free: its last reader
+        // was tap K-3 of the live tile, which completed before the hop result of tap K-2 was signalled)
+        GFC_ESTAMP(404);
+        if (!v0_loaded) load_v0(next);
+        GFC_ESTAMP(405);
+        store_v0(Vb + ((vbase + (live ? K : 0)) % 3) * L::VBUF);
+        publish(v_ready);
+        GFC_ESTAMP(406);
+      }
+      if (live) {
+        tc5::mbar_wait(item_done, par_id); par_id ^= 1;   // every dH product of the live tile has completed
+        GFC_ESTAMP(407);
+        ++n_items;
+        if (!has_next || (n_items % w.flush_every) == 0) flush();
+        GFC_ESTAMP(408);
+        vbase = (vbase + K) % 3;
+      }
       if (has_next) store_xt();
+      GFC_ESTAMP(409);
+      if (!has_next) break;
+      tile = next;
+      next += 1;
+      ++it;
     }
-    if (n_items == 0) flush(false);
     if (w.dbp) {
 #pragma unroll
-      for (int s = 0; s < 2; ++s)
-#pragma unroll
-        for (int i = 0; i < L::CPT; ++i) atomicAdd(dbs + s * L::SS + hf * L::CPT + i, dbacc[s][i]);
+      for (int i = 0; i < 4; ++i) atomicAdd(dbs + 4 * (lane % PPR) + i, dbacc[i]);
       worker_bar();
       if (wt < FH) w.dbp[(size_t)part * F + fh * FH + wt] = dbs[wt];
     }
@@ -1033,6 +1122,7 @@ static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
 
 int launch_wide(const WideArgs& a0, int G, int F, int mode, cudaStream_t st) {
   WideArgs a = a0;
+  a.no_prefetch = g_wide_no_prefetch;
   a.gpc = 128 / a.N;
   if (a.gpc > a.B) a.gpc = a.B;
   a.ntiles = ceil_div(a.B, a.gpc);
@@ -1064,8 +1154,8 @@ static int launch_wide_dh_t(const WideDhArgs& a0, int* nparts_out, cudaStream_t 
 
 // feature slice: the K+1 [128 x FH] fp32 regions (K accumulators + the hop result) share 320 TMEM columns
 static int dh_slice(int F, int K) {
-  if ((K + 1) * F <= 320) return F;
-  if ((K + 1) * (F / 2) <= 320 && (F / 2) % 32 == 0) return F / 2;
+  if ((K + 1) * 64 <= 320 && F % 64 == 0) return 64;
+  if ((K + 1) * 32 <= 320 && F % 32 == 0) return 32;
   return 0;
 }
 
@@ -1097,16 +1187,17 @@ int launch_wide_dh(const WideDhArgs& a0, int G, int F, cudaStream_t st) {
   a.ntiles = ceil_div(a.B, a.gpc);
   a.nparts = wide_dh_nparts(a.B, a.N, F, a.K);
   if (a.flush_every <= 0) a.flush_every = g_wide_flush_every;
+  a.no_prefetch = g_wide_no_prefetch;
   const int fhs = dh_slice(F, a.K);
 #define GFC_DH_CASE(g, f, s) if (G == g && F == f && fhs == s) return launch_wide_dh_t<g, f, s>(a, nullptr, st);
   GFC_DH_CASE(128, 128, 64)
-  GFC_DH_CASE(128, 128, 128)
+  GFC_DH_CASE(128, 128, 32)
   GFC_DH_CASE(64, 64, 64)
   GFC_DH_CASE(64, 64, 32)
   GFC_DH_CASE(128, 64, 64)
   GFC_DH_CASE(128, 64, 32)
   GFC_DH_CASE(64, 128, 64)
-  GFC_DH_CASE(64, 128, 128)
+  GFC_DH_CASE(64, 128, 32)
 #undef GFC_DH_CASE
   set_error("launch_wide_dh: unsupported shape G=%d F=%d K=%d", G, F, a.K);
   return GFC_ERR_UNSUPPORTED;

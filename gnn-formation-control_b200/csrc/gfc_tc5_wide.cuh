@@ -17,6 +17,7 @@ struct WideArgs {
   int gpc, ntiles;         // filled by launch_wide
   int act;
   float slope;
+  int no_prefetch;         // experiment: skip the L2 bulk prefetch
   int tma_out;             // filled by launch_wide: the y tile leaves through the TMA store engine
   long long* dbg;          // optional clock stamps of CTA 0 (issuer at [0..), worker warp 2 at [2048..)), else null
 };
@@ -33,10 +34,13 @@ struct WideDhArgs {
   int B, N, K;
   int gpc, ntiles, nparts; // filled by launch_wide_dh
   int flush_every;         // tiles chained into the TMEM accumulators between drains (0 = default)
+  int no_prefetch;         // experiment: skip the L2 bulk prefetch
+  long long* dbg;          // optional clock stamps of CTA 0
   int act;
   float slope;
 };
 extern int g_wide_flush_every;
+extern int g_wide_no_prefetch;
 bool wide_dh_supported(int N, int G, int F, int K);
 int wide_dh_nparts(int B, int N, int F, int K);   // number of partial buffers launch_wide_dh writes
 int launch_wide_dh(const WideDhArgs& a, int G, int F, cudaStream_t st);

@@ -17,8 +17,9 @@ def run():
         hp.fwd(0, st)
     else:
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        dh = which == "dh"
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(hp.x[0]), C.ptr(hp.pos[0]), RADIUS, hp.mode, C.ptr(hp.h), C.ptr(hp.y[0]),
-                                         C.ptr(hp.dY[0]), C.ptr(hp.dX[0]), null, null, B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
+                                         C.ptr(hp.dY[0]), null if dh else C.ptr(hp.dX[0]), C.ptr(hp.dH) if dh else null, C.ptr(hp.db) if dh else null, B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
                                          C.PREC_FP32_3XTF32, C.ptr(hp.wsb), hp.nbb, st), "bwd")
 for _ in range(2): run()
 torch.cuda.synchronize()
@@ -31,7 +32,7 @@ names = {100: "I wait w_ready s0", 101: "I wait w_ready s1", 110: "I got w_ready
          130: "I h_full 0", 131: "I h_full 1", 132: "I h_full 2", 133: "I h_full 3", 140: "I commit s0", 141: "I commit s1",
          200: "W wait mma_done s0", 201: "W wait mma_done s1", 210: "W got mma_done s0", 211: "W got mma_done s1", 220: "W stored s0", 221: "W stored s1",
          230: "W published s0", 231: "W published s1", 240: "W tail start", 241: "W P built", 250: "W last mma_done s0", 251: "W last mma_done s1",
-         242: "W after worker_bar", 244: "W grp0 pairs", 245: "W grp0 st16", 246: "W grp1 pairs", 247: "W grp1 st16", 248: "W st_wait", 243: "W build_p done", 271: "W got out_full", 272: "W epi iter", 273: "W epi tmem loaded", 260: "W w0 stored s0", 261: "W w0 stored s1", 270: "W epilogue done"}
+         242: "W after worker_bar", 244: "W grp0 pairs", 245: "W grp0 st16", 246: "W grp1 pairs", 247: "W grp1 st16", 248: "W st_wait", 243: "W build_p done", 271: "W got out_full", 272: "W epi iter", 273: "W epi tmem loaded", 300: "I wait p_ready", 301: "I got p_ready", 310: "I wait v_ready", 311: "I got v_ready", 312: "I hop issued", 313: "I got x_ready", 314: "I dH issued", 400: "W wait hop_done", 401: "W got hop_done", 402: "W wrote back", 403: "W side jobs done", 404: "W loop done", 405: "W v0 loaded", 406: "W v0 stored", 407: "W item_done", 408: "W flushed", 409: "W xt stored", 260: "W w0 stored s0", 261: "W w0 stored s1", 270: "W epilogue done"}
 ev = []
 for base in (0, 2048):
     a = t[base:base + 2000].reshape(-1, 2)
