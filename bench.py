@@ -190,11 +190,26 @@ class HotPath:
                                          C.PREC_FP32_3XTF32, C.ptr(self.wsb), self.nbb, st), "gfc_filter_bwd_pos")
         return C.last_launch_count()
 
+    def enable_peer_exchange(self, px):
+        """data-parallel: the backward's second-stage reduction becomes the fused reduce + one-shot all-reduce
+        over NVLink peer memory (gfc_filter_bwd_pos_dp) instead of reduce kernel + NCCL all-reduce"""
+        self.px = px
+
+    def bwd_dp(self, i, st):
+        C, w, px = self.C, self.w, self.px
+        B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        C.check(C.lib.gfc_filter_bwd_pos_dp(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
+                                            C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.grads),
+                                            B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32,
+                                            C.ptr(self.wsb), self.nbb, px.buf_ptrs, px.sig_ptrs, px.rank, px.world,
+                                            1.0, st), "gfc_filter_bwd_pos_dp")
+        return C.last_launch_count()
+
     def step(self, i):
         st = self.stream()
         n = self.fwd(i, st)
         if self.train:
-            n += self.bwd(i, st)
+            n += self.bwd_dp(i, st) if getattr(self, "px", None) is not None else self.bwd(i, st)
         self.launches_per_step = n
         return n
 
@@ -209,7 +224,7 @@ def ring_size(w):
 def timed_steps(torch, hp, steps, warmup, world, dist, use_graph):
     """W warm-up + exactly K timed steps; returns ms for the K steps (this rank)."""
     ring = hp.ring
-    allreduce = world > 1 and hp.train
+    allreduce = world > 1 and hp.train and getattr(hp, "px", None) is None   # NCCL only without the fused exchange
 
     def one(i):
         hp.step(i % ring)
@@ -464,6 +479,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python (no CUDA graph)")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: plain NCCL all-reduce instead of the fused peer exchange")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of the other configs")
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU baseline work")
     args = ap.parse_args()
@@ -505,6 +521,17 @@ def main():
         sampler.start()
     ring = ring_size(w)
     hp = HotPath(w, dev, ring)
+    collective = "none"
+    if world > 1 and w["train"]:
+        collective = "NCCL all-reduce of the flat [dH|db] bucket every step"
+        if not args.nccl:
+            try:
+                import gnnfc
+                hp.enable_peer_exchange(gnnfc.PeerExchange(hp.grads.numel(), dev))
+                collective = ("fused into the gradient-reduction kernel: one-shot all-reduce of the flat [dH|db] bucket "
+                              "over NVLink peer memory (symmetric memory, P2P stores + flags)")
+            except Exception as ex:   # symmetric memory unavailable on this box: the NCCL collective still is
+                sys.stderr.write("bench: peer exchange unavailable (%s); using NCCL\n" % str(ex)[:160])
     use_graph = not args.no_graph
     ms = timed_steps(torch, hp, steps, warmup, world, dist, use_graph)
     launches = hp.launches_per_step * steps
@@ -583,7 +610,7 @@ def main():
                                 l2="inputs rotate through a ring of %d distinct batches = %.0f MB (> 126 MB L2)"
                                    % (ring, ring * w["B"] * bpg["total"] / 1e6),
                                 launch="CUDA graph replay" if getattr(hp, "graph_used", False) else "python loop",
-                                collective="none" if world == 1 else "NCCL all-reduce of the flat [dH|db] bucket every step"),
+                                collective=collective),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, extra=extra)
         print(json.dumps(line))
     if world > 1:

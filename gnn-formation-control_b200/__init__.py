@@ -12,8 +12,8 @@ from . import _cabi
 from ._cabi import GfcError, version, last_launch_count
 from .gso import build_gso, build_csr, SparseGSO
 from .graph_filter import GraphFilterBatch, graph_filter
-from .dp import GradBucket, shard_range, broadcast_parameters
+from .dp import GradBucket, PeerExchange, shard_range, broadcast_parameters
 
 __all__ = ["GraphFilterBatch", "graph_filter", "build_gso", "build_csr", "SparseGSO",
-           "GradBucket", "shard_range", "broadcast_parameters", "GfcError", "version",
+           "GradBucket", "PeerExchange", "shard_range", "broadcast_parameters", "GfcError", "version",
            "last_launch_count"]

@@ -42,6 +42,11 @@ SIGNATURES = {
     "gfc_filter_fwd_pos": (_i, [_p, _p, _d, _i, _p, _p, _p] + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_filter_bwd": (_i, [_p] * 8 + [_i] * 6 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_filter_bwd_pos": (_i, [_p, _p, _d, _i] + [_p] * 6 + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),
+    "gfc_dp_exchange_bytes": (_sz, [_i, _i]),
+    "gfc_dp_signal_bytes": (_sz, [_i, _i]),
+    "gfc_filter_bwd_pos_dp": (_i, [_p, _p, _d, _i] + [_p] * 5 + [_i] * 5 + [_i, _f, _i, _p, _sz, _p, _p, _i, _i, _f, _p]),
+    "gfc_filter_bwd_dp": (_i, [_p] * 7 + [_i] * 6 + [_i, _f, _i, _p, _sz, _p, _p, _i, _i, _f, _p]),
+    "gfc_dp_allreduce": (_i, [_p, _p, _i, _p, _p, _i, _i, _f, _p]),
     "gfc_csr_count": (_i, [_p, _i, _i, _d, _i, _p, _p]),
     "gfc_csr_scan": (_i, [_p, _i, _i, _p, _p]),
     "gfc_csr_fill": (_i, [_p, _i, _i, _d, _i, _p, _i64, _p, _p, _p]),

@@ -4,6 +4,7 @@
 #include "gfc_tile.cuh"
 #include "gfc_generic.cuh"
 #include "gfc_tc5_wide.cuh"
+#include "gfc_dp.cuh"
 #include <string.h>
 #include <math.h>
 
@@ -206,10 +207,12 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
 }
 
 // ---- backward -----------------------------------------------------------------
+// dp != nullptr: dH / db are the two halves of one flat bucket (db == dH + F*E*K*G) and the second-stage
+// reduction is fused with the all-reduce over peer memory (gfc_dp.cu)
 static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, const float* h, const float* yout,
                            const float* dY, float* dX, float* dH, float* db,
                            int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
-                           void* ws, size_t ws_bytes, cudaStream_t st) {
+                           void* ws, size_t ws_bytes, cudaStream_t st, const DpCtx* dp = nullptr) {
   launch_counter() = 0;
   int rc = check_common(fn, B, N, G, F, K, E, act, prec);
   if (rc) return rc;
@@ -217,10 +220,12 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   if (B == 0) {
     if (dH) GFC_CUDA_TRY(cudaMemsetAsync(dH, 0, nH * sizeof(float), st));
     if (db) GFC_CUDA_TRY(cudaMemsetAsync(db, 0, (size_t)F * sizeof(float), st));
+    if (dp) return launch_reduce_allreduce(dH, 1, (int)nH, db, 1, F, dH, *dp, st);
     return GFC_OK;
   }
   GFC_REQUIRE(h && dY, GFC_ERR_BAD_ARG, "%s: NULL tensor pointer", fn);
   GFC_REQUIRE(!dH || x, GFC_ERR_BAD_ARG, "%s: x is required for dH", fn);
+  GFC_REQUIRE(!dp || (dH && db && db == dH + nH), GFC_ERR_BAD_ARG, "%s: the dp bucket must be contiguous [dH | db]", fn);
   GFC_REQUIRE(act == GFC_ACT_NONE || yout, GFC_ERR_BAD_ARG, "%s: y_out is required with a fused activation", fn);
   GFC_REQUIRE(gs.kind == GSRC_DENSE ? gs.S != nullptr : gs.pos != nullptr, GFC_ERR_BAD_ARG, "%s: NULL graph source", fn);
   if (!dX && !dH && !db) return GFC_OK;
@@ -275,6 +280,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       rc = launch_wide_dh(da, G, F, st);
       if (rc) return rc;
       if (g_skip_grad_reduce) return GFC_OK;
+      if (dp) return launch_reduce_allreduce(dhp, np, (int)nH, dbp, np, F, dH, *dp, st);
       return launch_reduce_parts(dhp, np, (int)nH, dH, db ? dbp : nullptr, np, F, db, st);
     }
     if (!p.h_smem && a.dX) {
@@ -288,6 +294,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_tile_bwd(a, gs.kind, st);
     if (rc) return rc;
     if (g_skip_grad_reduce) return GFC_OK;  // profiling aid, see gfc_set_option
+    if (dp) return launch_reduce_allreduce(a.dHp, p.nparts, (int)nH, a.dbp, p.grid, F, dH, *dp, st);
     return launch_reduce_parts(dH ? a.dHp : nullptr, p.nparts, (int)nH, dH,
                                db ? a.dbp : nullptr, p.grid, F, db, st);
   }
@@ -345,6 +352,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_xpose_out(Zw, dX, B, N, G, E, K, st);
     if (rc) return rc;
   }
+  if (dp) return launch_reduce_allreduce(dH, 1, (int)nH, db, 1, F, dH, *dp, st);
   return GFC_OK;
 }
 
@@ -449,6 +457,42 @@ extern "C" int gfc_filter_bwd_pos(const float* x, const float* pos, double radiu
   GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
   return filter_bwd_impl("gfc_filter_bwd_pos", gs, x, h, y_out, dY, dX, dH, db, B, N, G, F, K, 1, act, slope,
                          precision, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- (e) data-parallel variants: gradients leave through the fused reduce + all-reduce kernel --------
+extern "C" int gfc_filter_bwd_pos_dp(const float* x, const float* pos, double radius, int mode, const float* h,
+                                     const float* y_out, const float* dY, float* dX, float* grads,
+                                     int B, int N, int G, int F, int K, int act, float slope, int precision,
+                                     void* workspace, size_t workspace_bytes,
+                                     void* const* peer_buf, void* const* peer_sig, int rank, int world, float scale,
+                                     void* stream) {
+  GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
+  DpCtx dp{peer_buf, peer_sig, rank, world, scale};
+  if (!grads) { set_error("gfc_filter_bwd_pos_dp: NULL gradient bucket"); return GFC_ERR_BAD_ARG; }
+  return filter_bwd_impl("gfc_filter_bwd_pos_dp", gs, x, h, y_out, dY, dX, grads, grads + (size_t)F * K * G,
+                         B, N, G, F, K, 1, act, slope, precision, workspace, workspace_bytes, (cudaStream_t)stream, &dp);
+}
+
+extern "C" int gfc_filter_bwd_dp(const float* x, const float* S, const float* h, const float* y_out,
+                                 const float* dY, float* dX, float* grads,
+                                 int B, int N, int G, int F, int K, int E, int act, float slope, int precision,
+                                 void* workspace, size_t workspace_bytes,
+                                 void* const* peer_buf, void* const* peer_sig, int rank, int world, float scale,
+                                 void* stream) {
+  GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
+  DpCtx dp{peer_buf, peer_sig, rank, world, scale};
+  if (!grads) { set_error("gfc_filter_bwd_dp: NULL gradient bucket"); return GFC_ERR_BAD_ARG; }
+  return filter_bwd_impl("gfc_filter_bwd_dp", gs, x, h, y_out, dY, dX, grads, grads + (size_t)F * E * K * G,
+                         B, N, G, F, K, E, act, slope, precision, workspace, workspace_bytes, (cudaStream_t)stream, &dp);
+}
+
+/* all-reduce of an arbitrary flat fp32 bucket through the same kernel (in place allowed) */
+extern "C" int gfc_dp_allreduce(const float* in, float* out, int n, void* const* peer_buf, void* const* peer_sig,
+                                int rank, int world, float scale, void* stream) {
+  launch_counter() = 0;
+  GFC_REQUIRE(in && out && n > 0, GFC_ERR_BAD_ARG, "gfc_dp_allreduce: bad arguments");
+  DpCtx dp{peer_buf, peer_sig, rank, world, scale};
+  return launch_reduce_allreduce(in, 1, n, nullptr, 0, 0, out, dp, (cudaStream_t)stream);
 }
 
 // ---- (d) CSR variant: workspace pipeline with SpMM hops -------------------------

@@ -127,7 +127,7 @@ tc5_fwd_kernel(const TileArgs a) {
       __syncthreads();
       if (k == 0 && tile == (int)blockIdx.x) GFC_STAMP(a, 1);
       if (k == 1 && tile == (int)blockIdx.x) GFC_STAMP(a, 14);
-      if (tid == 0) {
+      if (warp == 0 && tc5::elect_one()) {
         tc5::fence_after_sync();
         const uint32_t a_hi = a_base + (uint32_t)((buf * 2) * L::A_TERM * 4);
         const uint32_t a_lo = a_hi + (uint32_t)(L::A_TERM * 4);

@@ -74,7 +74,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 
 // exact fp64 rule, kept out of line so the (rare) rounding-band case is a real branch and the fp64 /
 // conversion instructions are not if-converted into every pair test
-__device__ __noinline__ bool wide_adjacent_exact(float ax, float ay, float bx, float by, double thr) {
+static __device__ __noinline__ bool wide_adjacent_exact(float ax, float ay, float bx, float by, double thr) {
   return sqdist64(ax, ay, bx, by) <= thr;
 }
 __device__ __forceinline__ bool wide_adjacent(float2 a, float2 b, double thr, float thr_lo, float thr_hi) {

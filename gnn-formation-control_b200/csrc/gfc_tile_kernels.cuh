@@ -146,13 +146,18 @@ __device__ __forceinline__ void store_dx_tile(const float* __restrict__ Zs, floa
   }
 }
 
-// adjacency decision for one pair: fp32 screen, fp64 rule inside the rounding band
+// adjacency decision for one pair: fp32 screen, fp64 rule inside the rounding band.  The exact rule is
+// kept out of line so that the (rare) band case is a real branch: if-converted, its fp64 and conversion
+// instructions ran for every pair and dominated the GSO phase (profiles/r1).
+static __device__ __noinline__ bool pair_adjacent_exact(float xi, float yi, float xj, float yj, double thr) {
+  return sqdist64(xi, yi, xj, yj) <= thr;
+}
 __device__ __forceinline__ bool pair_adjacent(float xi, float yi, float xj, float yj, const TileArgs& a) {
   const float dx = xi - xj, dy = yi - yj;
   const float s = fmaf(dx, dx, dy * dy);
   if (s < a.thr_lo) return true;
   if (s > a.thr_hi) return false;
-  return sqdist64(xi, yi, xj, yj) <= a.thr;
+  return pair_adjacent_exact(xi, yi, xj, yj, a.thr);
 }
 
 // GSO tile Ss[j][m][n] from dense S (GSRC_DENSE) or rebuilt from positions.

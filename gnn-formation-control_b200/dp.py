@@ -72,3 +72,48 @@ def broadcast_parameters(params, src=0, group=None):
         return
     for p in params:
         dist.broadcast(p.data, src=src, group=group)
+
+
+class PeerExchange:
+    """Peer-mapped exchange + signal buffers for the fused gradient reduction / all-reduce kernel
+    (``gfc_filter_bwd*_dp``, ``gfc_dp_allreduce``; csrc/gfc_dp.cu).
+
+    The buffers live in CUDA symmetric memory (``torch.distributed._symmetric_memory``): every rank allocates the
+    same sizes, the rendezvous maps all of them into every process, and the kernels store into / poll them
+    directly over NVLink.  ``world == 1`` (or no process group) needs no mapping: the rank talks to itself."""
+
+    def __init__(self, numel, device, group=None):
+        import ctypes as ct
+        from . import _cabi as C
+        self.C, self.n = C, int(numel)
+        init = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if init else 0
+        self.world = dist.get_world_size(group) if init else 1
+        nb = C.lib.gfc_dp_exchange_bytes(self.n, self.world)
+        ns = C.lib.gfc_dp_signal_bytes(self.n, self.world)
+        assert nb > 0 and ns > 0, "bucket / world size not supported by the peer exchange"
+        self.bytes = nb + ns
+        if self.world > 1:
+            import torch.distributed._symmetric_memory as symm
+            self.mem = symm.empty(self.bytes, dtype=torch.uint8, device=device)
+            self.mem.zero_()
+            torch.cuda.synchronize(device)
+            self.handle = symm.rendezvous(self.mem, group=(group or dist.group.WORLD))
+            bases = [int(p) for p in self.handle.buffer_ptrs]
+            dist.barrier(group)
+        else:
+            self.mem = torch.zeros(self.bytes, dtype=torch.uint8, device=device)
+            self.handle = None
+            bases = [self.mem.data_ptr()]
+        arr = ct.c_void_p * self.world
+        self.buf_ptrs = arr(*[ct.c_void_p(b) for b in bases])
+        self.sig_ptrs = arr(*[ct.c_void_p(b + nb) for b in bases])
+
+    def allreduce_(self, flat, scale=1.0, stream=None):
+        """in-place all-reduce of a flat fp32 CUDA tensor (sum * scale) through the fused kernel"""
+        C = self.C
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() == self.n
+        st = C.ct.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream if stream is None else stream)
+        C.check(C.lib.gfc_dp_allreduce(C.ptr(flat), C.ptr(flat), self.n, self.buf_ptrs, self.sig_ptrs,
+                                       self.rank, self.world, float(scale), st), "gfc_dp_allreduce")
+        return flat

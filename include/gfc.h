@@ -154,6 +154,42 @@ int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const int32_t* col
                        int act, float slope, int precision,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- (e) data-parallel training: fused gradient reduction + all-reduce ------ *
+ * The reference is single-GPU (suhaas_agent.py:19); data parallelism shards the
+ * batch of graphs over ranks and sums the flat gradient bucket [dH | db].  These
+ * entry points replace "second-stage reduction kernel + ncclAllReduce" by ONE
+ * kernel that reduces this rank's per-CTA partials and exchanges the result over
+ * NVLink peer memory (one-shot: every rank stores its slice into every peer's
+ * exchange buffer, signals, waits for all peers, sums in rank order -> every rank
+ * holds bit-identical gradients).
+ *   peer_buf[r] / peer_sig[r]: device pointers, valid on THIS device, to rank r's
+ *   exchange / signal buffer (peer-mapped memory, e.g. torch symmetric memory or
+ *   cudaIpc handles), each of gfc_dp_exchange_bytes / gfc_dp_signal_bytes for the
+ *   bucket size n = F*E*K*G + F, zero-initialised once before the first call.
+ *   grads: the bucket [dH (F*E*K*G) | db (F)], written on every rank.
+ *   Every rank of the group must make the same sequence of calls.              */
+size_t gfc_dp_exchange_bytes(int n, int world);
+size_t gfc_dp_signal_bytes(int n, int world);
+int gfc_filter_bwd_pos_dp(const float* x, const float* pos, double radius, int mode,
+                          const float* h, const float* y_out, const float* dY,
+                          float* dX, float* grads,
+                          int B, int N, int G, int F, int K,
+                          int act, float slope, int precision,
+                          void* workspace, size_t workspace_bytes,
+                          void* const* peer_buf, void* const* peer_sig,
+                          int rank, int world, float scale, void* stream);
+int gfc_filter_bwd_dp(const float* x, const float* S, const float* h, const float* y_out,
+                      const float* dY, float* dX, float* grads,
+                      int B, int N, int G, int F, int K, int E,
+                      int act, float slope, int precision,
+                      void* workspace, size_t workspace_bytes,
+                      void* const* peer_buf, void* const* peer_sig,
+                      int rank, int world, float scale, void* stream);
+/* all-reduce (sum * scale) of any flat fp32 bucket through the same kernel; in == out allowed */
+int gfc_dp_allreduce(const float* in, float* out, int n,
+                     void* const* peer_buf, void* const* peer_sig,
+                     int rank, int world, float scale, void* stream);
+
 /* ---- introspection used by bench.py / tests -------------------------------- *
  * Which kernel family a shape dispatches to: 1 = fused shared-memory tile
  * kernel, 2 = workspace pipeline (dense hops), 0 = unsupported.               */
