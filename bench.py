@@ -320,7 +320,7 @@ def kernel_alone_ms(torch, hp, which, reps):
             C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 0), "gfc_set_option")
 
 
-def e2e_steps(torch, w, dev, steps, warmup, world, dist):
+def e2e_steps(torch, w, dev, steps, warmup, world, dist, use_graph=True):
     """same metric through the public module API with HOST (pinned) inputs.  Every step copies that
     step's positions + x host->device (copy stream, double-buffered so the copy of step s+1 overlaps
     the compute of step s), runs addPositions + forward + loss + backward through the drop-in
@@ -377,12 +377,68 @@ def e2e_steps(torch, w, dev, steps, warmup, world, dist):
         hloss[i].copy_(loss.detach().reshape(1), non_blocking=True)
         done[i].record(main)
 
+    # The training step (addPositions + forward + loss + backward [+ gradient exchange] + loss read-back) is
+    # captured once per device buffer set with torch.cuda.graph — PyTorch's whole-step capture, the way a user
+    # removes Python launch overhead from a fixed-shape loop — and replayed; the H2D copies of the next step's
+    # inputs stay outside the graphs on the copy stream so that they overlap the current step.
+    graphs = None
+    if use_graph:
+        try:
+            xin_static = [dx[i].detach().requires_grad_(True) for i in range(2)]
+
+            def body(i):
+                m.addPositions(dpos[i], RADIUS, w["mode"])
+                if w["train"]:
+                    m.zero_grad(set_to_none=True)
+                    xin_static[i].grad = None
+                    y = m(xin_static[i])
+                    loss = y.square().mean()
+                    loss.backward()
+                    if bucket is not None:
+                        bucket.sync_grads()
+                else:
+                    with torch.no_grad():
+                        y = m(dx[i])
+                        if layers2:
+                            m2.addPositions(dpos[i], RADIUS, w["mode"])
+                            y = m2(y)
+                        loss = y.mean()
+                hloss[i].copy_(loss.detach().reshape(1), non_blocking=True)
+
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    body(0); body(1)
+            main.wait_stream(side)
+            torch.cuda.synchronize()
+            graphs = []
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    body(i)
+                graphs.append(g)
+            torch.cuda.synchronize()
+        except Exception as ex:
+            sys.stderr.write("bench: e2e CUDA-graph capture failed (%s); eager module calls\n" % str(ex)[:160])
+            graphs = None
+            torch.cuda.synchronize()
+
+    def compute_graphed(s):
+        i = s % 2
+        main.wait_event(ready[i])
+        graphs[i].replay()
+        free[i].record(main)
+        done[i].record(main)
+
+    step_fn = compute_graphed if graphs is not None else compute
+
     def run(n):
         prefetch(0)
         for s in range(n):
             if s + 1 < n:
                 prefetch(s + 1)
-            compute(s)
+            step_fn(s)
             if s > 0:   # result of the previous step: wait for ITS copy only, step s is already enqueued
                 done[(s - 1) % 2].synchronize()
                 seen.append(float(hloss[(s - 1) % 2][0]))
@@ -402,6 +458,7 @@ def e2e_steps(torch, w, dev, steps, warmup, world, dist):
         dist.barrier()
     ms = e0.elapsed_time(e1)
     h2d = hpos[0].numel() * 4 + hx[0].numel() * 4
+    e2e_steps.graphed = graphs is not None
     return ms, h2d, 4, seen[-1]
 
 
@@ -565,13 +622,15 @@ def main():
 
     # end-to-end through the module API with host buffers
     e2e_n = max(3, min(steps, 200 if w["B"] * bpg["total"] < L2_BYTES else 5))
-    e_ms, h2d, d2h, _ = e2e_steps(torch, w, dev, e2e_n, 3, world, dist)
+    e_ms, h2d, d2h, _ = e2e_steps(torch, w, dev, e2e_n, 3, world, dist, use_graph)
     te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = dict(value=world * w["B"] * e2e_n / (float(te.item()) * 1e-3), unit="graphs/s",
                h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, steps=e2e_n,
-               api="gnnfc.GraphFilterBatch.addPositions/forward + loss.backward; pinned host inputs, H2D double-buffered on a copy stream, loss copied to pinned host every step")
+               api="gnnfc.GraphFilterBatch.addPositions/forward + loss.backward%s; pinned host inputs, H2D double-buffered "
+                   "on a copy stream every step, loss copied to pinned host every step and read by the host"
+                   % (" captured once with torch.cuda.graph and replayed" if getattr(e2e_steps, "graphed", False) else ""))
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
