@@ -48,6 +48,9 @@ WORKLOADS = {
                       "2-layer graph filter 128->128->128, K=3", B=16384, N=12, G=128, F=128, K=3, box=6.0,
                  seed=3, mode="binary_le", train=False, layers=2),
 }
+# cfg5 goes through the CSR entry points (kernel (d)): radius graph with ~16 neighbours (L = 28.3 at R = 2)
+CFG5 = dict(desc="cfg5: 1024-agent sparse swarm (radius graph, ~16 neighbours), K=5, F=32->32, CSR SpMM diffusion, "
+                 "batch 256 graphs", B=256, N=1024, G=32, F=32, K=5, box=28.3, seed=4, mode="binary_le")
 RADIUS = 2.0
 SLOPE = 0.01
 
@@ -462,6 +465,41 @@ def e2e_steps(torch, w, dev, steps, warmup, world, dist, use_graph=True):
     return ms, h2d, 4, seen[-1]
 
 
+def csr_workload(torch, dev, steps=5):
+    """cfg5 through the public module API: per step CSR build from positions (count/scan/fill), SpMM-diffusion
+    forward and backward.  Device-timed with CUDA events."""
+    import gnnfc
+    w = CFG5
+    B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+    pos = torch.from_numpy(make_positions(B, N, w["box"], w["seed"])).to(dev)
+    gen = torch.Generator(device=dev).manual_seed(w["seed"])
+    x = torch.randn(B, G, N, device=dev, generator=gen).requires_grad_(True)
+    dY = torch.randn(B, F, N, device=dev, generator=gen)
+    m = gnnfc.GraphFilterBatch(G, F, K, activation="leaky_relu").to(dev)
+
+    def step():
+        m.addSparseGSO(pos, RADIUS, w["mode"])
+        m.zero_grad(set_to_none=True); x.grad = None
+        y = m(x)
+        y.backward(dY)
+        return m.S
+
+    for _ in range(2):
+        csr = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    nnz = float(csr.rowptr[:, N].float().mean().item())
+    bytes_per_graph = 2 * (4 * (N + 1) + 4 * nnz) + 4 * N * (3 * G + 2 * F)     # SURVEY §8d, CSR read fwd+bwd
+    return dict(workload=w["desc"], value=B / (ms * 1e-3), unit="graphs/s", ms_per_step=ms, steps=steps,
+                mean_degree=nnz / N, algorithmic_GBps=B * bytes_per_graph / (ms * 1e-3) / 1e9,
+                note="workspace pipeline (Z round-trips HBM); not yet a fused kernel")
+
+
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
 def cpu_reference_step_fn(w, sample_B):
     """the reference's CPU path for one batch: vectorised GSO builder restatement +
@@ -653,6 +691,10 @@ def main():
                 torch.cuda.empty_cache()
             except Exception as ex:  # side measurement must never break the headline line
                 extra[name] = dict(error=str(ex)[:200])
+        try:
+            extra["cfg5"] = csr_workload(torch, dev)
+        except Exception as ex:
+            extra["cfg5"] = dict(error=str(ex)[:200])
 
     clocks = sampler.stop() if rank == 0 else None
     cpu = None
