@@ -130,6 +130,7 @@ static size_t wide_ws_extra(int B, int N, int G, int F, int K, int backward) {
   if (backward && wide_dh_supported(N, G, F, K)) {
     const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
     n += align_up(np * F * K * G * sizeof(float), 256) + align_up(np * F * sizeof(float), 256);
+    n += align_up((size_t)B * N * F * sizeof(float), 256);   // dY o act'(y), handed from the dX kernel to the dH kernel
   }
   return n;
 }
@@ -250,6 +251,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
+    float* wide_dpre = nullptr;
     if (dX && use_wide(gs, norm, N, G, F, K, 1, prec) && a.vec_ok && aligned16(gs.pos) && aligned16(dX)) {
       // dX on the tcgen05 path (V_k = P^k (dY o act'), dX = sum_k V_k H_k); dH / db below
       uint16_t* hp = reinterpret_cast<uint16_t*>(wsb + p.ws_bytes);
@@ -259,6 +261,12 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
       wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
       wa.B = B; wa.N = N; wa.K = K; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
+      if (dH && act != GFC_ACT_NONE && wide_dh_supported(N, G, F, K)) {
+        const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
+        wide_dpre = reinterpret_cast<float*>(wsb + p.ws_bytes + wide_pack_bytes(G, F, K) +
+                                             align_up(np * nH * sizeof(float), 256) + align_up(np * F * sizeof(float), 256));
+        wa.d_out = wide_dpre;
+      }
       rc = launch_wide(wa, G, F, 1, st);
       if (rc) return rc;
       a.dX = nullptr;
@@ -273,7 +281,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       float* dbp = reinterpret_cast<float*>(base + align_up((size_t)np * nH * sizeof(float), 256));
       WideDhArgs da{};
       da.pos = gs.pos; da.thr = a.thr; da.thr_lo = a.thr_lo; da.thr_hi = a.thr_hi;
-      da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr;
+      da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre;
       da.dHp = dhp; da.dbp = db ? dbp : nullptr;
       da.B = B; da.N = N; da.K = K; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
       GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)np * nH * sizeof(float), st));   // partials are accumulated with red.add

@@ -373,6 +373,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
             v.y = act_grad(v.y, yo.y, w.act, w.slope);
             v.z = act_grad(v.z, yo.z, w.act, w.slope);
             v.w = act_grad(v.w, yo.w, w.act, w.slope);
+            // hand dY o act'(y) to the dH kernel: it then streams ONE tensor and never waits on the mask
+            if (w.d_out && ok) *reinterpret_cast<float4*>(w.d_out + off) = v;
           }
           xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
         }
@@ -624,7 +626,7 @@ struct DhLayout {
   static constexpr int OFF_SP = OFF_P + 2 * P_BYTES;
   static constexpr int OFF_DB = OFF_SP + 2 * ROWS * 8;
   static constexpr int OFF_BAR = OFF_DB + FH * 4;
-  static constexpr int NBAR = 5;
+  static constexpr int NBAR = 6;
   static constexpr int BYTES_MIN = OFF_BAR + NBAR * 8 + 16;
   static constexpr int BYTES = BYTES_MIN < 120 * 1024 ? 120 * 1024 : BYTES_MIN;   // one CTA per SM (TMEM is taken whole)
   static constexpr int TM_X = 0;                     // 3 planes x 64 columns (128 rows, two per column)
@@ -649,7 +651,10 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   uint64_t* item_done = bars + 2;    // issuer (commit) -> workers: every MMA of the tile complete
   uint64_t* p_ready = bars + 3;
   uint64_t* x_ready = bars + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+  // V_0 of the next tile has its own barrier: a fast warp may publish it right after its last write-back, and
+  // on a shared barrier that second arrival could complete the write-back phase before a slow warp arrived
+  uint64_t* v0_ready = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
@@ -668,6 +673,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     tc5::mbar_init(item_done, 1);
     tc5::mbar_init(p_ready, kWorkerWarps);
     tc5::mbar_init(x_ready, kWorkerWarps);
+    tc5::mbar_init(v0_ready, kWorkerWarps);
     tc5::fence_mbar_init();
   }
   if (warp == 1) tc5::tmem_alloc(tmem_ptr, 512);
@@ -682,7 +688,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     if (tc5::elect_one()) {
       constexpr uint32_t kIdesc = tc5::idesc_bf16(128, FH, 0, 1);   // B = V planes, MN-major
       const uint32_t v_addr = tc5::smem_u32(Vb), p_addr = tc5::smem_u32(Pb);
-      uint32_t par_vr = 0, par_pr = 0, par_xr = 0;
+      uint32_t par_vr = 0, par_v0 = 0, par_pr = 0, par_xr = 0;
       const int ksteps = (w.gpc * N + 15) >> 4;
       int it = 0, vbase = 0;
       int nstamp = 0;
@@ -697,7 +703,8 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
           GFC_DSTAMP(310);
-          tc5::mbar_wait(v_ready, par_vr); par_vr ^= 1;
+          if (k == 0) { tc5::mbar_wait(v0_ready, par_v0); par_v0 ^= 1; }
+          else { tc5::mbar_wait(v_ready, par_vr); par_vr ^= 1; }
           tc5::fence_after_sync();
           GFC_DSTAMP(311);
           const uint32_t vs = v_addr + ((vbase + k) % 3) * L::VBUF;
@@ -775,8 +782,12 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     auto prefetch_tile = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
-      tc5::bulk_prefetch_l2(w.dY + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
-      if (w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+      if (w.dpre) {
+        tc5::bulk_prefetch_l2(w.dpre + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+      } else {
+        tc5::bulk_prefetch_l2(w.dY + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+        if (w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+      }
       if (fh == 0) tc5::bulk_prefetch_l2(w.x + (size_t)b0 * G * N, (uint32_t)gcount * G * N * 4u);
     };
     // X^T operand: x[(b0 + j), g, n] -> TMEM lane g, column (tile row / 2).  The 16x256b store shape lets a
@@ -855,21 +866,29 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         const int row = 16 * ww + RPI * i + lane / PPR;
         const bool ok = row < rows_used;
         const size_t off = ((size_t)b0 * N + row) * F + fh * FH + 4 * (lane % PPR);
-        float4 v = ldg_f32x4(w.dY + off, ok);
-        if (w.act != GFC_ACT_NONE) {
-          const float4 yo = ldg_f32x4(w.yout + off, ok);
-          v.x = act_grad(v.x, yo.x, w.act, w.slope);
-          v.y = act_grad(v.y, yo.y, w.act, w.slope);
-          v.z = act_grad(v.z, yo.z, w.act, w.slope);
-          v.w = act_grad(v.w, yo.w, w.act, w.slope);
+        float4 v;
+        if (w.dpre) {
+          v = ldg_f32x4(w.dpre + off, ok);      // not consumed before store_v0: the load latency is never exposed
+        } else {
+          v = ldg_f32x4(w.dY + off, ok);
+          if (w.act != GFC_ACT_NONE) {
+            const float4 yo = ldg_f32x4(w.yout + off, ok);
+            v.x = act_grad(v.x, yo.x, w.act, w.slope);
+            v.y = act_grad(v.y, yo.y, w.act, w.slope);
+            v.z = act_grad(v.z, yo.z, w.act, w.slope);
+            v.w = act_grad(v.w, yo.w, w.act, w.slope);
+          }
         }
         xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
-        dbacc[0] += v.x; dbacc[1] += v.y; dbacc[2] += v.z; dbacc[3] += v.w;
       }
     };
     auto store_v0 = [&](unsigned char* vbuf) {
       const int pi = lane % PPR;
       const bool odd = pi & 1;
+#pragma unroll
+      for (int i = 0; i < FH / 8; ++i) {
+        dbacc[0] += xin[4 * i]; dbacc[1] += xin[4 * i + 1]; dbacc[2] += xin[4 * i + 2]; dbacc[3] += xin[4 * i + 3];
+      }
 #pragma unroll
       for (int i = 0; i < FH / 8; i += 2) {
         float snd[4], rcv[4], own[4];
@@ -990,22 +1009,21 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
               publish(p_ready); p_done = true;
             }
           }
-          if (xt_slot < 4) load_xt_slot(next, xt_slot++);
-          if (k == nwb - 1) { while (xt_slot < 4) load_xt_slot(next, xt_slot++); }
+          if (xt_slot < 2) load_xt_slot(next, xt_slot++);   // half of X^T early; the rest once V_0's registers are free
         }
         GFC_ESTAMP(403);
       }
       if (has_next) {
         if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 8); publish(p_ready); }
-        while (xt_slot < 4) load_xt_slot(next, xt_slot++);
         // V_0 of the next tile goes into the ring buffer after the live tile's last one (free: its last reader
         // was tap K-3 of the live tile, which completed before the hop result of tap K-2 was signalled)
         GFC_ESTAMP(404);
         if (!v0_loaded) load_v0(next);
         GFC_ESTAMP(405);
         store_v0(Vb + ((vbase + (live ? K : 0)) % 3) * L::VBUF);
-        publish(v_ready);
+        publish(v0_ready);
         GFC_ESTAMP(406);
+        while (xt_slot < 4) load_xt_slot(next, xt_slot++);   // latency hides behind the last tap's MMAs / the drain
       }
       if (live) {
         tc5::mbar_wait(item_done, par_id); par_id ^= 1;   // every dH product of the live tile has completed

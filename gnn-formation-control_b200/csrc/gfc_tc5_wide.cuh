@@ -13,6 +13,7 @@ struct WideArgs {
   const uint16_t* hpack;   // taps as bf16x3 planes in ring-stage order (wide_pack_taps_kernel)
   const float* bias;       // MODE 0: [F] or null
   float* out;              // MODE 0: y [B,N,F];  MODE 1: dX [B,G,N]
+  float* d_out;            // MODE 1, optional: dY o act'(y) [B,N,F] written for the dH kernel (else null)
   int B, N, K;
   int gpc, ntiles;         // filled by launch_wide
   int act;
@@ -29,6 +30,7 @@ struct WideDhArgs {
   const float* x;          // [B,G,N]
   const float* dY;         // [B,N,F]
   const float* yout;       // [B,N,F] forward output (activation mask) or null
+  const float* dpre;       // optional [B,N,F]: dY o act'(y) already formed by the dX kernel (then dY / yout are not read)
   float* dHp;              // [nparts][F*K*G] per-CTA-group partial gradients (every element written)
   float* dbp;              // [nparts][F] or null
   int B, N, K;

@@ -17,9 +17,10 @@ def run():
         hp.fwd(0, st)
     else:
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
-        dh = which == "dh"
+        dh = which in ("dh", "both")
+        dx = which in ("bwd", "both")
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(hp.x[0]), C.ptr(hp.pos[0]), RADIUS, hp.mode, C.ptr(hp.h), C.ptr(hp.y[0]),
-                                         C.ptr(hp.dY[0]), null if dh else C.ptr(hp.dX[0]), C.ptr(hp.dH) if dh else null, C.ptr(hp.db) if dh else null, B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
+                                         C.ptr(hp.dY[0]), C.ptr(hp.dX[0]) if dx else null, C.ptr(hp.dH) if dh else null, C.ptr(hp.db) if dh else null, B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
                                          C.PREC_FP32_3XTF32, C.ptr(hp.wsb), hp.nbb, st), "bwd")
 for _ in range(2): run()
 torch.cuda.synchronize()
