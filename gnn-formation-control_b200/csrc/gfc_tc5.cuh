@@ -259,6 +259,30 @@ __device__ __forceinline__ void split_bf16x3(float x, uint32_t& p0, uint32_t& p1
 // two fp32 bit patterns -> one word of two bf16 (upper halves); `a` at the lower address
 __device__ __forceinline__ uint32_t pack_bf16_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
 
+// shared-memory matrix descriptor (no swizzle) from byte offsets
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16);
+  const uint32_t hi = ((sbo >> 4) & 0x3fffu) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+
+// 8 consecutive channels of one row -> one 16-byte chunk in each of the three planes
+__device__ __forceinline__ void store_chunk3(unsigned char* plane0, int plane_bytes, const float (&v)[8]) {
+  uint32_t a[8], b[8], c[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16x3(v[i], a[i], b[i], c[i]);
+  *reinterpret_cast<uint4*>(plane0) = make_uint4(pack_bf16_hi(a[0], a[1]), pack_bf16_hi(a[2], a[3]),
+                                                 pack_bf16_hi(a[4], a[5]), pack_bf16_hi(a[6], a[7]));
+  *reinterpret_cast<uint4*>(plane0 + plane_bytes) =
+      make_uint4(pack_bf16_hi(b[0], b[1]), pack_bf16_hi(b[2], b[3]), pack_bf16_hi(b[4], b[5]),
+                 pack_bf16_hi(b[6], b[7]));
+  *reinterpret_cast<uint4*>(plane0 + 2 * plane_bytes) =
+      make_uint4(pack_bf16_hi(c[0], c[1]), pack_bf16_hi(c[2], c[3]), pack_bf16_hi(c[4], c[5]),
+                 pack_bf16_hi(c[6], c[7]));
+}
+
+
 // panel layout helpers (see header comment); offsets in floats
 __host__ __device__ constexpr int panel_floats(int rows) { return rows * 4 + 4; }
 __device__ __forceinline__ int panel_off(int row, int col, int pfloats) {

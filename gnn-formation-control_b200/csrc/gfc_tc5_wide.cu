@@ -29,6 +29,8 @@
 #include <string.h>
 
 namespace gfc {
+using tc5::make_desc;
+using tc5::store_chunk3;
 
 template <int CIN, int COUT>
 struct WideLayout {
@@ -65,12 +67,6 @@ constexpr int kWideThreads = 320;   // warp 0: MMA issuer, warp 1: TMA producer 
 constexpr int kWorkerWarps = 8;
 int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
 int g_wide_no_prefetch = 0;    // experiment switch
-
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  const uint32_t lo = ((saddr >> 4) & 0x3fffu) | (((lbo >> 4) & 0x3fffu) << 16);
-  const uint32_t hi = ((sbo >> 4) & 0x3fffu) | (1u << 14);
-  return ((uint64_t)hi << 32) | lo;
-}
 
 // exact fp64 rule, kept out of line so the (rare) rounding-band case is a real branch and the fp64 /
 // conversion instructions are not if-converted into every pair test
@@ -151,21 +147,6 @@ __device__ __forceinline__ float ldg_cg(const float* p) {
   return v;
 }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-// 8 consecutive channels of one row -> one 16-byte chunk in each of the three planes
-__device__ __forceinline__ void store_chunk3(unsigned char* plane0, int plane_bytes, const float (&v)[8]) {
-  uint32_t a[8], b[8], c[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tc5::split_bf16x3(v[i], a[i], b[i], c[i]);
-  *reinterpret_cast<uint4*>(plane0) = make_uint4(tc5::pack_bf16_hi(a[0], a[1]), tc5::pack_bf16_hi(a[2], a[3]),
-                                                 tc5::pack_bf16_hi(a[4], a[5]), tc5::pack_bf16_hi(a[6], a[7]));
-  *reinterpret_cast<uint4*>(plane0 + plane_bytes) =
-      make_uint4(tc5::pack_bf16_hi(b[0], b[1]), tc5::pack_bf16_hi(b[2], b[3]), tc5::pack_bf16_hi(b[4], b[5]),
-                 tc5::pack_bf16_hi(b[6], b[7]));
-  *reinterpret_cast<uint4*>(plane0 + 2 * plane_bytes) =
-      make_uint4(tc5::pack_bf16_hi(c[0], c[1]), tc5::pack_bf16_hi(c[2], c[3]), tc5::pack_bf16_hi(c[4], c[5]),
-                 tc5::pack_bf16_hi(c[6], c[7]));
-}
 
 template <int CIN, int COUT, int MODE>
 __global__ void __launch_bounds__(kWideThreads, 1)

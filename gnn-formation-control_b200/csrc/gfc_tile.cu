@@ -4,6 +4,8 @@
 
 namespace gfc {
 
+int g_disable_tcgen05 = 0;
+
 __global__ void __launch_bounds__(256)
 pack_taps_kernel(const float* __restrict__ h, int F, int KG, int for_bwd, float4* __restrict__ out) {
   const int total = (KG * F) >> 1;  // float4 elements
@@ -122,6 +124,11 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   if (per_sm > cap) per_sm = cap;
   p->grid = di.sm_count * per_sm;
   if (p->grid > p->ntiles) p->grid = p->ntiles;
+  if (backward && p->variant == VAR_N8_32_32_3 && !g_disable_tcgen05) {
+    // the tcgen05 backward of this shape is persistent with one CTA per SM and keeps dH in registers
+    const int g5 = tc5_bwd_grid_n8_32_32_3(B);
+    if (g5 > 0) { p->grid = g5; p->acc_regs = 1; }
+  }
   p->nparts = p->acc_regs ? p->grid : (p->grid < 8 ? p->grid : 8);
   // workspace
   size_t off = 0;
@@ -153,8 +160,6 @@ int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_
   return GFC_OK;
 }
 
-int g_disable_tcgen05 = 0;
-
 int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st) {
   switch (a.p.variant) {
     case VAR_N8_32_32_3:
@@ -168,7 +173,9 @@ int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st) {
 
 int launch_tile_bwd(const TileArgs& a, int gsrc, cudaStream_t st) {
   switch (a.p.variant) {
-    case VAR_N8_32_32_3: return tile_bwd_n8_32_32_3(a, gsrc, st);
+    case VAR_N8_32_32_3:
+      if (!g_disable_tcgen05 && a.vec_ok && a.p.acc_regs) return tc5_bwd_n8_32_32_3(a, gsrc, st);
+      return tile_bwd_n8_32_32_3(a, gsrc, st);
     case VAR_128_128_3: return tile_bwd_128_128_3(a, gsrc, st);
     case VAR_N64_128_128_4: return tile_bwd_n64_128_128_4(a, gsrc, st);
     default: return tile_bwd_generic(a, gsrc, st);
