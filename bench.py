@@ -217,6 +217,24 @@ class HotPath:
         return n
 
 
+def tensor_flops_per_graph(w):
+    """bf16 tensor-core flops ISSUED per graph by the tcgen05 wide path (fp32 accuracy costs 6 bf16 MMAs per tap
+    product and 3 per hop product; 128-row tiles of floor(128/N) graphs, block-diagonal hop matrix) and the
+    algorithmic fp32-equivalent flops of SURVEY §8d, forward (+ backward when training)."""
+    N, G, F, K = w["N"], w["G"], w["F"], w["K"]
+    gpc = max(1, 128 // N)
+    taps = 2 * 128 * (K * G) * F * 6 / gpc                  # per graph share of a tile
+    hops = (K - 1) * 2 * 128 * (((gpc * N + 15) // 16) * 16) * G * 3 / gpc
+    issued_fwd = taps + hops
+    useful_fwd = 2 * (K - 1) * G * N * N + 2 * N * K * G * F
+    layers = w.get("layers", 1)
+    if not w["train"]:
+        return issued_fwd * layers, useful_fwd * layers
+    # backward: dX kernel = forward with the roles swapped; dH kernel = the same MMA volume again
+    useful_bwd = useful_fwd + 2 * N * K * G * F + (K - 1) * 2 * G * N * N
+    return 3 * issued_fwd, useful_fwd + useful_bwd
+
+
 def ring_size(w):
     per = w["B"] * bytes_per_graph(w)["total"]
     if per >= 2 * L2_BYTES:
@@ -687,6 +705,16 @@ def main():
                                    ms_per_step=ms2 / st2, steps=st2,
                                    dominant_kernel_GBps=w2["B"] * bytes_per_graph(w2)[wk] / (k2 * 1e-3) / 1e9,
                                    dominant_kernel_ms=k2)
+                if w2["G"] >= 64 and w2["F"] >= 64:   # tensor-pipe roofline of the tcgen05 wide path
+                    issued, useful = tensor_flops_per_graph(w2)
+                    rate = w2["B"] * st2 / (ms2 * 1e-3)
+                    tpeak = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+                    sus = float(tpeak.get("bf16_tflops_sustained", 1400.0))
+                    extra[name]["tensor"] = dict(
+                        bound="tensor", issued_bf16_tflops=rate * issued / 1e12, peak_tflops=sus,
+                        frac=rate * issued / 1e12 / sus, useful_fp32_equivalent_tflops=rate * useful / 1e12,
+                        peak_source="measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if tpeak else "fallback",
+                        note="issued = bf16x3 split products (6 MMAs per tap product, 3 per hop product) over the whole step")
                 del hp2
                 torch.cuda.empty_cache()
             except Exception as ex:  # side measurement must never break the headline line
