@@ -240,3 +240,55 @@ class GraphFilterBatch(nn.Module):
         else:
             reprString += "no GSO stored"
         return reprString
+
+
+class GraphFilter(GraphFilterBatch):
+    """``GraphFilter(G, F, K, E=1, bias=True)`` — graphML.py:1111 (``LSIGF``, graphML.py:48).
+
+    One GSO ``S [E,N,N]`` shared by every batch element: x [B,G,Nin] -> y [B,F,Nin]
+    in x's dtype (``LSIGF`` has none of ``BatchLSIGF``'s float64 casts). The shared
+    GSO is presented to the batch kernels as ``B`` identical graphs."""
+
+    def __init__(self, G, F, K, E=1, bias=True, activation=None, negative_slope=0.01,
+                 precision="fp32"):
+        super().__init__(G, F, K, E, bias, activation, negative_slope, precision, reference_dtype=False)
+        self._srcB = 0
+
+    def addGSO(self, S):
+        # same checks, same order, as graphML.py:1190-1197
+        assert len(S.shape) == 3
+        assert S.shape[0] == self.E
+        self.N = S.shape[1]
+        assert S.shape[2] == self.N
+        self.S = S
+        self._src, self._srcB = None, 0
+
+    def addPositions(self, pos, radius, mode="binary_le"):
+        raise TypeError("GraphFilter holds one GSO [E,N,N]; use GraphFilterBatch for per-sample positions")
+
+    addSparseGSO = addPositions
+
+    def _source(self, device, B=None):
+        if self._src is None or self._srcB != B:
+            S = self.S
+            assert S is not None, "call addGSO before forward"
+            _require_cuda(S, "the GSO")
+            S32 = S.detach().to(device=device, dtype=torch.float32)
+            self._src = _Src(_SRC_DENSE, S=S32.unsqueeze(0).expand(B, -1, -1, -1).contiguous())
+            self._srcB = B
+        return self._src
+
+    def forward(self, x):
+        _require_cuda(x, "x")
+        B, G, Nin = x.shape
+        assert G == self.G
+        N = self.N
+        assert Nin <= N
+        if Nin < N:  # graphML.py:1205-1209
+            x = torch.cat((x, torch.zeros(B, G, N - Nin, dtype=x.dtype, device=x.device)), dim=2)
+        src = self._source(x.device, B)
+        ymem = graph_filter(x, self.weight, self.bias, src, self.activation, self.negative_slope, self.precision)
+        u = ymem.permute(0, 2, 1)
+        if Nin < N:
+            u = torch.index_select(u, 2, torch.arange(Nin, device=u.device))  # graphML.py:1216-1217
+        return u.to(x.dtype)

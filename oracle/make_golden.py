@@ -107,6 +107,57 @@ def run_ref_filter(gml, h, b, S, x, dOut, leaky, nin=None):
     return out
 
 
+def run_ref_same_gso(gml, h, b, S, x, dOut, leaky):
+    """the reference's same-GSO layer (GraphFilter / LSIGF, graphML.py:1111, :48)."""
+    F, E, K, G = h.shape
+    m = gml.GraphFilter(G, F, K, E, bias=b is not None)
+    with torch.no_grad():
+        m.weight.copy_(torch.from_numpy(h))
+        if b is not None:
+            m.bias.copy_(torch.from_numpy(b))
+    xt = torch.from_numpy(x).clone().requires_grad_(True)
+    m.addGSO(torch.from_numpy(S))
+    y = m(xt)
+    if leaky:
+        y = torch.nn.LeakyReLU()(y)
+    (y * torch.from_numpy(dOut).to(y.dtype)).sum().backward()
+    out = dict(h=h, S=S, x=x, dOut=dOut, leaky=np.int32(leaky),
+               y=y.detach().numpy(), dX=xt.grad.numpy(), dH=m.weight.grad.numpy())
+    if b is not None:
+        out["b"] = b
+        out["db"] = m.bias.grad.numpy()
+    return out
+
+
+def same_gso_goldens():
+    gml = ri.graphml()
+    rng = np.random.default_rng(4321)
+
+    def taps(G, F, K, E, bias, seed):
+        torch.manual_seed(seed)
+        m = gml.GraphFilter(G, F, K, E, bias=bias)
+        return (m.weight.detach().numpy().copy(),
+                m.bias.detach().numpy().copy() if bias else None)
+
+    # E=2, weighted asymmetric GSO, Nin < N, LeakyReLU (float32 throughout: LSIGF has no
+    # dtype casts, so the reference's float32 parameters reject a float64 input)
+    h, b = taps(6, 5, 3, 2, True, 10)
+    S = rng.standard_normal((2, 7, 7)).astype(np.float32)
+    x = rng.standard_normal((4, 6, 5)).astype(np.float32)
+    dOut = rng.standard_normal((4, 5, 5)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "samegso_e2_nin.npz"),
+                        **run_ref_same_gso(gml, h, b, S, x, dOut, True))
+
+    # float32 in (the dtype the reference's models feed), one 8-robot normalised GSO, 32->32, K=3
+    g8 = np.load(os.path.join(OUT, "gso_expert8.npz"))
+    S = g8["s_symnorm"][5].astype(np.float32)[None]
+    h, b = taps(32, 32, 3, 1, True, 11)
+    x = rng.standard_normal((16, 32, 8)).astype(np.float32)
+    dOut = rng.standard_normal((16, 32, 8)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "samegso_cfg2_f32.npz"),
+                        **run_ref_same_gso(gml, h, b, S, x, dOut, False))
+
+
 def filter_goldens():
     gml = ri.graphml()
     rng = np.random.default_rng(1234)
@@ -185,5 +236,6 @@ if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
     gso_goldens()
     filter_goldens()
+    same_gso_goldens()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -16,11 +16,12 @@ from util import rel_err
 GSO_FILES = ["gso_expert3.npz", "gso_expert8.npz", "gso_expert12.npz", "gso_ties.npz", "gso_ties_r5.npz"]
 FILTER_FILES = ["filter_cfg1.npz", "filter_general_e2.npz", "filter_k1_nobias.npz", "filter_nin_lt_n.npz",
                 "filter_cfg2_symnorm.npz", "filter_cyclic.npz", "filter_cfg4_n12.npz"]
+SAME_GSO_FILES = ["samegso_e2_nin.npz", "samegso_cfg2_f32.npz"]
 
 
 def test_golden_inventory(golden_dir):
     have = sorted(os.path.basename(p) for p in glob.glob(os.path.join(golden_dir, "*.npz")))
-    assert have == sorted(GSO_FILES + FILTER_FILES)
+    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES)
 
 
 @pytest.mark.parametrize("name", GSO_FILES)
@@ -91,6 +92,32 @@ def test_torch_port_matches_golden(golden_dir, name):
     assert rel_err(h.grad.numpy(), g["dH"]) < 2e-7
     if b is not None:
         assert rel_err(b.grad.numpy(), g["db"]) < 2e-7
+
+
+@pytest.mark.parametrize("name", SAME_GSO_FILES)
+def test_same_gso_oracle_matches_reference_golden(golden_dir, name):
+    """GraphFilter / LSIGF (graphML.py:1111, :48): one GSO for the batch == the batch filter on
+    B copies of it; the reference runs this layer in fp32, so its outputs are fp32-rounded."""
+    import torch
+    g = np.load(os.path.join(golden_dir, name))
+    B = g["x"].shape[0]
+    gb = {k: g[k] for k in g.files}
+    gb["S"] = np.broadcast_to(g["S"], (B,) + g["S"].shape).copy()
+    y, dX, dH, db = _run_oracle(gb)
+    assert g["y"].dtype == np.float32
+    assert rel_err(y, g["y"]) < 2e-6 and rel_err(dX, g["dX"]) < 2e-6
+    assert rel_err(dH, g["dH"]) < 2e-6 and rel_err(db, g["db"]) < 2e-6
+    # op-faithful fp32 port reproduces the reference's own rounding
+    h = torch.from_numpy(g["h"]).requires_grad_(True)
+    b = torch.from_numpy(g["b"]).requires_grad_(True)
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    yt = lsigf.lsigf_same_gso_torch(h, torch.from_numpy(g["S"]), x, b)
+    assert yt.dtype == torch.float32
+    if int(g["leaky"]):
+        yt = lsigf.activation_torch(yt, lsigf.ACT_LEAKY_RELU)
+    (yt * torch.from_numpy(g["dOut"])).sum().backward()
+    assert rel_err(yt.detach().numpy(), g["y"]) < 1e-6
+    assert rel_err(x.grad.numpy(), g["dX"]) < 1e-6 and rel_err(h.grad.numpy(), g["dH"]) < 1e-6
 
 
 def test_closed_form_gradients_match_autograd():
