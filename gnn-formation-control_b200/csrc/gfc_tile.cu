@@ -20,6 +20,9 @@ __global__ void __launch_bounds__(256)
 reduce_parts_kernel(const float* __restrict__ pa, int npa, int na, float* __restrict__ oa, int blocks_a,
                     const float* __restrict__ pb, int npb, int nb, float* __restrict__ ob) {
   __shared__ float red[8][32];
+  // programmatic dependent launch: wait for the kernel that wrote the partials; let the next kernel's CTAs queue
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const float* parts; int nparts, n; float* out; int blk;
   if ((int)blockIdx.x < blocks_a) { parts = pa; nparts = npa; n = na; out = oa; blk = blockIdx.x; }
   else { parts = pb; nparts = npb; n = nb; out = ob; blk = blockIdx.x - blocks_a; }
@@ -154,8 +157,17 @@ int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_
   const int blocks_a = parts_a ? ceil_div(n_a, 32) : 0;
   const int blocks_b = parts_b ? ceil_div(n_b, 32) : 0;
   if (blocks_a + blocks_b == 0) return GFC_OK;
-  reduce_parts_kernel<<<blocks_a + blocks_b, 256, 0, st>>>(parts_a, nparts_a, n_a, out_a, blocks_a,
-                                                           parts_b, nparts_b, n_b, out_b);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks_a + blocks_b);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  GFC_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_parts_kernel, parts_a, nparts_a, n_a, out_a, blocks_a,
+                                  parts_b, nparts_b, n_b, out_b));
   GFC_LAUNCH_CHECK("reduce_parts_kernel");
   return GFC_OK;
 }
@@ -163,7 +175,7 @@ int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_
 int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st) {
   switch (a.p.variant) {
     case VAR_N8_32_32_3:
-      if (!g_disable_tcgen05 && a.vec_ok) return tc5_fwd_n8_32_32_3(a, gsrc, st);
+      if (!g_disable_tcgen05 && a.vec_ok && !a.single_pass) return tc5_fwd_n8_32_32_3(a, gsrc, st);
       return tile_fwd_n8_32_32_3(a, gsrc, st);
     case VAR_128_128_3: return tile_fwd_128_128_3(a, gsrc, st);
     case VAR_N64_128_128_4: return tile_fwd_n64_128_128_4(a, gsrc, st);

@@ -87,10 +87,11 @@ int tile_fwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_bwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_fwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_bwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
-// tcgen05 / TMEM kernels (gfc_tc5_small.cu)
+// tcgen05 / TMEM kernels of the cfg2 shape (gfc_tc5_n8.cu)
 int tc5_fwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);
-int tc5_bwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);   // gfc_tc5_small_bwd.cu
+int tc5_bwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tc5_bwd_grid_n8_32_32_3(int B);
+extern int g_pdl;              // gfc_set_option(GFC_OPT_PDL), gfc_tc5_n8.cu
 extern int g_disable_tcgen05;  // gfc_set_option(GFC_OPT_DISABLE_TCGEN05)
 
 }  // namespace gfc

@@ -203,7 +203,8 @@ int gfc_tile_plan_info(int B, int N, int G, int F, int K, int backward, int from
 enum {
   GFC_OPT_SKIP_GRAD_REDUCE = 1,
   GFC_OPT_DISABLE_TCGEN05 = 2, /* 1: use the mma.sync tile kernels where a tcgen05 kernel exists (A/B comparison) */
-  GFC_OPT_WIDE_FLUSH_EVERY = 3 /* tiles chained into the TMEM dH accumulators between drains (default 2) */
+  GFC_OPT_WIDE_FLUSH_EVERY = 3, /* tiles chained into the TMEM dH accumulators between drains (default 2) */
+  GFC_OPT_PDL = 4 /* 1 (default): the cfg2-shape kernels and the gradient reduction use programmatic dependent launch */
 };
 int gfc_set_option(int key, int value);
 /* Debug aid: a device buffer of >= 1184*16 int64 in which the fused tile kernels stamp the SM
