@@ -672,7 +672,7 @@ def main():
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("%s:%s" % (args.config, which))
     roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    kernel=("tc5_bwd_kernel<pos> (tcgen05, bf16x3)" if (which == "bwd" and args.config.startswith("cfg2")) else "%s kernel of %s" % (which, args.config)), kernel_ms=k_ms, algorithmic_bytes_per_launch=alg_bytes,
+                    kernel=("tc5_n8_bwd_kernel<pos> (tcgen05, bf16x3)" if (which == "bwd" and args.config.startswith("cfg2")) else "%s kernel of %s" % (which, args.config)), kernel_ms=k_ms, algorithmic_bytes_per_launch=alg_bytes,
                     launches_in_timed_call=k_launch, peak_source=peak_src,
                     how="CUDA events around a graph of %d back-to-back launches over rotating batches x %d replays" % (ring, reps))
 

@@ -69,6 +69,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!done);
 }
 
+// same wait, but the warp is suspended by the hardware until the phase completes (or `hint_ns` elapse) instead
+// of re-issuing try_wait every few cycles: a spinning warp takes issue slots from the warps it is waiting for
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 1000000u) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!done);
+}
+
 // ---- descriptors --------------------------------------------------------------------------
 // shared-memory matrix descriptor, no swizzle (cute::UMMA::SmemDescriptor, version 1 = Blackwell)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {

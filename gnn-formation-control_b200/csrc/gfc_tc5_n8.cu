@@ -157,9 +157,17 @@ __device__ __forceinline__ void store_tap_chunk(unsigned char* Hb, int cchunk, i
   store_chunk3(Hb + cchunk * PB + n * 16, 32 * 16, v);
 }
 
-// all threads of the CTA: producers arrive after their first tile, issuer warps after the one-time setup
-template <int NT>
-__device__ __forceinline__ void cta_bar1() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+
+// contiguous graph range of a CTA, cut into tiles of up to GPC graphs (the last one may be partial: graphs are
+// spread evenly over the CTAs instead of handing out whole tiles, so no SM waits for a neighbour's extra tile)
+struct CtaRange {
+  int begin, end, ntiles;
+  __device__ __forceinline__ CtaRange(int B) {
+    begin = (int)(((long long)blockIdx.x * B) / gridDim.x);
+    end = (int)(((long long)(blockIdx.x + 1) * B) / gridDim.x);
+    ntiles = (end - begin + GPC - 1) / GPC;
+  }
+};
 
 // ======================================================================================================
 // forward
@@ -169,8 +177,7 @@ struct FwdLayout {
   static constexpr int OFF_Z = 0;
   static constexpr int OFF_H = 2 * Z_BYTES;
   static constexpr int OFF_S = OFF_H + HB_BYTES;
-  static constexpr int OFF_BIAS = OFF_S + S_BYTES;
-  static constexpr int OFF_BAR = OFF_BIAS + F * 4;            // ops_ready[2], done[2], tmem ptr
+  static constexpr int OFF_BAR = OFF_S + S_BYTES;             // ops_ready[2], done[2], tmem_ready, tmem ptr
   static constexpr size_t BYTES = OFF_BAR + 64;
   static constexpr int TMEM_COLS = 256;                       // two accumulators of 96 columns at 0 and 128
 };
@@ -185,14 +192,14 @@ tc5_n8_fwd_kernel(const TileArgs a) {
   unsigned char* Zb = sm8 + L::OFF_Z;
   unsigned char* Hb = sm8 + L::OFF_H;
   float* Ss = reinterpret_cast<float*>(sm8 + L::OFF_S);
-  float* bias_s = reinterpret_cast<float*>(sm8 + L::OFF_BIAS);
   uint64_t* ops_ready = reinterpret_cast<uint64_t*>(sm8 + L::OFF_BAR);
   uint64_t* done = ops_ready + 2;
+  uint64_t* tmem_ready = ops_ready + 4;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 48);
-  const TilePlan& p = a.p;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = warp, c = lane;
   const bool producer = tid < kProducers;
+  const CtaRange rg(a.p.B);
   GFC_STAMP(a, 7);
   GFC_STAMP_NS(a, 8);
 
@@ -202,55 +209,28 @@ tc5_n8_fwd_kernel(const TileArgs a) {
     tc5::mbar_init(&ops_ready[1], 16);
     tc5::mbar_init(&done[0], 1);
     tc5::mbar_init(&done[1], 1);
+    tc5::mbar_init(tmem_ready, 1);
     tc5::fence_mbar_init();
+  }
+  // L2 prefetch of this CTA's first two tiles (no data is consumed, so it may run ahead of the PDL dependency:
+  // the DRAM / TLB latency of the first loads overlaps the previous kernel's tail)
+  if (producer && lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int g0 = rg.begin + t * GPC + j;
+      if (g0 < rg.end) tc5::bulk_prefetch_l2(a.x + (size_t)g0 * G * N, G * N * 4);
+    }
   }
   __syncthreads();
   pdl_wait();
   pdl_trigger();
 
-  float xcol[N];
-  float2 mypos = make_float2(0.f, 0.f);
-  float s0 = 0.f, s1 = 0.f;
-  auto request = [&](int tile) {
-    const int b0 = tile * GPC;
-    const bool ok = j < min(GPC, p.B - b0);
-    if (ok) load_x_column<TileCfg<8, 32, 32, 3, 512, 2>>(xcol, a.x, b0, j, c, 1);
-    else {
-#pragma unroll
-      for (int n = 0; n < N; ++n) xcol[n] = 0.f;
-    }
-    if (GSRC == GSRC_POS) {
-      mypos = (ok && lane < N) ? __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)(b0 + j) * N + lane)
-                               : make_float2(0.f, 0.f);
-    } else {
-      const float* src = a.S + (size_t)(b0 + j) * N * N;
-      s0 = ok ? __ldg(src + lane) : 0.f;
-      s1 = ok ? __ldg(src + lane + 32) : 0.f;
-    }
-  };
-
   if (!producer) {
-    // =========================== issuer warp: one-time setup, then the MMA chains ============================
+    // =========================== issuer warp: TMEM, then the MMA chains =====================================
     tc5::tmem_alloc(tmem_ptr, L::TMEM_COLS);
-    {  // taps -> B[n = f][k = c] planes (c = k*G + g: the rows of h are already c-contiguous), bias
-      const int f = lane;
-      float4 u[KG / 8], w[KG / 8];
-#pragma unroll
-      for (int cc = 0; cc < KG / 8; ++cc) {
-        const float4* src = reinterpret_cast<const float4*>(a.h + (size_t)f * KG + cc * 8);
-        u[cc] = __ldg(src);
-        w[cc] = __ldg(src + 1);
-      }
-      bias_s[lane] = a.bias ? __ldg(a.bias + lane) : 0.f;
-#pragma unroll
-      for (int cc = 0; cc < KG / 8; ++cc) {
-        const float v[8] = {u[cc].x, u[cc].y, u[cc].z, u[cc].w, w[cc].x, w[cc].y, w[cc].z, w[cc].w};
-        store_tap_chunk(Hb, cc, f, v);
-      }
-    }
-    tc5::fence_proxy_async();
     tc5::fence_before_sync();
-    cta_bar1<kFwdThreads>();
+    __syncwarp();
+    if (lane == 0) tc5::mbar_arrive(tmem_ready);
     tc5::fence_after_sync();
     const uint32_t tmem = *tmem_ptr;
     if (tc5::elect_one()) {
@@ -258,11 +238,10 @@ tc5_n8_fwd_kernel(const TileArgs a) {
                          kI32 = tc5::idesc_bf16(128, 32, 1, 0);
       const uint32_t z_base = tc5::smem_u32(Zb), h_base = tc5::smem_u32(Hb);
       const uint64_t bd = tc5::make_desc(h_base, PB, 128);
-      uint32_t itl = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++itl) {
+      for (int itl = 0; itl < rg.ntiles; ++itl) {
         const int buf = itl & 1;
-        tc5::mbar_wait(&ops_ready[buf], (itl >> 1) & 1);
-        tc5::fence_after_sync();
+        tc5::mbar_wait_suspend(&ops_ready[buf], (itl >> 1) & 1);       // (also orders the taps, written before the
+        tc5::fence_after_sync();                               //  producers' first arrival)
         const uint32_t zb = z_base + buf * L::Z_BYTES;
         uint64_t a0 = tc5::make_desc(zb, 128, PV), a1 = tc5::make_desc(zb + V_PLANE, 128, PV),
                  a2 = tc5::make_desc(zb + 2 * V_PLANE, 128, PV);
@@ -283,16 +262,42 @@ tc5_n8_fwd_kernel(const TileArgs a) {
   } else {
     // =========================== producers / epilogue ========================================================
     float* Sw = Ss + j * N * N;
-    auto produce = [&](int tile, int buf) {
-      const int b0 = tile * GPC;
-      const bool ok = j < min(GPC, p.B - b0);
+    // running global pointers of this (graph slot, column) thread; they advance by one tile per request
+    int gq = rg.begin + j;
+    const float* px = a.x + ((size_t)gq * G + c) * N;
+    const float2* ppos = reinterpret_cast<const float2*>(a.pos) + (size_t)gq * N + lane;
+    const float* ps = a.S + (size_t)gq * N * N + lane;
+    float xcol[N];
+    float2 mypos = make_float2(0.f, 0.f);
+    float s0 = 0.f, s1 = 0.f;
+    bool okr = false;
+    auto request = [&]() {
+      okr = gq < rg.end;
+      if (okr) {
+        const float4 u = __ldg(reinterpret_cast<const float4*>(px)), w = __ldg(reinterpret_cast<const float4*>(px) + 1);
+        xcol[0] = u.x; xcol[1] = u.y; xcol[2] = u.z; xcol[3] = u.w;
+        xcol[4] = w.x; xcol[5] = w.y; xcol[6] = w.z; xcol[7] = w.w;
+      } else {
+#pragma unroll
+        for (int n = 0; n < N; ++n) xcol[n] = 0.f;
+      }
+      if (GSRC == GSRC_POS) {
+        mypos = (okr && lane < N) ? __ldg(ppos) : make_float2(0.f, 0.f);
+      } else {
+        s0 = okr ? __ldg(ps) : 0.f;
+        s1 = okr ? __ldg(ps + 32) : 0.f;
+      }
+      gq += GPC; px += (size_t)GPC * G * N; ppos += GPC * N; ps += GPC * N * N;
+      if (lane == 0 && gq < rg.end) tc5::bulk_prefetch_l2(px - c * N, G * N * 4);   // the tile after, into L2
+    };
+    auto produce = [&](int t, int buf) {
+      const bool ok = okr;
       unsigned char* Zt = Zb + buf * L::Z_BYTES + j * PV + c * 16;
       warp_gso<GSRC, true>(Sw, a, ok, mypos, s0, s1, lane);     // slot = S^T: z_{k+1}[n] = sum_m S[m][n] z_k[m]
       float z[N];
 #pragma unroll
       for (int n = 0; n < N; ++n) z[n] = xcol[n];
-      const int nxt = tile + gridDim.x;
-      if (nxt < p.ntiles) request(nxt);
+      if (t + 1 < rg.ntiles) request();
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         store_chunk3(Zt + k * G * 16, V_PLANE, z);
@@ -304,28 +309,39 @@ tc5_n8_fwd_kernel(const TileArgs a) {
       if (lane == 0) tc5::mbar_arrive(&ops_ready[buf]);
     };
 
-    request(blockIdx.x);
+    // taps -> B[n = f][k = c] planes (c = k*G + g: the rows of h are already c-contiguous); warps 0..11 convert
+    // one 8-c chunk each, visible to the issuer through the first ops_ready arrival
+    float4 tu, tw;
+    if (warp < KG / 8) {
+      const float4* src = reinterpret_cast<const float4*>(a.h + (size_t)lane * KG + warp * 8);
+      tu = __ldg(src);
+      tw = __ldg(src + 1);
+    }
+    request();
     GFC_STAMP(a, 0);
-    produce(blockIdx.x, 0);
-    GFC_STAMP(a, 1);
-    cta_bar1<kFwdThreads>();
-    tc5::fence_after_sync();
-    const uint32_t tmem = *tmem_ptr;
     const int q = warp & 3, cg = warp >> 2;              // TMEM lane quadrant, 8-column group of this warp
     float bb[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) bb[i] = bias_s[cg * 8 + i];
-    uint32_t itl = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++itl) {
+    for (int i = 0; i < 8; ++i) bb[i] = a.bias ? __ldg(a.bias + cg * 8 + i) : 0.f;
+    if (warp < KG / 8) {
+      const float v[8] = {tu.x, tu.y, tu.z, tu.w, tw.x, tw.y, tw.z, tw.w};
+      store_tap_chunk(Hb, warp, lane, v);
+    }
+    produce(0, 0);
+    GFC_STAMP(a, 1);
+    uint32_t tmem = 0;
+    for (int itl = 0; itl < rg.ntiles; ++itl) {
       const int buf = itl & 1;
-      const int b0 = tile * GPC;
-      const int rows_used = min(GPC, p.B - b0) * N;
-      {
-        const int nxt = tile + gridDim.x;
-        if (nxt < p.ntiles) produce(nxt, buf ^ 1);
+      const int b0 = rg.begin + itl * GPC;
+      const int rows_used = min(GPC, rg.end - b0) * N;
+      if (itl + 1 < rg.ntiles) produce(itl + 1, buf ^ 1);
+      if (itl == 0) {
+        GFC_STAMP(a, 2);
+        tc5::mbar_wait_suspend(tmem_ready, 0);
+        tc5::fence_after_sync();
+        tmem = *tmem_ptr;
       }
-      if (itl == 0) GFC_STAMP(a, 2);
-      tc5::mbar_wait(&done[buf], (itl >> 1) & 1);
+      tc5::mbar_wait_suspend(&done[buf], (itl >> 1) & 1);
       tc5::fence_after_sync();
       uint32_t r0[8], r1[8], r2[8];
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 128 + cg * 8);
@@ -364,8 +380,8 @@ struct BwdLayout {
   static constexpr int OFF_H = 2 * VX_BYTES;
   static constexpr int OFF_S = OFF_H + HB_BYTES;
   static constexpr int OFF_DB = OFF_S + S_BYTES;
-  static constexpr int OFF_BAR = OFF_DB + F * 4;               // ops_ready[2], dx_done[2], dh_done[2], tmem ptr
-  static constexpr size_t BYTES = OFF_BAR + 64;
+  static constexpr int OFF_BAR = OFF_DB + F * 4;               // ops_ready[2], dx_done[2], dh_done[2], tmem_ready, ptr
+  static constexpr size_t BYTES = OFF_BAR + 80;
   static constexpr int TMEM_COLS = 512;                        // buffer b: dX blocks at b*256, dH blocks at b*256+128
 };
 constexpr int kBwdThreads = kProducers + 64;                   // + warp 16 (dX chain) + warp 17 (dH chain)
@@ -383,12 +399,13 @@ tc5_n8_bwd_kernel(const TileArgs a) {
   uint64_t* ops_ready = reinterpret_cast<uint64_t*>(sm8 + L::OFF_BAR);
   uint64_t* dx_done = ops_ready + 2;
   uint64_t* dh_done = ops_ready + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 48);
-  const TilePlan& p = a.p;
+  uint64_t* tmem_ready = ops_ready + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 64);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = warp, c = lane;
   const bool producer = tid < kProducers;
   const bool want_dx = a.dX != nullptr, want_dh = a.dHp != nullptr, want_db = a.dbp != nullptr;
+  const CtaRange rg(a.p.B);
   GFC_STAMP(a, 7);
   GFC_STAMP_NS(a, 8);
 
@@ -399,79 +416,43 @@ tc5_n8_bwd_kernel(const TileArgs a) {
       tc5::mbar_init(&dx_done[i], 1);
       tc5::mbar_init(&dh_done[i], 1);
     }
+    tc5::mbar_init(tmem_ready, 1);
     tc5::fence_mbar_init();
   }
   if (tid < F) dbs[tid] = 0.f;
+  // L2 prefetch of this CTA's first two tiles of dY and x (nothing is consumed: may run ahead of the PDL dependency)
+  if (producer && lane == 0) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+      const int g0 = rg.begin + t * GPC + j;
+      if (g0 < rg.end) {
+        tc5::bulk_prefetch_l2(a.dY + (size_t)g0 * N * F, N * F * 4);
+        if (want_dh) tc5::bulk_prefetch_l2(a.x + (size_t)g0 * G * N, G * N * 4);
+      }
+    }
+  }
   __syncthreads();
   pdl_wait();
   pdl_trigger();
 
-  float xcol[N], dyc[N], yoc[N];
-  float2 mypos = make_float2(0.f, 0.f);
-  float s0 = 0.f, s1 = 0.f;
-  auto request = [&](int tile) {
-    const int b0 = tile * GPC;
-    const bool ok = j < min(GPC, p.B - b0);
-    if (GSRC == GSRC_POS) {
-      mypos = (ok && lane < N) ? __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)(b0 + j) * N + lane)
-                               : make_float2(0.f, 0.f);
-    } else {
-      const float* src = a.S + (size_t)(b0 + j) * N * N;
-      s0 = ok ? __ldg(src + lane) : 0.f;
-      s1 = ok ? __ldg(src + lane + 32) : 0.f;
-    }
-    const float* dsrc = a.dY + ((size_t)(b0 + j) * N) * F + c;
-    const float* ysrc = (a.act != GFC_ACT_NONE) ? a.yout + ((size_t)(b0 + j) * N) * F + c : nullptr;
-#pragma unroll
-    for (int n = 0; n < N; ++n) {
-      dyc[n] = ok ? __ldg(dsrc + (size_t)n * F) : 0.f;
-      yoc[n] = (ok && ysrc) ? __ldg(ysrc + (size_t)n * F) : 1.f;
-    }
-    if (want_dh) {
-      if (ok) load_x_column<TileCfg<8, 32, 32, 3, 512, 2>>(xcol, a.x, b0, j, c, 1);
-      else {
-#pragma unroll
-        for (int n = 0; n < N; ++n) xcol[n] = 0.f;
-      }
-    }
-  };
-  const int q = warp & 3, cg = warp >> 2;
-  float hacc[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) hacc[i] = 0.f;
-  float dbreg = 0.f;
-
   if (!producer) {
     // =========================== issuers: warp 16 -> dX chain, warp 17 -> dH chain ==========================
     const bool is_dx = warp == kProducers / 32;
-    if (is_dx) tc5::tmem_alloc(tmem_ptr, L::TMEM_COLS);
-    if (want_dx) {
-      // taps -> B[n = g][k = c] planes, c = k*F + f:  B[g][c] = h[f][k*G + g]  (loads coalesced along g);
-      // each issuer warp converts half of the twelve 8-c chunks
-      constexpr int HALF = KF / 16;
-      const int g = lane, cc0 = is_dx ? 0 : HALF;
-      float v[HALF][8];
-#pragma unroll
-      for (int cc = 0; cc < HALF; ++cc) {
-        const int cchunk = cc0 + cc;
-        const int k = cchunk / (F / 8), f0 = (cchunk % (F / 8)) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[cc][i] = __ldg(a.h + (size_t)(f0 + i) * KG + k * G + g);
-      }
-#pragma unroll
-      for (int cc = 0; cc < HALF; ++cc) store_tap_chunk(Hb, cc0 + cc, g, v[cc]);
+    if (is_dx) {
+      tc5::tmem_alloc(tmem_ptr, L::TMEM_COLS);
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(tmem_ready);
+    } else {
+      tc5::mbar_wait_suspend(tmem_ready, 0);
     }
-    tc5::fence_proxy_async();
-    tc5::fence_before_sync();
-    cta_bar1<kBwdThreads>();
     tc5::fence_after_sync();
     const uint32_t tmem = *tmem_ptr;
     if ((is_dx ? want_dx : want_dh) && tc5::elect_one()) {
       const uint32_t v_base = tc5::smem_u32(Vb), h_base = tc5::smem_u32(Hb);
-      uint32_t itl = 0;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++itl) {
+      for (int itl = 0; itl < rg.ntiles; ++itl) {
         const int buf = itl & 1;
-        tc5::mbar_wait(&ops_ready[buf], (itl >> 1) & 1);
+        tc5::mbar_wait_suspend(&ops_ready[buf], (itl >> 1) & 1);
         tc5::fence_after_sync();
         const uint32_t vb = v_base + buf * L::VX_BYTES;
         if (is_dx) {
@@ -515,22 +496,66 @@ tc5_n8_bwd_kernel(const TileArgs a) {
   } else {
     // =========================== producers / epilogue ========================================================
     float* Sw = Ss + j * N * N;
-    auto produce = [&](int tile, int buf) {
-      const int b0 = tile * GPC;
-      const bool ok = j < min(GPC, p.B - b0);
+    int gq = rg.begin + j;
+    const float* px = a.x + ((size_t)gq * G + c) * N;
+    const float* pdy = a.dY + (size_t)gq * N * F + c;
+    const float* py = a.yout + (size_t)gq * N * F + c;
+    const float2* ppos = reinterpret_cast<const float2*>(a.pos) + (size_t)gq * N + lane;
+    const float* ps = a.S + (size_t)gq * N * N + lane;
+    const bool has_act = a.act != GFC_ACT_NONE;
+    // d(pre) = yo > 0 ? dy : dy * neg  (act_grad of gfc_common.cuh without the per-element branches; yo = 1 when
+    // there is no activation)
+    const float neg = a.act == GFC_ACT_LEAKY_RELU ? a.slope : (a.act == GFC_ACT_RELU ? 0.f : 1.f);
+    float xcol[N], dyc[N], yoc[N];
+    float2 mypos = make_float2(0.f, 0.f);
+    float s0 = 0.f, s1 = 0.f;
+    bool okr = false;
+    auto request = [&]() {
+      okr = gq < rg.end;
+      if (GSRC == GSRC_POS) {
+        mypos = (okr && lane < N) ? __ldg(ppos) : make_float2(0.f, 0.f);
+      } else {
+        s0 = okr ? __ldg(ps) : 0.f;
+        s1 = okr ? __ldg(ps + 32) : 0.f;
+      }
+#pragma unroll
+      for (int n = 0; n < N; ++n) {
+        dyc[n] = okr ? __ldg(pdy + n * F) : 0.f;
+        yoc[n] = (okr && has_act) ? __ldg(py + n * F) : 1.f;
+      }
+      if (want_dh) {
+        if (okr) {
+          const float4 u = __ldg(reinterpret_cast<const float4*>(px)), w = __ldg(reinterpret_cast<const float4*>(px) + 1);
+          xcol[0] = u.x; xcol[1] = u.y; xcol[2] = u.z; xcol[3] = u.w;
+          xcol[4] = w.x; xcol[5] = w.y; xcol[6] = w.z; xcol[7] = w.w;
+        } else {
+#pragma unroll
+          for (int n = 0; n < N; ++n) xcol[n] = 0.f;
+        }
+      }
+      gq += GPC; px += (size_t)GPC * G * N; pdy += (size_t)GPC * N * F; py += (size_t)GPC * N * F;
+      ppos += GPC * N; ps += GPC * N * N;
+      if (lane == 0 && gq < rg.end) {   // the tile after, into L2
+        tc5::bulk_prefetch_l2(pdy - c, N * F * 4);
+        if (has_act) tc5::bulk_prefetch_l2(py - c, N * F * 4);
+        if (want_dh) tc5::bulk_prefetch_l2(px - c * N, G * N * 4);
+      }
+    };
+    float dbreg = 0.f;
+    auto produce = [&](int t, int buf) {
+      const bool ok = okr;
       unsigned char* Vt = Vb + buf * L::VX_BYTES + j * PV + c * 16;
       unsigned char* Xt = Vb + buf * L::VX_BYTES + L::OFF_X + j * PB + c * 16;
       warp_gso<GSRC, false>(Sw, a, ok, mypos, s0, s1, lane);    // slot = S: V_{k+1}[n] = sum_m S[n][m] V_k[m]
       float v[N];
 #pragma unroll
-      for (int n = 0; n < N; ++n) v[n] = act_grad(dyc[n], yoc[n], a.act, a.slope);
+      for (int n = 0; n < N; ++n) v[n] = yoc[n] > 0.f ? dyc[n] : dyc[n] * neg;
       if (want_db) {
 #pragma unroll
         for (int n = 0; n < N; ++n) dbreg += v[n];
       }
       if (want_dh) store_chunk3(Xt, 32 * 16, xcol);
-      const int nxt = tile + gridDim.x;
-      if (nxt < p.ntiles) request(nxt);
+      if (t + 1 < rg.ntiles) request();
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         store_chunk3(Vt + k * F * 16, V_PLANE, v);
@@ -542,27 +567,39 @@ tc5_n8_bwd_kernel(const TileArgs a) {
       if (lane == 0) tc5::mbar_arrive(&ops_ready[buf]);
     };
 
-    request(blockIdx.x);
+    // taps -> B[n = g][k = c] planes, c = k*F + f:  B[g][c] = h[f][k*G + g]  (loads coalesced along g); warps
+    // 0..11 convert one 8-c chunk each, visible to the issuers through the first ops_ready arrival
+    float tv[8];
+    if (want_dx && warp < KF / 8) {
+      const int k = warp / (F / 8), f0 = (warp % (F / 8)) * 8;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tv[i] = __ldg(a.h + (size_t)(f0 + i) * KG + k * G + lane);
+    }
+    request();
     GFC_STAMP(a, 0);
-    produce(blockIdx.x, 0);
+    if (want_dx && warp < KF / 8) store_tap_chunk(Hb, warp, lane, tv);
+    produce(0, 0);
     GFC_STAMP(a, 1);
-    cta_bar1<kBwdThreads>();
-    tc5::fence_after_sync();
-    const uint32_t tmem = *tmem_ptr;
-    uint32_t itl = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++itl) {
+    const int q = warp & 3, cg = warp >> 2;
+    float hacc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) hacc[i] = 0.f;
+    uint32_t tmem = 0;
+    for (int itl = 0; itl < rg.ntiles; ++itl) {
       const int buf = itl & 1;
-      const int b0 = tile * GPC;
-      const int rows_used = min(GPC, p.B - b0) * N;
-      {
-        const int nxt = tile + gridDim.x;
-        if (nxt < p.ntiles) produce(nxt, buf ^ 1);
+      const int b0 = rg.begin + itl * GPC;
+      const int rows_used = min(GPC, rg.end - b0) * N;
+      if (itl + 1 < rg.ntiles) produce(itl + 1, buf ^ 1);
+      if (itl == 0) {
+        GFC_STAMP(a, 2);
+        tc5::mbar_wait_suspend(tmem_ready, 0);
+        tc5::fence_after_sync();
+        tmem = *tmem_ptr;
       }
-      if (itl == 0) GFC_STAMP(a, 2);
       const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 256 + cg * 8);
       // ---- dX straight from TMEM: this thread's row (j', n'), 8 channels g ------------------------------
       if (want_dx) {
-        tc5::mbar_wait(&dx_done[buf], (itl >> 1) & 1);
+        tc5::mbar_wait_suspend(&dx_done[buf], (itl >> 1) & 1);
         tc5::fence_after_sync();
         uint32_t r0[8], r1[8], r2[8];
         tc5::tmem_ld8u(taddr, r0);
@@ -581,7 +618,7 @@ tc5_n8_bwd_kernel(const TileArgs a) {
       if (itl == 0) GFC_STAMP(a, 3);
       // ---- dH tile -> running fp32 sums (lane = (k, f), 8 channels g) -----------------------------------
       if (want_dh) {
-        tc5::mbar_wait(&dh_done[buf], (itl >> 1) & 1);
+        tc5::mbar_wait_suspend(&dh_done[buf], (itl >> 1) & 1);
         tc5::fence_after_sync();
         if (q < 3) {
           uint32_t r0[8], r1[8], r2[8];

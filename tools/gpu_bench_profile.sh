@@ -11,6 +11,6 @@ timeout 300 $CMD > gpurun_out/plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu1.log 2>&1
 echo "ncu launches exit $?"
 timeout 300 $CMD > gpurun_out/plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc5_bwd -s 4 -c 3 -o gpurun_out/prof_cfg2 $CMD > gpurun_out/ncu2.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:tc5_n8_bwd -s 4 -c 3 -o gpurun_out/prof_cfg2 $CMD > gpurun_out/ncu2.log 2>&1
 echo "ncu full exit $?"
 fi

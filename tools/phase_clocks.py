@@ -38,6 +38,13 @@ for which, labels in (("fwd", ["setup", "load+gso", "hops", "mma+store"]),
         base = t[:, 7]
         print("   tcgen05 fwd timeline (median cycles since entry): " +
               ", ".join("%s=%.0f" % (nm, np.median(t[:, sl] - base)) for nm, sl in seq))
+    if which == "bwd" and t[:, 10].any():
+        tt = t[t[:, 10] != 0]
+        seq = [("produce(1) start", 10), ("gso", 11), ("act+X", 12), ("V0 stored", 13), ("hop1", 14), ("all stored", 15), ("arrived", 5),
+               ("stamp2", 2), ("dX epi", 3), ("dH epi", 4), ("final", 6)]
+        base = tt[:, 7]
+        print("   bwd timeline (median cycles since entry): " +
+              ", ".join("%s=%.0f" % (nm, np.median(tt[:, sl] - base)) for nm, sl in seq))
     ns0, ns1 = t[:, 8], t[:, 9]
     print("   globaltimer: CTA starts spread %.2f us, CTA duration median %.2f us, first start -> last end %.2f us"
           % ((ns0.max() - ns0.min()) / 1e3, np.median(ns1 - ns0) / 1e3, (ns1.max() - ns0.min()) / 1e3))
