@@ -72,7 +72,19 @@ struct GenericPlan {
   int nsplit;          // split of the dH reduction
   int nchunks, rows_per_chunk;  // db partial sums
   size_t ws_s, ws_z, ws_d, ws_dhp, ws_dbp, ws_bytes;
+  int rows_ok;         // the tap contractions run on the tensor-core tile kernels ("rows" plan, VAR_ROWS)
+  TilePlan rows;       //   ... with this plan; its partial buffers / packed taps live at ws_rows
+  size_t ws_rows;
 };
+
+// Tap contractions of the workspace pipeline on the tensor cores: the states Zw are a row-major [rows x C] matrix,
+// i.e. `rows` one-node graphs with C input features and one tap, so the fused tile kernels apply unchanged
+// (forward: Y = act(Zw H^T + b); backward: D = dY o act', db, dH += D^T Zw, U = D H written over Zw in place).
+static bool rows_plan(long long rows, long long C, int F, int backward, TilePlan* p) {
+  if (rows <= 0 || rows > 0x7fffffffLL || C > 8192) return false;
+  if (!plan_tile((int)rows, 1, (int)C, F, 1, backward, GSRC_DENSE, p)) return false;
+  return p->variant == VAR_ROWS;
+}
 
 static void plan_generic(int B, int N, int G, int F, int K, int E, int backward, int need_s, GenericPlan* g) {
   const long long rows = (long long)B * N;
@@ -102,6 +114,9 @@ static void plan_generic(int B, int N, int G, int F, int K, int E, int backward,
     if (g->nchunks < 1) g->nchunks = 1;
     g->ws_dbp = off; off += align_up((size_t)g->nchunks * F * sizeof(float), 256);
   }
+  g->rows_ok = rows_plan(rows, C, F, backward, &g->rows) ? 1 : 0;
+  g->ws_rows = off;
+  if (g->rows_ok) off += align_up(g->rows.ws_bytes, 256);
   g->ws_bytes = off;
 }
 
@@ -118,6 +133,54 @@ static int need_ws(const char* fn, const void* ws, size_t have, size_t need) {
   GFC_REQUIRE(ws != nullptr && have >= need, GFC_ERR_WORKSPACE, "%s: workspace %zu B < required %zu B", fn, have, need);
   GFC_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, GFC_ERR_WORKSPACE, "%s: workspace must be 256-byte aligned", fn);
   return GFC_OK;
+}
+
+static int rows_fwd(const GenericPlan& g, char* wsb, const float* Zw, const float* h, const float* bias, float* y,
+                    int act, float slope, int prec, cudaStream_t st) {
+  const TilePlan& p = g.rows;
+  TileArgs a{};
+  a.S = Zw;   // one dummy weight per row (K = 1: no hop ever reads it)
+  a.x = Zw; a.h = h; a.bias = bias; a.y = y;
+  a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+  a.vec_ok = aligned16(Zw) && aligned16(y);
+  a.p = p;
+  if (!p.h_smem) {
+    float4* hp = reinterpret_cast<float4*>(wsb + g.ws_rows + p.ws_hpack);
+    int rc = launch_pack_taps(h, p.F, p.KG, 0, hp, st);
+    if (rc) return rc;
+    a.hpack = hp;
+  }
+  return launch_tile_fwd(a, GSRC_DENSE, st);
+}
+
+// Zw holds the states Z on entry (read only when dH is wanted) and U = D H on return (when want_u)
+static int rows_bwd(const GenericPlan& g, char* wsb, float* Zw, const float* h, const float* yout, const float* dY,
+                    bool want_u, float* dH, float* db, int act, float slope, int prec, const DpCtx* dp,
+                    cudaStream_t st) {
+  const TilePlan& p = g.rows;
+  const size_t nH = (size_t)p.F * p.KG;
+  TileArgs a{};
+  a.S = Zw;
+  a.x = Zw; a.h = h; a.yout = yout; a.dY = dY;
+  a.dX = want_u ? Zw : nullptr;
+  a.dHp = dH ? reinterpret_cast<float*>(wsb + g.ws_rows + p.ws_dhp) : nullptr;
+  a.dbp = db ? reinterpret_cast<float*>(wsb + g.ws_rows + p.ws_dbp) : nullptr;
+  a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+  a.vec_ok = aligned16(Zw) && aligned16(dY) && (!yout || aligned16(yout));
+  a.p = p;
+  int rc;
+  if (!p.h_smem && want_u) {
+    float4* hp = reinterpret_cast<float4*>(wsb + g.ws_rows + p.ws_hpack);
+    rc = launch_pack_taps(h, p.F, p.KG, 1, hp, st);
+    if (rc) return rc;
+    a.hpack = hp;
+  }
+  if (dH && !p.acc_regs) GFC_CUDA_TRY(cudaMemsetAsync(a.dHp, 0, (size_t)p.nparts * nH * sizeof(float), st));
+  rc = launch_tile_bwd(a, GSRC_DENSE, st);
+  if (rc) return rc;
+  if (!dH && !db) return GFC_OK;
+  if (dp) return launch_reduce_allreduce(a.dHp, p.nparts, (int)nH, a.dbp, p.grid, p.F, dH, *dp, st);
+  return launch_reduce_parts(dH ? a.dHp : nullptr, p.nparts, (int)nH, dH, db ? a.dbp : nullptr, p.grid, p.F, db, st);
 }
 
 // ---- tcgen05 wide path eligibility -------------------------------------------------
@@ -204,6 +267,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
     if (rc) return rc;
   }
+  if (g.rows_ok) return rows_fwd(g, wsb, Zw, h, bias, y, act, slope, prec, st);
   return launch_sgemm(Zw, C, 1, h, 1, C, y, F, 0, (long long)B * N, F, C, 1, bias, act, slope, st);
 }
 
@@ -325,6 +389,29 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   float* Dw = reinterpret_cast<float*>(wsb + g.ws_d);
   const long long rows = (long long)B * N;
   const long long C = (long long)E * K * G;
+  if (g.rows_ok) {
+    // tensor-core pipeline: states -> one fused kernel (D, db, dH, U in place) -> Horner hops
+    if (dH) {
+      rc = launch_xpose_in(x, Zw, B, N, G, E, K, st);
+      if (rc) return rc;
+      for (int k = 1; k < K; ++k) {
+        rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
+        if (rc) return rc;
+      }
+    }
+    rc = rows_bwd(g, wsb, Zw, h, (act != GFC_ACT_NONE) ? yout : nullptr, dY, dX != nullptr, dH, db, act, slope, prec,
+                  dp, st);
+    if (rc) return rc;
+    if (dX) {
+      for (int k = K - 2; k >= 0; --k) {
+        rc = launch_hop_dense(Zw, S, B, N, G, E, K, k + 1, k, 1, st);
+        if (rc) return rc;
+      }
+      rc = launch_xpose_out(Zw, dX, B, N, G, E, K, st);
+      if (rc) return rc;
+    }
+    return GFC_OK;
+  }
   rc = launch_dpre(dY, yout, Dw, rows * F, act, slope, st);
   if (rc) return rc;
   if (db) {
@@ -536,6 +623,7 @@ extern "C" int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const i
     rc = launch_hop_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, k - 1, k, 0, st);
     if (rc) return rc;
   }
+  if (g.rows_ok) return rows_fwd(g, static_cast<char*>(workspace), Zw, h, bias, y, act, slope, precision, st);
   return launch_sgemm(Zw, C, 1, h, 1, C, y, F, 0, (long long)B * N, F, C, 1, bias, act, slope, st);
 }
 
@@ -570,6 +658,28 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
   float* Dw = reinterpret_cast<float*>(wsb + g.ws_d);
   const long long rows = (long long)B * N;
   const long long C = (long long)K * G;
+  if (g.rows_ok) {
+    if (dH) {
+      rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);
+      if (rc) return rc;
+      for (int k = 1; k < K; ++k) {
+        rc = launch_hop_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, k - 1, k, 0, st);
+        if (rc) return rc;
+      }
+    }
+    rc = rows_bwd(g, wsb, Zw, h, (act != GFC_ACT_NONE) ? y_out : nullptr, dY, dX != nullptr, dH, db, act, slope,
+                  precision, nullptr, st);
+    if (rc) return rc;
+    if (dX) {
+      for (int k = K - 2; k >= 0; --k) {
+        rc = launch_hop_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, k + 1, k, 1, st);
+        if (rc) return rc;
+      }
+      rc = launch_xpose_out(Zw, dX, B, N, G, 1, K, st);
+      if (rc) return rc;
+    }
+    return GFC_OK;
+  }
   rc = launch_dpre(dY, y_out, Dw, rows * F, act, slope, st);
   if (rc) return rc;
   if (db) {

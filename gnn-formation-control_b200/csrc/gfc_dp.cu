@@ -14,6 +14,7 @@
 // reduce_parts_kernel + ncclAllReduce pair of the plain DP path.
 #include "gfc_common.cuh"
 #include "gfc_dp.cuh"
+#include "gfc_tile.cuh"   // g_pdl
 
 namespace gfc {
 
@@ -35,6 +36,9 @@ __global__ void __launch_bounds__(256)
 reduce_allreduce_kernel(const float* __restrict__ pa, int npa, int na, const float* __restrict__ pb, int npb, int nb,
                         float* __restrict__ out, const DpPeers peers, int rank, int world, float scale) {
   __shared__ unsigned int s_epoch;
+  // programmatic dependent launch: this grid may be scheduled while the backward kernel drains
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int n = na + nb;
   const int nblocks = gridDim.x, c = blockIdx.x;
   const int per = (n + nblocks - 1) / nblocks;
@@ -113,7 +117,17 @@ int launch_reduce_allreduce(const float* pa, int npa, int na, const float* pb, i
     GFC_REQUIRE(peers.buf[r] && peers.sig[r], GFC_ERR_BAD_ARG, "dp: NULL peer pointer for rank %d", r);
   }
   const int n = na + nb;
-  reduce_allreduce_kernel<<<dp_blocks(n), 256, 0, st>>>(pa, npa, na, pb, npb, nb, out, peers, dp.rank, dp.world, dp.scale);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(dp_blocks(n));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  GFC_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_allreduce_kernel, pa, npa, na, pb, npb, nb, out, peers, dp.rank,
+                                  dp.world, dp.scale));
   GFC_LAUNCH_CHECK("reduce_allreduce_kernel");
   return GFC_OK;
 }

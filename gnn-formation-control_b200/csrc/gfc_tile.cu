@@ -79,6 +79,7 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   if (N == 8 && G == 32 && F == 32 && K == 3) { p->variant = VAR_N8_32_32_3; p->threads = 512; p->nb = 2; }
   else if (N == 64 && G == 128 && F == 128 && K == 4) p->variant = VAR_N64_128_128_4;
   else if (G == 128 && F == 128 && K == 3) p->variant = VAR_128_128_3;
+  if (N == 1 && K == 1) { p->variant = VAR_ROWS; p->threads = 384; p->nb = 4; }
   if (F > p->threads) return 0;
   DeviceInfo di;
   if (get_device_info(&di)) return 0;
@@ -86,6 +87,9 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   p->ldz = p->KG + (backward ? 8 : 4);
   p->ldd = F + 4;
   int gpc = 128 / N;
+  // row contraction: one 16-row MMA task per warp and tile (a CTA of this register footprint owns its SM, so the
+  // tile must keep all of its warps busy between the two barriers)
+  if (p->variant == VAR_ROWS) gpc = 16 * (p->threads / 32);
   if (gpc < 1) gpc = 1;
   if (gpc > B) gpc = B;
   {  // small batches: spread the graphs over the SMs instead of filling 128-row tiles
@@ -98,14 +102,17 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
   // prefer a footprint that lets two CTAs share an SM, as long as a tile keeps >= 64 rows
   const long long half_floats = limit_floats / 2 - 256;
   int chosen = 0, chosen_h = 0;
-  for (int pass = 0; pass < 2 && !chosen; ++pass) {
-    const long long lim = pass == 0 ? half_floats : limit_floats;
-    for (int gcur = gpc; gcur >= 1; gcur = (gcur > 1 ? (gcur + 1) / 2 : 0)) {
-      p->gpc = gcur; p->rows = gcur * N; p->rpad = (p->rows + 15) & ~15;
-      if (pass == 0 && p->rows < 64 && gcur != gpc) break;
-      if (tile_smem_floats(p, gsrc, 1) <= lim) { chosen = gcur; chosen_h = 1; break; }
-      if (tile_smem_floats(p, gsrc, 0) <= lim) { chosen = gcur; chosen_h = 0; break; }
-      if (gcur == 1) break;
+  // the row contraction re-reads the packed taps for every 16-row task: insist on taps in shared memory first
+  for (int need_h = (p->variant == VAR_ROWS ? 1 : 0); need_h >= 0 && !chosen; --need_h) {
+    for (int pass = (p->variant == VAR_ROWS ? 1 : 0); pass < 2 && !chosen; ++pass) {
+      const long long lim = pass == 0 ? half_floats : limit_floats;
+      for (int gcur = gpc; gcur >= 1; gcur = (gcur > 1 ? (gcur + 1) / 2 : 0)) {
+        p->gpc = gcur; p->rows = gcur * N; p->rpad = (p->rows + 15) & ~15;
+        if (pass == 0 && p->rows < 64 && gcur != gpc) break;
+        if (tile_smem_floats(p, gsrc, 1) <= lim) { chosen = gcur; chosen_h = 1; break; }
+        if (!need_h && tile_smem_floats(p, gsrc, 0) <= lim) { chosen = gcur; chosen_h = 0; break; }
+        if (gcur == 1) break;
+      }
     }
   }
   if (!chosen) return 0;
@@ -179,6 +186,7 @@ int launch_tile_fwd(const TileArgs& a, int gsrc, cudaStream_t st) {
       return tile_fwd_n8_32_32_3(a, gsrc, st);
     case VAR_128_128_3: return tile_fwd_128_128_3(a, gsrc, st);
     case VAR_N64_128_128_4: return tile_fwd_n64_128_128_4(a, gsrc, st);
+    case VAR_ROWS: return tile_fwd_rows(a, gsrc, st);
     default: return tile_fwd_generic(a, gsrc, st);
   }
 }
@@ -190,6 +198,7 @@ int launch_tile_bwd(const TileArgs& a, int gsrc, cudaStream_t st) {
       return tile_bwd_n8_32_32_3(a, gsrc, st);
     case VAR_128_128_3: return tile_bwd_128_128_3(a, gsrc, st);
     case VAR_N64_128_128_4: return tile_bwd_n64_128_128_4(a, gsrc, st);
+    case VAR_ROWS: return tile_bwd_rows(a, gsrc, st);
     default: return tile_bwd_generic(a, gsrc, st);
   }
 }

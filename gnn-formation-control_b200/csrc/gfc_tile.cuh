@@ -11,7 +11,8 @@ enum {
   VAR_GENERIC = 0,     // runtime N,G,F,K; 256 threads, 4 n-tiles per warp task
   VAR_N8_32_32_3 = 1,  // cfg2: N=8, G=F=32, K=3; 512 threads, 2 n-tiles per warp task
   VAR_128_128_3 = 2,   // the reference policy's layer (suhaas_model.py:33-42): G=F=128, K=3, any N
-  VAR_N64_128_128_4 = 3  // cfg3
+  VAR_N64_128_128_4 = 3,  // cfg3
+  VAR_ROWS = 4         // N = 1, K = 1: plain row contraction [rows x G] . [G x F] (the workspace pipeline's tap GEMMs); 384 threads
 };
 
 // Host-computed plan: how a [B graphs] x [N nodes] batch is cut into tiles of
@@ -87,6 +88,8 @@ int tile_fwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_bwd_128_128_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_fwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
 int tile_bwd_n64_128_128_4(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_fwd_rows(const TileArgs& a, int gsrc, cudaStream_t st);
+int tile_bwd_rows(const TileArgs& a, int gsrc, cudaStream_t st);
 // tcgen05 / TMEM kernels of the cfg2 shape (gfc_tc5_n8.cu)
 int tc5_fwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);
 int tc5_bwd_n8_32_32_3(const TileArgs& a, int gsrc, cudaStream_t st);

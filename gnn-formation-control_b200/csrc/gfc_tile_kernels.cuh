@@ -82,7 +82,27 @@ __device__ __forceinline__ void load_x_tile(float* __restrict__ Zs, const float*
   const int tid = threadIdx.x;
   const int GN = G * N;
   const float* src = x + (size_t)b0 * GN;
-  if (vec_ok && (N & 3) == 0) {
+  if (vec_ok && N == 1 && (G & 3) == 0) {   // rows are already contiguous: 128-bit copies
+    const int G4 = G >> 2, total = gcount * G4;
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    constexpr int U = 8;   // loads in flight per thread: the tile load is the latency chain of this mode
+    for (int q0 = tid; q0 < total; q0 += U * CFG::kThreads) {
+      float4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = q0 + u * CFG::kThreads;
+        if (q < total) v[u] = __ldg(s4 + q);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int q = q0 + u * CFG::kThreads;
+        if (q < total) {
+          const int j = q / G4, g4 = q - j * G4;
+          *reinterpret_cast<float4*>(Zs + (size_t)j * ldz + g4 * 4) = v[u];
+        }
+      }
+    }
+  } else if (vec_ok && (N & 3) == 0) {
     const int N4 = N >> 2, G4 = G >> 2;
     const int per_graph = N4 * G4;
     const int total = gcount * per_graph;
@@ -118,7 +138,14 @@ __device__ __forceinline__ void store_dx_tile(const float* __restrict__ Zs, floa
   const int tid = threadIdx.x;
   const int GN = G * N;
   float* dst = dX + (size_t)b0 * GN;
-  if (vec_ok && (N & 3) == 0) {
+  if (vec_ok && N == 1 && (G & 3) == 0) {
+    const int G4 = G >> 2, total = gcount * G4;
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int q = tid; q < total; q += CFG::kThreads) {
+      const int j = q / G4, g4 = q - j * G4;
+      d4[q] = *reinterpret_cast<const float4*>(Zs + (size_t)j * ldz + g4 * 4);
+    }
+  } else if (vec_ok && (N & 3) == 0) {
     const int N4 = N >> 2, G4 = G >> 2;
     const int per_graph = N4 * G4;
     const int total = gcount * per_graph;
@@ -669,18 +696,33 @@ tile_bwd_kernel(const TileArgs a) {
       if (a.vec_ok) {
         const float4* d4 = reinterpret_cast<const float4*>(dsrc);
         const float4* y4 = reinterpret_cast<const float4*>(ysrc);
-        for (int i4 = tid; i4 < (total >> 2); i4 += CFG::kThreads) {
-          float4 v = __ldg(d4 + i4);
-          if (ysrc) {
-            const float4 yo = __ldg(y4 + i4);
-            v.x = act_grad(v.x, yo.x, a.act, a.slope);
-            v.y = act_grad(v.y, yo.y, a.act, a.slope);
-            v.z = act_grad(v.z, yo.z, a.act, a.slope);
-            v.w = act_grad(v.w, yo.w, a.act, a.slope);
+        constexpr int U = 4;   // (dY, y) pairs in flight per thread
+        const int total4 = total >> 2;
+        for (int q0 = tid; q0 < total4; q0 += U * CFG::kThreads) {
+          float4 v[U], yo[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i4 = q0 + u * CFG::kThreads;
+            if (i4 < total4) {
+              v[u] = __ldg(d4 + i4);
+              if (ysrc) yo[u] = __ldg(y4 + i4);
+            }
           }
-          const int i = i4 << 2;
-          const int r = i / F, f = i - r * F;
-          *reinterpret_cast<float4*>(Ds + (size_t)r * ldd + f) = v;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int i4 = q0 + u * CFG::kThreads;
+            if (i4 < total4) {
+              if (ysrc) {
+                v[u].x = act_grad(v[u].x, yo[u].x, a.act, a.slope);
+                v[u].y = act_grad(v[u].y, yo[u].y, a.act, a.slope);
+                v[u].z = act_grad(v[u].z, yo[u].z, a.act, a.slope);
+                v[u].w = act_grad(v[u].w, yo[u].w, a.act, a.slope);
+              }
+              const int i = i4 << 2;
+              const int r = i / F, f = i - r * F;
+              *reinterpret_cast<float4*>(Ds + (size_t)r * ldd + f) = v[u];
+            }
+          }
         }
       } else {
         for (int i = tid; i < total; i += CFG::kThreads) {
