@@ -11,9 +11,9 @@ directory, whose name is not a Python identifier).
 from . import _cabi
 from ._cabi import GfcError, version, last_launch_count
 from .gso import build_gso, build_csr, SparseGSO
-from .graph_filter import GraphFilterBatch, GraphFilter, graph_filter
+from .graph_filter import GraphFilterBatch, GraphFilter, GraphFilterBatchGSO, graph_filter
 from .dp import GradBucket, PeerExchange, shard_range, broadcast_parameters
 
-__all__ = ["GraphFilterBatch", "GraphFilter", "graph_filter", "build_gso", "build_csr", "SparseGSO",
+__all__ = ["GraphFilterBatch", "GraphFilter", "GraphFilterBatchGSO", "graph_filter", "build_gso", "build_csr", "SparseGSO",
            "GradBucket", "PeerExchange", "shard_range", "broadcast_parameters", "GfcError", "version",
            "last_launch_count"]

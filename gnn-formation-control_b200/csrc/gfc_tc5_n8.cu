@@ -177,8 +177,8 @@ struct FwdLayout {
   static constexpr int OFF_Z = 0;
   static constexpr int OFF_H = 2 * Z_BYTES;
   static constexpr int OFF_S = OFF_H + HB_BYTES;
-  static constexpr int OFF_BAR = OFF_S + S_BYTES;             // ops_ready[2], done[2], tmem_ready, tmem ptr
-  static constexpr size_t BYTES = OFF_BAR + 64;
+  static constexpr int OFF_BAR = OFF_S + S_BYTES;             // ops_ready[2][K], done[2], tmem_ready, tmem ptr
+  static constexpr size_t BYTES = OFF_BAR + 96;
   static constexpr int TMEM_COLS = 256;                       // two accumulators of 96 columns at 0 and 128
 };
 constexpr int kFwdThreads = kProducers + 32;
@@ -192,10 +192,10 @@ tc5_n8_fwd_kernel(const TileArgs a) {
   unsigned char* Zb = sm8 + L::OFF_Z;
   unsigned char* Hb = sm8 + L::OFF_H;
   float* Ss = reinterpret_cast<float*>(sm8 + L::OFF_S);
-  uint64_t* ops_ready = reinterpret_cast<uint64_t*>(sm8 + L::OFF_BAR);
-  uint64_t* done = ops_ready + 2;
-  uint64_t* tmem_ready = ops_ready + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 48);
+  uint64_t* ops_ready = reinterpret_cast<uint64_t*>(sm8 + L::OFF_BAR);   // [buffer][tap k]: state k of the tile stored
+  uint64_t* done = ops_ready + 2 * K;
+  uint64_t* tmem_ready = done + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 80);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = warp, c = lane;
   const bool producer = tid < kProducers;
@@ -205,8 +205,8 @@ tc5_n8_fwd_kernel(const TileArgs a) {
 
   // ---- mbarriers (nothing here touches global memory: under PDL it overlaps the previous kernel's tail) -----
   if (tid == 0) {
-    tc5::mbar_init(&ops_ready[0], 16);
-    tc5::mbar_init(&ops_ready[1], 16);
+#pragma unroll
+    for (int i = 0; i < 2 * K; ++i) tc5::mbar_init(&ops_ready[i], 16);
     tc5::mbar_init(&done[0], 1);
     tc5::mbar_init(&done[1], 1);
     tc5::mbar_init(tmem_ready, 1);
@@ -240,8 +240,6 @@ tc5_n8_fwd_kernel(const TileArgs a) {
       const uint64_t bd = tc5::make_desc(h_base, PB, 128);
       for (int itl = 0; itl < rg.ntiles; ++itl) {
         const int buf = itl & 1;
-        tc5::mbar_wait_suspend(&ops_ready[buf], (itl >> 1) & 1);       // (also orders the taps, written before the
-        tc5::fence_after_sync();                               //  producers' first arrival)
         const uint32_t zb = z_base + buf * L::Z_BYTES;
         uint64_t a0 = tc5::make_desc(zb, 128, PV), a1 = tc5::make_desc(zb + V_PLANE, 128, PV),
                  a2 = tc5::make_desc(zb + 2 * V_PLANE, 128, PV);
@@ -249,6 +247,10 @@ tc5_n8_fwd_kernel(const TileArgs a) {
         const uint32_t acc = tmem + buf * 128;
 #pragma unroll 1
         for (int s = 0; s < KG / 16; ++s) {
+          if ((s & (G / 16 - 1)) == 0) {   // the MMAs of tap k start as soon as z_k is stored (the hops go on)
+            tc5::mbar_wait_suspend(&ops_ready[buf * K + s / (G / 16)], (itl >> 1) & 1);   // (k = 0 also orders the
+            tc5::fence_after_sync();                                                      //  taps of the first tile)
+          }
           tc5::mma_bf16_ss(acc, a0, b, kI96, s == 0 ? 0u : 1u);     // p0 . [q0 | q1 | q2]
           tc5::mma_bf16_ss(acc, a1, b, kI64, 1u);                   // p1 . [q0 | q1]
           tc5::mma_bf16_ss(acc, a2, b, kI32, 1u);                   // p2 .  q0
@@ -301,12 +303,12 @@ tc5_n8_fwd_kernel(const TileArgs a) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         store_chunk3(Zt + k * G * 16, V_PLANE, z);
+        tc5::fence_proxy_async();
+        if (k == 0) tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(&ops_ready[buf * K + k]);
         if (k + 1 < K) hop8(Sw, z);
       }
-      tc5::fence_proxy_async();
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(&ops_ready[buf]);
     };
 
     // taps -> B[n = f][k = c] planes (c = k*G + g: the rows of h are already c-contiguous); warps 0..11 convert
@@ -380,8 +382,8 @@ struct BwdLayout {
   static constexpr int OFF_H = 2 * VX_BYTES;
   static constexpr int OFF_S = OFF_H + HB_BYTES;
   static constexpr int OFF_DB = OFF_S + S_BYTES;
-  static constexpr int OFF_BAR = OFF_DB + F * 4;               // ops_ready[2], dx_done[2], dh_done[2], tmem_ready, ptr
-  static constexpr size_t BYTES = OFF_BAR + 80;
+  static constexpr int OFF_BAR = OFF_DB + F * 4;               // ops_ready[2][K], dx_done[2], dh_done[2], tmem_ready, ptr
+  static constexpr size_t BYTES = OFF_BAR + 112;
   static constexpr int TMEM_COLS = 512;                        // buffer b: dX blocks at b*256, dH blocks at b*256+128
 };
 constexpr int kBwdThreads = kProducers + 64;                   // + warp 16 (dX chain) + warp 17 (dH chain)
@@ -397,10 +399,10 @@ tc5_n8_bwd_kernel(const TileArgs a) {
   float* Ss = reinterpret_cast<float*>(sm8 + L::OFF_S);
   float* dbs = reinterpret_cast<float*>(sm8 + L::OFF_DB);
   uint64_t* ops_ready = reinterpret_cast<uint64_t*>(sm8 + L::OFF_BAR);
-  uint64_t* dx_done = ops_ready + 2;
-  uint64_t* dh_done = ops_ready + 4;
-  uint64_t* tmem_ready = ops_ready + 6;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 64);
+  uint64_t* dx_done = ops_ready + 2 * K;   // ops_ready[buffer][k]: V_k (and, with k = 0, XT) of the tile stored
+  uint64_t* dh_done = dx_done + 2;
+  uint64_t* tmem_ready = dh_done + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sm8 + L::OFF_BAR + 96);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int j = warp, c = lane;
   const bool producer = tid < kProducers;
@@ -411,8 +413,9 @@ tc5_n8_bwd_kernel(const TileArgs a) {
 
   if (tid == 0) {
 #pragma unroll
+    for (int i = 0; i < 2 * K; ++i) tc5::mbar_init(&ops_ready[i], 16);
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
-      tc5::mbar_init(&ops_ready[i], 16);
       tc5::mbar_init(&dx_done[i], 1);
       tc5::mbar_init(&dh_done[i], 1);
     }
@@ -452,9 +455,12 @@ tc5_n8_bwd_kernel(const TileArgs a) {
       const uint32_t v_base = tc5::smem_u32(Vb), h_base = tc5::smem_u32(Hb);
       for (int itl = 0; itl < rg.ntiles; ++itl) {
         const int buf = itl & 1;
-        tc5::mbar_wait_suspend(&ops_ready[buf], (itl >> 1) & 1);
-        tc5::fence_after_sync();
         const uint32_t vb = v_base + buf * L::VX_BYTES;
+        if (!is_dx) {   // the dH chain contracts over rows: it needs every V_k of the tile
+#pragma unroll
+          for (int k = 0; k < K; ++k) tc5::mbar_wait_suspend(&ops_ready[buf * K + k], (itl >> 1) & 1);
+          tc5::fence_after_sync();
+        }
         if (is_dx) {
           // dX[row][g] = sum_c V[row][c] H[c][g]: A = VT read MN-major (M = row), 16 columns c per MMA
           constexpr uint32_t kI96 = tc5::idesc_bf16(128, 96, 1, 0), kI64 = tc5::idesc_bf16(128, 64, 1, 0),
@@ -465,6 +471,10 @@ tc5_n8_bwd_kernel(const TileArgs a) {
           const uint32_t acc = tmem + buf * 256;
 #pragma unroll 1
           for (int s = 0; s < KF / 16; ++s) {
+            if ((s & (F / 16 - 1)) == 0) {   // the MMAs of V_k start as soon as V_k is stored (the hops go on)
+              tc5::mbar_wait_suspend(&ops_ready[buf * K + s / (F / 16)], (itl >> 1) & 1);
+              tc5::fence_after_sync();
+            }
             tc5::mma_bf16_ss(acc, a0, b, kI96, s == 0 ? 0u : 1u);
             tc5::mma_bf16_ss(acc, a1, b, kI64, 1u);
             tc5::mma_bf16_ss(acc, a2, b, kI32, 1u);
@@ -559,12 +569,12 @@ tc5_n8_bwd_kernel(const TileArgs a) {
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         store_chunk3(Vt + k * F * 16, V_PLANE, v);
+        tc5::fence_proxy_async();
+        if (k == 0) tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(&ops_ready[buf * K + k]);
         if (k + 1 < K) hop8(Sw, v);
       }
-      tc5::fence_proxy_async();
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(&ops_ready[buf]);
     };
 
     // taps -> B[n = g][k = c] planes, c = k*F + f:  B[g][c] = h[f][k*G + g]  (loads coalesced along g); warps

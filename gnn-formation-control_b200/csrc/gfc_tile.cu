@@ -13,13 +13,15 @@ pack_taps_kernel(const float* __restrict__ h, int F, int KG, int for_bwd, float4
     out[p] = pack_one(h, F, KG, for_bwd, p);
 }
 
-// out[i] = sum_p parts[p][i] in a fixed order (deterministic).  A CTA reduces 32 outputs:
-// 8 partial-classes x 32 lanes, then a fixed-order combine through shared memory.  Two
-// independent segments (dH and db) share one launch.
-__global__ void __launch_bounds__(256)
+// out[i] = sum_p parts[p][i] in a fixed order (deterministic).  A CTA reduces 32 outputs: 32 partial-classes x 32
+// lanes — every thread issues all of its (<= 8) loads before the first add, so the whole reduction is one L2
+// round trip for up to 256 partial buffers — then a fixed-order combine through shared memory.  Two independent
+// segments (dH and db) share one launch.
+constexpr int kReduceClasses = 32;
+__global__ void __launch_bounds__(32 * kReduceClasses)
 reduce_parts_kernel(const float* __restrict__ pa, int npa, int na, float* __restrict__ oa, int blocks_a,
                     const float* __restrict__ pb, int npb, int nb, float* __restrict__ ob) {
-  __shared__ float red[8][32];
+  __shared__ float red[kReduceClasses][33];
   // programmatic dependent launch: wait for the kernel that wrote the partials; let the next kernel's CTAs queue
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -30,22 +32,23 @@ reduce_parts_kernel(const float* __restrict__ pa, int npa, int na, float* __rest
   const int i = blk * 32 + lane;
   float s = 0.f;
   if (i < n) {
-    int p = pg;
-    for (; p + 56 < nparts; p += 64) {
+    for (int p0 = pg; p0 < nparts; p0 += 8 * kReduceClasses) {
       float v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = parts[(size_t)(p + 8 * u) * n + i];
+      for (int u = 0; u < 8; ++u) {
+        const int p = p0 + u * kReduceClasses;
+        v[u] = p < nparts ? parts[(size_t)p * n + i] : 0.f;
+      }
 #pragma unroll
       for (int u = 0; u < 8; ++u) s += v[u];
     }
-    for (; p < nparts; p += 8) s += parts[(size_t)p * n + i];
   }
   red[pg][lane] = s;
   __syncthreads();
   if (pg == 0 && i < n) {
     float r = red[0][lane];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) r += red[k][lane];
+    for (int k = 1; k < kReduceClasses; ++k) r += red[k][lane];
     out[i] = r;
   }
 }
@@ -166,7 +169,7 @@ int launch_reduce_parts(const float* parts_a, int nparts_a, int n_a, float* out_
   if (blocks_a + blocks_b == 0) return GFC_OK;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(blocks_a + blocks_b);
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(32 * kReduceClasses);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

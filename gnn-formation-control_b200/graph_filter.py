@@ -292,3 +292,63 @@ class GraphFilter(GraphFilterBatch):
         if Nin < N:
             u = torch.index_select(u, 2, torch.arange(Nin, device=u.device))  # graphML.py:1216-1217
         return u.to(x.dtype)
+
+
+class GraphFilterBatchGSO(GraphFilterBatch):
+    """``GraphFilterBatchGSO(G, F, K, E=1, bias=True)`` — graphML.py:2174 (``matrixPowersBatch`` :2063,
+    ``batchLSIGF`` :2107): one GSO per batch element given as ``[B,N,N]`` or ``[B,E,N,N]``.
+
+    The reference precomputes the powers ``S_b^k`` and contracts ``x_b S_b^k`` with the taps; that is the filter of
+    ``GraphFilterBatch`` evaluated in another order, so the same fused kernels serve it (the powers are never
+    formed on the device path).  Like the reference it runs in x's dtype (no float64 casts), requires
+    ``x.shape == (B, G, N)`` exactly (no zero-padding) and, given a GSO of another shape, keeps the previous one."""
+
+    def __init__(self, G, F, K, E=1, bias=True, activation=None, negative_slope=0.01, precision="fp32"):
+        super().__init__(G, F, K, E, bias, activation, negative_slope, precision, reference_dtype=False)
+        self.B = None
+
+    def addGSO(self, S):
+        # graphML.py:2229-2244: 3-d -> one edge feature; 4-d must carry E edge features; anything else is ignored
+        if len(S.shape) == 3 and S.shape[1] == S.shape[2]:
+            self.S = S.unsqueeze(1)
+        elif len(S.shape) == 4 and S.shape[1] == self.E and S.shape[2] == S.shape[3]:
+            self.S = S
+        self.N = self.S.shape[2]
+        self.B = self.S.shape[0]
+        self._src = None
+
+    @property
+    def SK(self):
+        """the reference's attribute ``SK [B,E,K,N,N]`` (graphML.py:2246), formed on demand with torch ops"""
+        S = self.S
+        cur = torch.eye(self.N, dtype=S.dtype, device=S.device).repeat(self.B, self.E, 1, 1)
+        out = [cur]
+        for _ in range(1, self.K):
+            cur = torch.matmul(cur, S)
+            out.append(cur)
+        return torch.stack(out, dim=2)
+
+    def addPositions(self, pos, radius, mode="binary_le"):
+        super().addPositions(pos, radius, mode)
+        self.B = pos.shape[0]
+
+    def forward(self, x):
+        _require_cuda(x, "x")
+        # batchLSIGF's asserts (graphML.py:2149-2154)
+        assert x.shape[0] == self.B
+        assert x.shape[1] == self.G
+        assert x.shape[2] == self.N
+        src = self._source(x.device)
+        ymem = graph_filter(x, self.weight, self.bias, src, self.activation, self.negative_slope, self.precision)
+        return ymem.permute(0, 2, 1).to(x.dtype)
+
+    def extra_repr(self):
+        reprString = "in_features=%d, out_features=%d, " % (
+            self.G, self.F) + "filter_taps=%d, " % (
+            self.K) + "edge_features=%d, " % (self.E) + \
+            "bias=%s, " % (self.bias is not None)
+        if self.S is not None:
+            reprString += "GSO stored: number_nodes=%d, batch_size=%d" % (self.N, self.B)
+        else:
+            reprString += "no GSO stored"
+        return reprString

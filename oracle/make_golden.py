@@ -158,6 +158,47 @@ def same_gso_goldens():
                         **run_ref_same_gso(gml, h, b, S, x, dOut, False))
 
 
+def batch_gso_goldens():
+    """GraphFilterBatchGSO (graphML.py:2174): precomputed powers, fp32, S given as [B,N,N] and as [B,E,N,N]"""
+    gml = ri.graphml()
+    rng = np.random.default_rng(777)
+
+    def run(h, b, S, x, dOut, leaky):
+        F, E, K, G = h.shape
+        m = gml.GraphFilterBatchGSO(G, F, K, E, bias=True)
+        with torch.no_grad():
+            m.weight.copy_(torch.from_numpy(h))
+            m.bias.copy_(torch.from_numpy(b))
+        xt = torch.from_numpy(x).clone().requires_grad_(True)
+        m.addGSO(torch.from_numpy(S))
+        y = m(xt)
+        if leaky:
+            y = torch.nn.LeakyReLU()(y)
+        (y * torch.from_numpy(dOut)).sum().backward()
+        return dict(h=h, b=b, S=S, x=x, dOut=dOut, leaky=np.int32(leaky), y=y.detach().numpy(), dX=xt.grad.numpy(),
+                    dH=m.weight.grad.numpy(), db=m.bias.grad.numpy(), repr=np.array(m.extra_repr()))
+
+    def taps(G, F, K, E, seed):
+        torch.manual_seed(seed)
+        m = gml.GraphFilterBatchGSO(G, F, K, E, bias=True)
+        return m.weight.detach().numpy().copy(), m.bias.detach().numpy().copy()
+
+    # 3-d S: the normalised GSOs of 24 frames of the 8-robot fixture, 32 -> 32, K = 3, LeakyReLU
+    g8 = np.load(os.path.join(OUT, "gso_expert8.npz"))
+    S = g8["s_symnorm"][40:64].astype(np.float32)
+    h, b = taps(32, 32, 3, 1, 20)
+    x = rng.standard_normal((24, 32, 8)).astype(np.float32)
+    dOut = rng.standard_normal((24, 32, 8)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "batchgso_cfg2_3d.npz"), **run(h, b, S, x, dOut, True))
+
+    # 4-d S with two edge features, weighted and asymmetric, odd sizes
+    h, b = taps(5, 6, 4, 2, 21)
+    S = (0.5 * rng.standard_normal((3, 2, 7, 7))).astype(np.float32)
+    x = rng.standard_normal((3, 5, 7)).astype(np.float32)
+    dOut = rng.standard_normal((3, 6, 7)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "batchgso_e2_4d.npz"), **run(h, b, S, x, dOut, False))
+
+
 def filter_goldens():
     gml = ri.graphml()
     rng = np.random.default_rng(1234)
@@ -237,5 +278,6 @@ if __name__ == "__main__":
     gso_goldens()
     filter_goldens()
     same_gso_goldens()
+    batch_gso_goldens()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

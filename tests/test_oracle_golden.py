@@ -17,11 +17,12 @@ GSO_FILES = ["gso_expert3.npz", "gso_expert8.npz", "gso_expert12.npz", "gso_ties
 FILTER_FILES = ["filter_cfg1.npz", "filter_general_e2.npz", "filter_k1_nobias.npz", "filter_nin_lt_n.npz",
                 "filter_cfg2_symnorm.npz", "filter_cyclic.npz", "filter_cfg4_n12.npz"]
 SAME_GSO_FILES = ["samegso_e2_nin.npz", "samegso_cfg2_f32.npz"]
+BATCH_GSO_FILES = ["batchgso_cfg2_3d.npz", "batchgso_e2_4d.npz"]
 
 
 def test_golden_inventory(golden_dir):
     have = sorted(os.path.basename(p) for p in glob.glob(os.path.join(golden_dir, "*.npz")))
-    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES)
+    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES)
 
 
 @pytest.mark.parametrize("name", GSO_FILES)
@@ -118,6 +119,20 @@ def test_same_gso_oracle_matches_reference_golden(golden_dir, name):
     (yt * torch.from_numpy(g["dOut"])).sum().backward()
     assert rel_err(yt.detach().numpy(), g["y"]) < 1e-6
     assert rel_err(x.grad.numpy(), g["dX"]) < 1e-6 and rel_err(h.grad.numpy(), g["dH"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", BATCH_GSO_FILES)
+def test_batch_gso_oracle_matches_reference_golden(golden_dir, name):
+    """GraphFilterBatchGSO (graphML.py:2174) contracts x with precomputed powers S^k in fp32: the same filter as
+    GraphFilterBatch up to fp32 rounding, so the fp64 oracle reproduces its outputs to ~1e-6"""
+    g = np.load(os.path.join(golden_dir, name))
+    gb = {k: g[k] for k in g.files}
+    if gb["S"].ndim == 3:
+        gb["S"] = gb["S"][:, None]
+    y, dX, dH, db = _run_oracle(gb)
+    assert g["y"].dtype == np.float32
+    assert rel_err(y, g["y"]) < 3e-6 and rel_err(dX, g["dX"]) < 3e-6
+    assert rel_err(dH, g["dH"]) < 3e-6 and rel_err(db, g["db"]) < 3e-6
 
 
 def test_closed_form_gradients_match_autograd():
