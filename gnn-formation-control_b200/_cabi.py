@@ -71,6 +71,8 @@ def _load():
 
 
 lib = _load()
+if os.environ.get("GFC_PDL") is not None:   # A/B switch for the programmatic-dependent-launch attribute
+    lib.gfc_set_option(OPT_PDL, int(os.environ["GFC_PDL"]))
 
 
 class GfcError(RuntimeError):

@@ -2,14 +2,16 @@
 // the per-CTA partials the backward kernels left behind) and all-reduces it over NVLink peer memory.
 //
 //   phase 1  each CTA owns a slice of the flat [dH | db] bucket: it sums the slice over this rank's partial buffers
-//            and stores the result straight into slot `rank` of EVERY peer's exchange buffer (P2P stores through
-//            NVSwitch; the local copy is an ordinary store), then releases a flag (epoch number) on every peer;
-//   phase 2  the CTA waits until the flags of all ranks for its slice carry the current epoch and sums the `world`
-//            slots in rank order (so every rank obtains bit-identical gradients), scales, writes the bucket.
-// One-shot: 2 x (world-1) x n floats cross the links per rank, ~one NVLink round trip of latency; there is no
-// grid-wide synchronisation (slices are independent) and no host involvement.  The exchange buffers are double
-// buffered by epoch parity: a rank can only start epoch e+2 after every peer has finished reading epoch e,
-// because it needs the peers' epoch e+1 flags to complete epoch e+1 first.
+//            and stores every result, packed with the epoch number into ONE 64-bit word {value, epoch}, straight
+//            into slot `rank` of EVERY peer's exchange buffer (P2P stores through NVSwitch);
+//   phase 2  the CTA polls its own slice of the `world` slots until every word carries the current epoch and sums
+//            the values in rank order (so every rank obtains bit-identical gradients), scales, writes the bucket.
+// The flag travels inside the data word (a naturally aligned 64-bit store is single-copy atomic), so there is no
+// release fence / acknowledgement round trip on the sender and no separate flag hop: the exchange costs one one-way
+// NVLink latency.  2 x (world-1) x n words cross the links per rank; there is no grid-wide synchronisation (slices
+// are independent) and no host involvement.  The exchange buffers are double buffered by epoch parity: a rank can
+// only start epoch e+2 after every peer has finished reading epoch e, because it needs the peers' epoch e+1 words to
+// complete epoch e+1 first.
 // The reference has no distributed code (single .to('cuda'), suhaas_agent.py:19); this replaces the
 // reduce_parts_kernel + ncclAllReduce pair of the plain DP path.
 #include "gfc_common.cuh"
@@ -18,41 +20,44 @@
 
 namespace gfc {
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_word(unsigned long long* p, float v, unsigned int epoch) {
+  const unsigned long long w = ((unsigned long long)epoch << 32) | __float_as_uint(v);
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long* p) {
+  unsigned long long w;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return w;
 }
 
 struct DpPeers {
-  float* buf[GFC_DP_MAX_WORLD];          // exchange buffer of every rank: [2][world][n]
-  unsigned int* sig[GFC_DP_MAX_WORLD];   // flags of every rank: [2][world][nblocks], then epochs [nblocks]
+  unsigned long long* buf[GFC_DP_MAX_WORLD];   // exchange buffer of every rank: {value, epoch} words [2][world][n]
+  unsigned int* sig[GFC_DP_MAX_WORLD];         // per-rank state: epochs [nblocks] (local use only)
 };
 
-__global__ void __launch_bounds__(256)
+constexpr int kDpClasses = 32;   // partial-classes per output: 32 lanes x 32 classes = 1024 threads per CTA
+
+__global__ void __launch_bounds__(32 * kDpClasses)
 reduce_allreduce_kernel(const float* __restrict__ pa, int npa, int na, const float* __restrict__ pb, int npb, int nb,
                         float* __restrict__ out, const DpPeers peers, int rank, int world, float scale) {
   __shared__ unsigned int s_epoch;
+  __shared__ float red[kDpClasses][33];
   // programmatic dependent launch: this grid may be scheduled while the backward kernel drains
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int n = na + nb;
   const int nblocks = gridDim.x, c = blockIdx.x;
-  const int per = (n + nblocks - 1) / nblocks;
+  const int per = (((n + nblocks - 1) / nblocks) + 31) & ~31;    // slice of this CTA: whole 32-float groups
   const int lo = c * per, hi = min(n, lo + per);
-  unsigned int* my_sig = peers.sig[rank];
-  unsigned int* epochs = my_sig + (size_t)2 * world * nblocks;
+  unsigned int* epochs = peers.sig[rank];
   if (threadIdx.x == 0) { s_epoch = epochs[c] + 1; epochs[c] = s_epoch; }
   __syncthreads();
   const unsigned int e = s_epoch;
   const int par = e & 1;
   // ---- phase 1: local fixed-order reduction of the slice, pushed to every rank ---------------------
-  // 32 elements at a time: 8 partial-classes x 32 lanes (8 loads in flight per thread), then a fixed-order
-  // combine through shared memory — the same order on every launch, so the gradients are deterministic
-  __shared__ float red[8][32];
+  // 32 outputs at a time: 32 partial-classes x 32 lanes; every thread issues all of its loads (<= 8 per pass)
+  // before the first add, so a slice of up to 256 partial buffers costs ONE L2 round trip; then a fixed-order
+  // combine through shared memory — the same order on every launch and every rank: deterministic gradients
   const int lane = threadIdx.x & 31, pg = threadIdx.x >> 5;
   for (int base = lo; base < hi; base += 32) {
     const int i = base + lane;
@@ -60,41 +65,44 @@ reduce_allreduce_kernel(const float* __restrict__ pa, int npa, int na, const flo
     if (i < hi) {
       const float* parts; int np, nn, ii;
       if (i < na) { parts = pa; np = npa; nn = na; ii = i; } else { parts = pb; np = npb; nn = nb; ii = i - na; }
-      int p = pg;
-      for (; p + 56 < np; p += 64) {
+      for (int p0 = pg; p0 < np; p0 += 8 * kDpClasses) {
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = parts[(size_t)(p + 8 * u) * nn + ii];
+        for (int u = 0; u < 8; ++u) {
+          const int p = p0 + u * kDpClasses;
+          v[u] = p < np ? parts[(size_t)p * nn + ii] : 0.f;
+        }
 #pragma unroll
         for (int u = 0; u < 8; ++u) s += v[u];
       }
-      for (; p < np; p += 8) s += parts[(size_t)p * nn + ii];
     }
     red[pg][lane] = s;
     __syncthreads();
-    if (pg == 0 && i < hi) {
+    if (pg < world && i < hi) {      // warp r pushes the finished 32 values to rank r (P2P stores through NVSwitch)
       float t = red[0][lane];
 #pragma unroll
-      for (int k = 1; k < 8; ++k) t += red[k][lane];
-      for (int r = 0; r < world; ++r) peers.buf[r][((size_t)par * world + rank) * n + i] = t;
+      for (int k = 1; k < kDpClasses; ++k) t += red[k][lane];
+      st_word(peers.buf[pg] + ((size_t)par * world + rank) * n + i, t, e);
     }
     __syncthreads();
   }
-  // (the barrier orders every thread's stores before thread t's system-scope release: cumulativity)
-  __syncthreads();
-  if ((int)threadIdx.x < world)
-    st_release_sys(peers.sig[threadIdx.x] + ((size_t)par * world + rank) * nblocks + c, e);
-  // ---- phase 2: wait for every rank's slice, sum in rank order ---------------------------------------
-  if ((int)threadIdx.x < world) {
-    const unsigned int* f = my_sig + ((size_t)par * world + threadIdx.x) * nblocks + c;
-    while ((int)(ld_acquire_sys(f) - e) < 0) { __nanosleep(40); }
-  }
-  __syncthreads();
-  const float* mine = peers.buf[rank] + (size_t)par * world * n;
-  for (int i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    float s = 0.f;
-    for (int r = 0; r < world; ++r) s += __ldcg(mine + (size_t)r * n + i);
-    out[i] = s * scale;
+  // ---- phase 2: poll every rank's words of the slice, sum in rank order ---------------------------------
+  const unsigned long long* mine = peers.buf[rank] + (size_t)par * world * n;
+  for (int base = lo; base < hi; base += 32) {
+    const int i = base + lane;
+    if (pg < world && i < hi) {      // warp r waits for rank r's 32 words
+      const unsigned long long* src = mine + (size_t)pg * n + i;
+      unsigned long long w = ld_word(src);
+      while ((unsigned int)(w >> 32) != e) { __nanosleep(20); w = ld_word(src); }
+      red[pg][lane] = __uint_as_float((unsigned int)w);
+    }
+    __syncthreads();
+    if (pg == 0 && i < hi) {
+      float t = red[0][lane];
+      for (int r = 1; r < world; ++r) t += red[r][lane];
+      out[i] = t * scale;
+    }
+    __syncthreads();
   }
 }
 
@@ -112,14 +120,14 @@ int launch_reduce_allreduce(const float* pa, int npa, int na, const float* pb, i
   GFC_REQUIRE(dp.peer_buf && dp.peer_sig && out, GFC_ERR_BAD_ARG, "dp: NULL exchange pointers");
   DpPeers peers;
   for (int r = 0; r < dp.world; ++r) {
-    peers.buf[r] = static_cast<float*>(dp.peer_buf[r]);
+    peers.buf[r] = static_cast<unsigned long long*>(dp.peer_buf[r]);
     peers.sig[r] = static_cast<unsigned int*>(dp.peer_sig[r]);
     GFC_REQUIRE(peers.buf[r] && peers.sig[r], GFC_ERR_BAD_ARG, "dp: NULL peer pointer for rank %d", r);
   }
   const int n = na + nb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(dp_blocks(n));
-  cfg.blockDim = dim3(256);
+  cfg.blockDim = dim3(32 * kDpClasses);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -138,9 +146,10 @@ using namespace gfc;
 
 extern "C" size_t gfc_dp_exchange_bytes(int n, int world) {
   if (n <= 0 || world <= 0 || world > GFC_DP_MAX_WORLD) return 0;
-  return align_up((size_t)2 * world * n * sizeof(float), 256);
+  return align_up((size_t)2 * world * n * sizeof(unsigned long long), 256);
 }
 extern "C" size_t gfc_dp_signal_bytes(int n, int world) {
   if (n <= 0 || world <= 0 || world > GFC_DP_MAX_WORLD) return 0;
-  return align_up(((size_t)2 * world + 1) * dp_blocks(n) * sizeof(unsigned int), 256);
+  (void)world;
+  return align_up((size_t)dp_blocks(n) * sizeof(unsigned int), 256);
 }

@@ -3,7 +3,7 @@
 #include "gfc_common.cuh"
 
 #define GFC_DP_MAX_WORLD 16
-#define GFC_DP_MAX_BLOCKS 64
+#define GFC_DP_MAX_BLOCKS 128
 
 namespace gfc {
 

@@ -159,9 +159,10 @@ int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const int32_t* col
  * batch of graphs over ranks and sums the flat gradient bucket [dH | db].  These
  * entry points replace "second-stage reduction kernel + ncclAllReduce" by ONE
  * kernel that reduces this rank's per-CTA partials and exchanges the result over
- * NVLink peer memory (one-shot: every rank stores its slice into every peer's
- * exchange buffer, signals, waits for all peers, sums in rank order -> every rank
- * holds bit-identical gradients).
+ * NVLink peer memory (one-shot: every rank stores its slice, as 64-bit words
+ * {value, epoch}, into every peer's exchange buffer, polls its own buffer until all
+ * peers' words carry the epoch, sums in rank order -> every rank holds bit-identical
+ * gradients).
  *   peer_buf[r] / peer_sig[r]: device pointers, valid on THIS device, to rank r's
  *   exchange / signal buffer (peer-mapped memory, e.g. torch symmetric memory or
  *   cudaIpc handles), each of gfc_dp_exchange_bytes / gfc_dp_signal_bytes for the
