@@ -642,7 +642,7 @@ def main():
                 import gnnfc
                 hp.enable_peer_exchange(gnnfc.PeerExchange(hp.grads.numel(), dev))
                 collective = ("fused into the gradient-reduction kernel: one-shot all-reduce of the flat [dH|db] bucket "
-                              "over NVLink peer memory (symmetric memory, P2P stores + flags)")
+                              "over NVLink peer memory (symmetric memory, P2P stores of {value, epoch} words)")
             except Exception as ex:   # symmetric memory unavailable on this box: the NCCL collective still is
                 sys.stderr.write("bench: peer exchange unavailable (%s); using NCCL\n" % str(ex)[:160])
     use_graph = not args.no_graph
