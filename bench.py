@@ -174,13 +174,12 @@ class HotPath:
                                          C.PREC_FP32_3XTF32, C.ptr(self.wsf), self.nbf, st), "gfc_filter_fwd_pos")
         n = C.last_launch_count()
         if self.layers == 2:
-            # layer 2 consumes layer 1's node-major output; the reference permutes it back to
-            # [B,F,N] (suhaas_model.py:186) before the next GraphFilterBatch
-            self.xt.copy_(self.y[i].permute(0, 2, 1))
-            C.check(C.lib.gfc_filter_fwd_pos(C.ptr(self.xt), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h2),
-                                             C.ptr(self.b2), C.ptr(self.y2[i]), B, N, G, F, K, C.ACT_LEAKY_RELU,
-                                             SLOPE, C.PREC_FP32_3XTF32, C.ptr(self.wsf), self.nbf, st),
-                    "gfc_filter_fwd_pos")
+            # layer 2 consumes layer 1's node-major output in place (the reference hands the next GraphFilterBatch
+            # a [B,F,N] view over exactly this memory, graphML.py:2362): no transposing copy between the layers
+            C.check(C.lib.gfc_filter_fwd_pos_nm(C.ptr(self.y[i]), C.ptr(self.pos[i]), RADIUS, self.mode,
+                                                C.ptr(self.h2), C.ptr(self.b2), C.ptr(self.y2[i]), B, N, G, F, K,
+                                                C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32, C.ptr(self.wsf),
+                                                self.nbf, st), "gfc_filter_fwd_pos_nm")
             n += C.last_launch_count()
         return n
 

@@ -41,6 +41,7 @@ SIGNATURES = {
     "gfc_tile_plan_info": (_i, [_i] * 7 + [ct.POINTER(_i)]),
     "gfc_filter_fwd": (_i, [_p, _p, _p, _p, _p] + [_i] * 6 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_filter_fwd_pos": (_i, [_p, _p, _d, _i, _p, _p, _p] + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),
+    "gfc_filter_fwd_pos_nm": (_i, [_p, _p, _d, _i, _p, _p, _p] + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_filter_bwd": (_i, [_p] * 8 + [_i] * 6 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_filter_bwd_pos": (_i, [_p, _p, _d, _i] + [_p] * 6 + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_dp_exchange_bytes": (_sz, [_i, _i]),

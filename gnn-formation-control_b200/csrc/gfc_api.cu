@@ -537,6 +537,40 @@ extern "C" int gfc_filter_fwd_pos(const float* x, const float* pos, double radiu
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
+extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double radius, int mode, const float* h,
+                                     const float* bias, float* y, int B, int N, int G, int F, int K,
+                                     int act, float slope, int precision,
+                                     void* workspace, size_t workspace_bytes, void* stream) {
+  const char* fn = "gfc_filter_fwd_pos_nm";
+  cudaStream_t st = (cudaStream_t)stream;
+  launch_counter() = 0;
+  int rc = check_common(fn, B, N, G, F, K, 1, act, precision);
+  if (rc) return rc;
+  if (B == 0) return GFC_OK;
+  GFC_REQUIRE(x_nm && pos && h && y, GFC_ERR_BAD_ARG, "%s: NULL pointer", fn);
+  double thr = 0; bool norm = false;
+  rc = gso_mode_threshold(mode, radius, &thr, &norm);
+  if (rc) return rc;
+  GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
+  GFC_REQUIRE(use_wide(gs, norm, N, G, F, K, 0, precision) && aligned16(x_nm) && aligned16(y) && aligned16(pos),
+              GFC_ERR_UNSUPPORTED, "%s: node-major input needs the tcgen05 wide path (binary GSO, G, F in {64,128}, "
+              "N <= 128, 16-byte aligned tensors); transpose to [B,G,N] and call gfc_filter_fwd_pos", fn);
+  TilePlan p;
+  GFC_REQUIRE(plan_tile(B, N, G, F, K, 0, GSRC_POS, &p), GFC_ERR_UNSUPPORTED, "%s: shape not covered", fn);
+  rc = need_ws(fn, workspace, workspace_bytes, p.ws_bytes + wide_ws_extra(B, N, G, F, K, 0));
+  if (rc) return rc;
+  TileArgs a{};
+  set_thresholds(a, thr, norm);
+  uint16_t* hp = reinterpret_cast<uint16_t*>(static_cast<char*>(workspace) + p.ws_bytes);
+  rc = launch_wide_pack(h, G, F, K, 0, hp, st);
+  if (rc) return rc;
+  WideArgs wa{};
+  wa.pos = pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
+  wa.in = x_nm; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K;
+  wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
+  return launch_wide(wa, G, F, 2, st);
+}
+
 extern "C" int gfc_filter_bwd(const float* x, const float* S, const float* h, const float* y_out,
                               const float* dY, float* dX, float* dH, float* db,
                               int B, int N, int G, int F, int K, int E, int act, float slope, int precision,

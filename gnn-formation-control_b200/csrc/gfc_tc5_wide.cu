@@ -17,6 +17,7 @@
 //     tap, and run the epilogue (bias + activation, or the dX transpose) of tile t while the
 //     issuing thread already feeds the tensor core with tile t+1.
 // MODE 0: forward,  IN = x [B,G,N],  OUT = y [B,N,F]   (CIN = G, COUT = F)
+// MODE 2: forward with the input given node-major, IN = x [B,N,G] (a previous layer's output), OUT = y [B,N,F]
 // MODE 1: backward dX: V_0 = dY o act'(y), V_k = P V_{k-1}, dX = sum_k V_k H_k^T-contraction
 //         (IN = dY [B,N,F], OUT = dX [B,G,N]; CIN = F, COUT = G) — the closed form of the autograd
 //         graph of graphML.py:2342-2366 for a symmetric 0/1 GSO.
@@ -177,7 +178,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
   const int t_end = min(w.ntiles, t_begin + tiles_per_cta);
 
   // ---- one-time setup -------------------------------------------------------------------------
-  for (int i = tid; i < COUT; i += kWideThreads) sbias[i] = (MODE == 0 && w.bias) ? __ldg(w.bias + i) : 0.f;
+  for (int i = tid; i < COUT; i += kWideThreads) sbias[i] = (MODE != 1 && w.bias) ? __ldg(w.bias + i) : 0.f;
   if (tid == 0) {
     for (int i = 0; i < L::NSTAGE; ++i) { tc5::mbar_init(&h_full[i], 1); tc5::mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -348,7 +349,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
           const bool ok = row < rows_used;
           const size_t off = ((size_t)b0 * N + row) * CIN + s * L::CS + 4 * (lane % PPR);
           float4 v = ldg_f32x4(w.in + off, ok);
-          if (w.act != GFC_ACT_NONE) {
+          if (MODE == 1 && w.act != GFC_ACT_NONE) {
             const float4 yo = ldg_f32x4(w.yout + off, ok);
             v.x = act_grad(v.x, yo.x, w.act, w.slope);
             v.y = act_grad(v.y, yo.y, w.act, w.slope);
@@ -515,7 +516,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         tc5::mbar_wait(&out_full[ob], (par_ofl >> ob) & 1); par_ofl ^= 1u << ob;
         tc5::fence_after_sync();
         GFC_KSTAMP(271);
-        if constexpr (MODE == 0) {
+        if constexpr (MODE != 1) {
           // y tile through swizzled staging buffers and the TMA store engine: full 128-byte lines
 #pragma unroll 1
           for (int pc = 0; pc < COUT / 32; ++pc) {
@@ -1103,7 +1104,7 @@ static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   a.tma_out = 0;
-  if (MODE == 0) {   // y viewed as [B*N rows, COUT cols]; one box = [gpc*N rows x 32 cols]
+  if (MODE != 1) {   // y viewed as [B*N rows, COUT cols]; one box = [gpc*N rows x 32 cols]
     int rc = encode_tmap_2d(&tmap, a.out, COUT, (uint64_t)a.B * a.N, 32, (uint32_t)(a.gpc * a.N));
     if (rc) return rc;
     a.tma_out = 1;
@@ -1115,7 +1116,7 @@ static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   if (rc) return rc;
   const int grid = a.ntiles < di.sm_count ? a.ntiles : di.sm_count;
   kern<<<grid, kWideThreads, L::BYTES, st>>>(a, tmap);
-  GFC_LAUNCH_CHECK(MODE == 0 ? "tc5_wide_kernel<fwd>" : "tc5_wide_kernel<dX>");
+  GFC_LAUNCH_CHECK(MODE == 0 ? "tc5_wide_kernel<fwd>" : MODE == 1 ? "tc5_wide_kernel<dX>" : "tc5_wide_kernel<fwd,node-major in>");
   return GFC_OK;
 }
 
@@ -1125,10 +1126,11 @@ int launch_wide(const WideArgs& a0, int G, int F, int mode, cudaStream_t st) {
   a.gpc = 128 / a.N;
   if (a.gpc > a.B) a.gpc = a.B;
   a.ntiles = ceil_div(a.B, a.gpc);
-  const int CIN = mode == 0 ? G : F, COUT = mode == 0 ? F : G;
+  const int CIN = mode != 1 ? G : F, COUT = mode != 1 ? F : G;
 #define GFC_WIDE_CASE(ci, co)                                                   \
   if (CIN == ci && COUT == co)                                                  \
-    return mode == 0 ? launch_wide_t<ci, co, 0>(a, st) : launch_wide_t<ci, co, 1>(a, st);
+    return mode == 0 ? launch_wide_t<ci, co, 0>(a, st)                          \
+         : mode == 1 ? launch_wide_t<ci, co, 1>(a, st) : launch_wide_t<ci, co, 2>(a, st);
   GFC_WIDE_CASE(128, 128)
   GFC_WIDE_CASE(64, 64)
   GFC_WIDE_CASE(128, 64)

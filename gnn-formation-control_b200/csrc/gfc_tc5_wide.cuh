@@ -8,7 +8,7 @@ struct WideArgs {
   const float* pos;        // [B,N,2]
   double thr;              // squared-distance threshold, fp64 rule (gfc_gso.cu)
   float thr_lo, thr_hi;    // fp32 screening band
-  const float* in;         // MODE 0: x [B,G,N];  MODE 1: dY [B,N,F]
+  const float* in;         // MODE 0: x [B,G,N];  MODE 1: dY [B,N,F];  MODE 2: x [B,N,G]
   const float* yout;       // MODE 1: forward output [B,N,F] (activation mask) or null
   const uint16_t* hpack;   // taps as bf16x3 planes in ring-stage order (wide_pack_taps_kernel)
   const float* bias;       // MODE 0: [F] or null
@@ -47,7 +47,7 @@ bool wide_dh_supported(int N, int G, int F, int K);
 int wide_dh_nparts(int B, int N, int F, int K);   // number of partial buffers launch_wide_dh writes
 int launch_wide_dh(const WideDhArgs& a, int G, int F, cudaStream_t st);
 
-// mode 0 = forward, 1 = backward dX
+// mode 0 = forward, 1 = backward dX, 2 = forward with node-major input x [B,N,G] (launch_wide only; pack / support as mode 0)
 bool wide_supported(int N, int G, int F, int K, int mode);
 size_t wide_pack_bytes(int G, int F, int K);
 int launch_wide_pack(const float* h, int G, int F, int K, int mode, uint16_t* out, cudaStream_t st);

@@ -61,13 +61,33 @@ class _LSIGF(torch.autograd.Function):
         B, Gx, N = x.shape
         assert Gx == G
         dev = x.device
-        x32 = x.detach().to(torch.float32).contiguous()
         w32 = weight.detach().to(torch.float32).contiguous()
         b32 = bias.detach().to(torch.float32).contiguous().view(-1) if bias is not None else None
         y = torch.empty((B, N, F_), dtype=torch.float32, device=dev)
+        # Stacked layers: the previous layer's output is a [B,G,N] VIEW over node-major [B,N,G] memory (the
+        # reference's own layout, graphML.py:2362).  Where the node-major entry point applies it is consumed in
+        # place — no transposing copy between the layers.
+        x32 = None
+        if (src.kind == _SRC_POS and x.dtype == torch.float32 and N > 1 and G > 1
+                and x.stride() == (N * G, 1, G)):
+            with torch.cuda.device(dev):
+                nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 0)
+                ws = _workspace(nb, dev)
+                rc = C.lib.gfc_filter_fwd_pos_nm(C.ptr(x), C.ptr(src.pos), src.radius, src.mode, C.ptr(w32),
+                                                 C.ptr(b32), C.ptr(y), B, N, G, F_, K, act, slope, prec,
+                                                 C.ptr(ws), nb, _stream())
+            if rc == C.GFC_OK:
+                x32 = x.detach()            # made contiguous only if a backward pass asks for it
+            elif rc != C.GFC_ERR_UNSUPPORTED:
+                C.check(rc, "gfc_filter_fwd_pos_nm")
+        done = x32 is not None
+        if not done:
+            x32 = x.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
             st = _stream()
-            if src.kind == _SRC_DENSE:
+            if done:
+                pass
+            elif src.kind == _SRC_DENSE:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 0)
                 ws = _workspace(nb, dev)
                 C.check(C.lib.gfc_filter_fwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(b32), C.ptr(y),
@@ -96,6 +116,7 @@ class _LSIGF(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dY):
         x32, w32, yout = ctx.saved_tensors
+        x32 = x32.contiguous()
         src, act, slope, prec = ctx.src, ctx.act, ctx.slope, ctx.prec
         F_, E, K, G = w32.shape
         B, _, N = x32.shape

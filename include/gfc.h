@@ -99,6 +99,16 @@ int gfc_filter_fwd_pos(const float* x, const float* pos, double radius, int mode
                        int B, int N, int G, int F, int K,
                        int act, float slope, int precision,
                        void* workspace, size_t workspace_bytes, void* stream);
+/* gfc_filter_fwd_pos with the input given NODE-major, x_nm [B, N, G] — the memory layout of a previous layer's
+ * output y — so stacked layers (suhaas_model.py:112-121 with more than one entry in nGraphFilterTaps) chain
+ * without the transposing copy of the reference's [B,F,N] view.  Available where the tcgen05 wide path applies
+ * (binary GSO rule, G and F in {64,128}, N <= 128, 16-byte aligned tensors); GFC_ERR_UNSUPPORTED otherwise —
+ * transpose and call gfc_filter_fwd_pos.  Same workspace as gfc_filter_workspace_bytes(..., backward = 0). */
+int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double radius, int mode,
+                          const float* h, const float* bias, float* y,
+                          int B, int N, int G, int F, int K,
+                          int act, float slope, int precision,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- (c) filter backward (replaces autograd through graphML.py:2342-2366) -- *
  * y_out is the forward OUTPUT (after the activation); it is only read when
