@@ -696,7 +696,7 @@ tile_bwd_kernel(const TileArgs a) {
       if (a.vec_ok) {
         const float4* d4 = reinterpret_cast<const float4*>(dsrc);
         const float4* y4 = reinterpret_cast<const float4*>(ysrc);
-        constexpr int U = 4;   // (dY, y) pairs in flight per thread
+        constexpr int U = CFG::kThreads >= 512 ? 1 : 4;   // (dY, y) pairs in flight per thread (64-register CTAs: 1)
         const int total4 = total >> 2;
         for (int q0 = tid; q0 < total4; q0 += U * CFG::kThreads) {
           float4 v[U], yo[U];
