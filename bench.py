@@ -266,17 +266,23 @@ def timed_steps(torch, hp, steps, warmup, world, dist, use_graph):
                     one(s)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            # one graph = several passes over the ring (about a millisecond of GPU work per replay, so the host
+            # enqueues far ahead of the device even with the clock sampler running); the remainder is ONE graph
+            unit = ring * max(1, min(8, 64 // ring))
+            while unit > ring and unit > steps:
+                unit -= ring
             gring = torch.cuda.CUDAGraph()
             with torch.cuda.graph(gring):
-                for s in range(ring):
+                for s in range(unit):
                     one(s)
             singles = []
-            for s in range(min(ring, steps % ring)):
+            if steps % unit:
                 g1 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g1):
-                    one(s)
+                    for s in range(steps % unit):
+                        one(s)
                 singles.append(g1)
-            graphs = (gring, singles)
+            graphs = (gring, singles, unit)
             gring.replay()
             torch.cuda.synchronize()
         except Exception as ex:
@@ -292,8 +298,8 @@ def timed_steps(torch, hp, steps, warmup, world, dist, use_graph):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     if graphs is not None:
-        gring, singles = graphs
-        for _ in range(steps // ring):
+        gring, singles, unit = graphs
+        for _ in range(steps // unit):
             gring.replay()
         for g1 in singles:
             g1.replay()

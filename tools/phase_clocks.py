@@ -9,8 +9,10 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg2"
 w = WORKLOADS[name]; dev = torch.device("cuda", 0)
 hp = HotPath(w, dev, 2)
 buf = torch.zeros(1184 * 16, dtype=torch.int64, device=dev)
-for which, labels in (("fwd", ["setup", "load+gso", "hops", "mma+store"]),
-                      ("bwd", ["setup", "load+gso", "hops", "dH mma", "U mma", "horner+dX", "final"])):
+# stamps of thread 0 (warp 0): 0 = first loads issued, 1 = produce(tile 0) done, 2 = produce(tile 1) done,
+# 3 = first epilogue (fwd: y stored; bwd: dX stored), 4 = bwd: dH tile drained, 6 = bwd: partials written
+for which, labels in (("fwd", ["setup", "produce(0)", "produce(1)", "epilogue(0)"]),
+                      ("bwd", ["setup", "produce(0)", "produce(1)", "dX epilogue(0)", "dH epilogue(0)"])):
     if which == "bwd" and not w["train"]:
         continue
     for _ in range(3):
@@ -31,20 +33,6 @@ for which, labels in (("fwd", ["setup", "load+gso", "hops", "mma+store"]),
         col = d[:, i]
         print("   %-12s %8.0f [%6.0f, %6.0f]" % (labels[i + 1], np.median(col), np.percentile(col, 10), np.percentile(col, 90)))
     print("   setup (entry -> stamp 0): %.0f cycles median" % np.median(t[:, 0] - t[:, 7]))
-    if which == "fwd" and t[:, 10].any():
-        seq = [("entry", 7), ("setup done", 0), ("x+gso issued", 10), ("tap0 A written", 11), ("fence.proxy", 12),
-               ("barrier k0", 1), ("tap0 MMAs issued", 13), ("barrier k1", 14), ("mbar wait k2", 15),
-               ("tap loop done", 2), ("epilogue done", 3)]
-        base = t[:, 7]
-        print("   tcgen05 fwd timeline (median cycles since entry): " +
-              ", ".join("%s=%.0f" % (nm, np.median(t[:, sl] - base)) for nm, sl in seq))
-    if which == "bwd" and t[:, 10].any():
-        tt = t[t[:, 10] != 0]
-        seq = [("produce(1) start", 10), ("gso", 11), ("act+X", 12), ("V0 stored", 13), ("hop1", 14), ("all stored", 15), ("arrived", 5),
-               ("stamp2", 2), ("dX epi", 3), ("dH epi", 4), ("final", 6)]
-        base = tt[:, 7]
-        print("   bwd timeline (median cycles since entry): " +
-              ", ".join("%s=%.0f" % (nm, np.median(tt[:, sl] - base)) for nm, sl in seq))
     ns0, ns1 = t[:, 8], t[:, 9]
     print("   globaltimer: CTA starts spread %.2f us, CTA duration median %.2f us, first start -> last end %.2f us"
           % ((ns0.max() - ns0.min()) / 1e3, np.median(ns1 - ns0) / 1e3, (ns1.max() - ns0.min()) / 1e3))
