@@ -72,8 +72,10 @@ def _load():
 
 
 lib = _load()
-if os.environ.get("GFC_PDL") is not None:   # A/B switch for the programmatic-dependent-launch attribute
+if os.environ.get("GFC_PDL") is not None:   # A/B switches (profiling aids)
     lib.gfc_set_option(OPT_PDL, int(os.environ["GFC_PDL"]))
+if os.environ.get("GFC_DISABLE_TCGEN05") is not None:
+    lib.gfc_set_option(OPT_DISABLE_TCGEN05, int(os.environ["GFC_DISABLE_TCGEN05"]))
 
 
 class GfcError(RuntimeError):

@@ -79,18 +79,60 @@ gso_build_kernel(const float* __restrict__ pos, int B, int N, double thr, int gp
   }
 }
 
-// ---- CSR builder --------------------------------------------------------------
+// CSR build, pass 1 and 3 share one loop: a CTA owns 256 rows of ONE graph and walks over all nodes of that graph
+// staged in shared memory (128-bit broadcasts), deciding each pair with the fp32 screen of the fused kernels
+// (s < thr_lo: inside, s > thr_hi: outside) and the exact fp64 rule of (a) only inside the rounding band — the same
+// bit-exact decisions as sqdist64(...) <= thr everywhere, at a third of the instruction count.
+static __device__ __noinline__ bool csr_pair_exact(float xi, float yi, float xj, float yj, double thr) {
+  return sqdist64(xi, yi, xj, yj) <= thr;
+}
+constexpr int kCsrChunk = 2048;   // nodes staged per pass (16 KB)
+
+template <bool FILL, bool NORM>
 __global__ void __launch_bounds__(256)
-csr_count_kernel(const float* __restrict__ pos, int B, int N, double thr, int32_t* __restrict__ deg) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= (long long)B * N) return;
-  const int b = (int)(row / N), i = (int)(row - (long long)b * N);
-  const float* gp = pos + (size_t)b * N * 2;
-  const float xi = gp[2 * i], yi = gp[2 * i + 1];
+csr_rows_kernel(const float* __restrict__ pos, int N, double thr, float thr_lo, float thr_hi,
+                int32_t* __restrict__ deg, const int32_t* __restrict__ rowptr, long long nnz_stride,
+                int32_t* __restrict__ colidx, float* __restrict__ vals) {
+  __shared__ float2 sp[kCsrChunk];
+  const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  const bool valid = i < N;
+  const float2* gp = reinterpret_cast<const float2*>(pos) + (size_t)b * N;
+  const float2 pi = valid ? __ldg(gp + i) : make_float2(0.f, 0.f);
+  const int32_t* rp = FILL ? rowptr + (size_t)b * (N + 1) : nullptr;
   int d = 0;
-  for (int m = 0; m < N; ++m)
-    d += (m != i) && (sqdist64(xi, yi, __ldg(gp + 2 * m), __ldg(gp + 2 * m + 1)) <= thr);
-  deg[row] = d;
+  long long w = 0;
+  double isd_i = 0.0;
+  if (FILL && valid) {
+    w = (long long)b * nnz_stride + rp[i];
+    if (NORM) isd_i = inv_sqrt_deg(rp[i + 1] - rp[i]);
+  }
+  for (int m0 = 0; m0 < N; m0 += kCsrChunk) {
+    const int cnt = min(kCsrChunk, N - m0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < cnt; q += 256) sp[q] = __ldg(gp + m0 + q);
+    __syncthreads();
+    if (!valid) continue;
+#pragma unroll 4
+    for (int q = 0; q < cnt; ++q) {
+      const float2 pj = sp[q];
+      const float dx = pi.x - pj.x, dy = pi.y - pj.y;
+      const float sq = fmaf(dx, dx, dy * dy);
+      bool e = sq < thr_lo;
+      if (!e && !(sq > thr_hi)) e = csr_pair_exact(pi.x, pi.y, pj.x, pj.y, thr);   // rounding band: exact rule
+      e = e && (m0 + q != i);
+      if (FILL) {
+        if (e) {
+          const int m = m0 + q;
+          colidx[w] = m;
+          if (vals) vals[w] = NORM ? (float)__dmul_rn(inv_sqrt_deg(rp[m + 1] - rp[m]), isd_i) : 1.f;
+          ++w;
+        }
+      } else {
+        d += e ? 1 : 0;
+      }
+    }
+  }
+  if (!FILL && valid) deg[(size_t)b * N + i] = d;
 }
 
 // rowptr[b, 0..N] = exclusive scan of deg[b, :]; one CTA per graph.
@@ -116,32 +158,17 @@ csr_scan_kernel(const int32_t* __restrict__ deg, int N, int32_t* __restrict__ ro
   for (int i = lo; i < hi; ++i) { rp[i] = run; run += d[i]; }
 }
 
-template <bool NORM>
-__global__ void __launch_bounds__(256)
-csr_fill_kernel(const float* __restrict__ pos, int B, int N, double thr,
-                const int32_t* __restrict__ rowptr, long long nnz_stride,
-                int32_t* __restrict__ colidx, float* __restrict__ vals) {
-  const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (row >= (long long)B * N) return;
-  const int b = (int)(row / N), i = (int)(row - (long long)b * N);
-  const float* gp = pos + (size_t)b * N * 2;
-  const int32_t* rp = rowptr + (size_t)b * (N + 1);
-  const float xi = gp[2 * i], yi = gp[2 * i + 1];
-  long long w = (long long)b * nnz_stride + rp[i];
-  const long long wend = (long long)b * nnz_stride + rp[i + 1];
-  const double isd_i = NORM ? inv_sqrt_deg(rp[i + 1] - rp[i]) : 0.0;
-  for (int m = 0; m < N && w < wend; ++m) {
-    if ((m != i) && (sqdist64(xi, yi, __ldg(gp + 2 * m), __ldg(gp + 2 * m + 1)) <= thr)) {
-      colidx[w] = m;
-      if (vals) vals[w] = NORM ? (float)__dmul_rn(inv_sqrt_deg(rp[m + 1] - rp[m]), isd_i) : 1.f;
-      ++w;
-    }
-  }
-}
-
 }  // namespace gfc
 
 using namespace gfc;
+
+// fp32 screening band around the squared-distance threshold (same band as set_thresholds in gfc_api.cu: an fp32
+// squared distance differs from the fp64 one by < 2^-22 relative; 4e-6 on each side)
+static void screen_band(double thr, float* lo, float* hi) {
+  if (!(thr >= 0)) { *lo = -1.f; *hi = -1.f; return; }
+  *lo = nextafterf((float)(thr * (1.0 - 4e-6)), -INFINITY);
+  *hi = nextafterf((float)(thr * (1.0 + 4e-6)), INFINITY);
+}
 
 static int mode_threshold(int mode, double radius, double* thr, bool* norm) {
   switch (mode) {
@@ -206,9 +233,12 @@ extern "C" int gfc_csr_count(const float* pos, int B, int N, double radius, int 
   double thr; bool norm;
   int rc = mode_threshold(mode, radius, &thr, &norm);
   if (rc) return rc;
-  long long rows = (long long)B * N;
-  csr_count_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pos, B, N, thr, deg);
-  GFC_LAUNCH_CHECK("csr_count_kernel");
+  GFC_REQUIRE(B <= 65535, GFC_ERR_UNSUPPORTED, "gfc_csr_count: B=%d > 65535 graphs per call", B);
+  float lo, hi;
+  screen_band(thr, &lo, &hi);
+  csr_rows_kernel<false, false><<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
+      pos, N, thr, lo, hi, deg, nullptr, 0, nullptr, nullptr);
+  GFC_LAUNCH_CHECK("csr_rows_kernel<count>");
   return GFC_OK;
 }
 
@@ -232,12 +262,16 @@ extern "C" int gfc_csr_fill(const float* pos, int B, int N, double radius, int m
   double thr; bool norm;
   int rc = mode_threshold(mode, radius, &thr, &norm);
   if (rc) return rc;
-  long long rows = (long long)B * N;
-  unsigned grid = (unsigned)((rows + 255) / 256);
+  GFC_REQUIRE(B <= 65535, GFC_ERR_UNSUPPORTED, "gfc_csr_fill: B=%d > 65535 graphs per call", B);
+  float lo, hi;
+  screen_band(thr, &lo, &hi);
+  const dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
   if (norm)
-    csr_fill_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, B, N, thr, rowptr, nnz_stride, colidx, vals);
+    csr_rows_kernel<true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, N, thr, lo, hi, nullptr, rowptr,
+                                                                         nnz_stride, colidx, vals);
   else
-    csr_fill_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, B, N, thr, rowptr, nnz_stride, colidx, vals);
-  GFC_LAUNCH_CHECK("csr_fill_kernel");
+    csr_rows_kernel<true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, N, thr, lo, hi, nullptr, rowptr,
+                                                                          nnz_stride, colidx, vals);
+  GFC_LAUNCH_CHECK("csr_rows_kernel<fill>");
   return GFC_OK;
 }
