@@ -119,6 +119,69 @@ hop_csr_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, const 
   }
 }
 
+// All hops of a CSR filter in ONE launch, one CTA per graph, the graph's current state [N x G] resident in shared
+// memory: hop t gathers the neighbour rows out of shared memory (instead of L2), keeps its results in registers
+// until every gather of the hop is done, then overwrites the shared state and writes the slot to the workspace
+// (coalesced) — the workspace is written once per slot and never re-read by the hops.
+//   forward  (ACCUM = false): slot k = hop(slot k-1),            k = 1 .. K-1   (first = 0,   step = +1)
+//   Horner   (ACCUM = true) : slot k = slot k + hop(slot k+1),   k = K-2 .. 0   (first = K-1, step = -1)
+constexpr int kHopsThreads = 1024, kHopsItems = 8;   // float4 results per thread: N * G <= 32768 floats
+template <bool ACCUM>
+__global__ void __launch_bounds__(kHopsThreads, 1)
+hops_csr_smem_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
+                     const float* __restrict__ vals, long long nnz_stride, int N, int G, int K, int first, int step,
+                     int count) {
+  extern __shared__ __align__(16) float zs[];            // [N][G]
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int C = K * G, G4 = G >> 2, total = N * G4;
+  const int32_t* rp = rowptr + (size_t)b * (N + 1);
+  const int32_t* ci = colidx + (size_t)b * nnz_stride;
+  const float* vv = vals ? vals + (size_t)b * nnz_stride : nullptr;
+  float* Wb = W + (size_t)b * N * C;
+  for (int idx = tid; idx < total; idx += kHopsThreads) {   // source slot -> shared memory
+    const int n = idx / G4, g4 = idx - n * G4;
+    *reinterpret_cast<float4*>(zs + (size_t)n * G + g4 * 4) =
+        *reinterpret_cast<const float4*>(Wb + (size_t)n * C + (size_t)first * G + g4 * 4);
+  }
+  __syncthreads();
+  int ksrc = first;
+  for (int t = 0; t < count; ++t, ksrc += step) {
+    const int kdst = ksrc + step;
+    float4 acc[kHopsItems];
+#pragma unroll
+    for (int it = 0; it < kHopsItems; ++it) {
+      const int idx = tid + it * kHopsThreads;
+      acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total) {
+        const int n = idx / G4, g4 = idx - n * G4;
+        if (ACCUM) acc[it] = *reinterpret_cast<const float4*>(Wb + (size_t)n * C + (size_t)kdst * G + g4 * 4);
+        const int beg = rp[n], end = rp[n + 1];
+        const float* src = zs + g4 * 4;
+        for (int i = beg; i < end; ++i) {
+          const int m = ci[i];
+          const float w = vv ? vv[i] : 1.f;
+          const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * G);
+          acc[it].x = fmaf(w, z.x, acc[it].x);
+          acc[it].y = fmaf(w, z.y, acc[it].y);
+          acc[it].z = fmaf(w, z.z, acc[it].z);
+          acc[it].w = fmaf(w, z.w, acc[it].w);
+        }
+      }
+    }
+    __syncthreads();                                        // every gather of this hop is done
+#pragma unroll
+    for (int it = 0; it < kHopsItems; ++it) {
+      const int idx = tid + it * kHopsThreads;
+      if (idx < total) {
+        const int n = idx / G4, g4 = idx - n * G4;
+        *reinterpret_cast<float4*>(zs + (size_t)n * G + g4 * 4) = acc[it];
+        *reinterpret_cast<float4*>(Wb + (size_t)n * C + (size_t)kdst * G + g4 * 4) = acc[it];
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // D = dY * act'(y_out)
 __global__ void __launch_bounds__(256)
 dpre_kernel(const float* __restrict__ dY, const float* __restrict__ yout, float* __restrict__ D,
@@ -243,6 +306,41 @@ int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const
   if (accum) hop_csr_kernel<true><<<grid, 256, 0, st>>>(W, rowptr, colidx, vals, nnz_stride, B, N, G, K, ksrc, kdst);
   else hop_csr_kernel<false><<<grid, 256, 0, st>>>(W, rowptr, colidx, vals, nnz_stride, B, N, G, K, ksrc, kdst);
   GFC_LAUNCH_CHECK("hop_csr_kernel");
+  return GFC_OK;
+}
+
+// the chain of K-1 hops (forward or Horner); falls back to one hop_csr_kernel launch per hop when a graph's state
+// does not fit the shared-memory kernel
+int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                    long long nnz_stride, int B, int N, int G, int K, int horner, cudaStream_t st) {
+  if (K < 2) return GFC_OK;
+  const size_t smem = (size_t)N * G * sizeof(float);
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  if ((long long)N * G <= (long long)kHopsThreads * kHopsItems * 4 && smem + 1024 <= (size_t)di.smem_optin) {
+    const int first = horner ? K - 1 : 0, step = horner ? -1 : 1;
+    if (horner) {
+      GFC_CUDA_TRY(cudaFuncSetAttribute(hops_csr_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hops_csr_smem_kernel<true><<<B, kHopsThreads, smem, st>>>(W, rowptr, colidx, vals, nnz_stride, N, G, K, first, step, K - 1);
+    } else {
+      GFC_CUDA_TRY(cudaFuncSetAttribute(hops_csr_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      hops_csr_smem_kernel<false><<<B, kHopsThreads, smem, st>>>(W, rowptr, colidx, vals, nnz_stride, N, G, K, first, step, K - 1);
+    }
+    GFC_LAUNCH_CHECK("hops_csr_smem_kernel");
+    return GFC_OK;
+  }
+  if (horner) {
+    for (int k = K - 2; k >= 0; --k) {
+      rc = launch_hop_csr(W, rowptr, colidx, vals, nnz_stride, B, N, G, K, k + 1, k, 1, st);
+      if (rc) return rc;
+    }
+  } else {
+    for (int k = 1; k < K; ++k) {
+      rc = launch_hop_csr(W, rowptr, colidx, vals, nnz_stride, B, N, G, K, k - 1, k, 0, st);
+      if (rc) return rc;
+    }
+  }
   return GFC_OK;
 }
 

@@ -11,6 +11,9 @@ int launch_hop_dense(float* W, const float* S, int B, int N, int G, int E, int K
 int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    long long nnz_stride, int B, int N, int G, int K, int ksrc, int kdst, int accum,
                    cudaStream_t st);
+// all K-1 hops of the CSR filter (horner = 0: slot k = hop(slot k-1); 1: slot k += hop(slot k+1), transposed lists)
+int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                    long long nnz_stride, int B, int N, int G, int K, int horner, cudaStream_t st);
 int launch_dpre(const float* dY, const float* yout, float* D, long long n, int act, float slope, cudaStream_t st);
 int launch_colsum(const float* D, long long rows, int F, int rows_per_chunk, int nchunks, float* part,
                   cudaStream_t st);
