@@ -12,8 +12,10 @@ from . import _cabi
 from ._cabi import GfcError, version, last_launch_count
 from .gso import build_gso, build_csr, SparseGSO
 from .graph_filter import GraphFilterBatch, GraphFilter, GraphFilterBatchGSO, graph_filter
+from .data import robot_major_to_batch, graphs_from_recording, gso_batch_from_recording, positions_from_recording
 from .dp import GradBucket, PeerExchange, shard_range, broadcast_parameters
 
 __all__ = ["GraphFilterBatch", "GraphFilter", "GraphFilterBatchGSO", "graph_filter", "build_gso", "build_csr", "SparseGSO",
+           "robot_major_to_batch", "graphs_from_recording", "gso_batch_from_recording", "positions_from_recording",
            "GradBucket", "PeerExchange", "shard_range", "broadcast_parameters", "GfcError", "version",
            "last_launch_count"]

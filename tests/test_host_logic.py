@@ -91,3 +91,47 @@ def test_grad_bucket_pack_unpack_single_process():
     g1 = p1.grad.clone()
     b.allreduce(); b.unpack()
     assert torch.allclose(p1.grad, 2 * g1) and p2.grad is not None and float(p2.grad.abs().sum()) == 0
+
+
+# --------------------------------------------------------------------------- #
+# recorded-data re-layout
+# --------------------------------------------------------------------------- #
+def test_recording_relayout_matches_the_reference_loops():
+    """gnnfc.data.* == the Python loops of RobotDataset.__init__ (custom_dataset.py:15-63) and the agent's
+    robot-0 view (suhaas_agent.py:117)"""
+    import numpy as np
+    import torch
+    import gnnfc
+    rng = np.random.default_rng(5)
+    nA, T = 4, 7
+    graph_rows = (rng.random((nA * T, nA * nA)) < 0.5).astype(np.float32)     # data.py:43 layout, robots concatenated
+    gt_rows = rng.standard_normal((nA * T, 2)).astype(np.float32)
+    # the reference's loops, restated
+    c3 = np.zeros((T, nA, nA, nA))
+    c2 = np.zeros((T, nA, 2))
+    for i in range(T):
+        for j in range(nA):
+            c3[i, j] = graph_rows[j * T + i].reshape((nA, nA))                  # custom_dataset.py:40-42
+            c2[i, j] = gt_rows[j * T + i]                                        # custom_dataset.py:32-34
+    assert np.array_equal(gnnfc.graphs_from_recording(graph_rows, nA).numpy(), c3.astype(np.float32))
+    assert np.array_equal(gnnfc.robot_major_to_batch(gt_rows, nA).numpy(), c2.astype(np.float32))
+    S = gnnfc.gso_batch_from_recording(graph_rows, nA)
+    assert S.shape == (T, 1, nA, nA) and S.is_contiguous() and S.dtype == torch.float32
+    assert np.array_equal(S[:, 0].numpy(), c3[:, 0].astype(np.float32))          # suhaas_agent.py:117
+    # the live reference class, when the reference tree is present (build container only)
+    from oracle import refimport
+    if refimport.available():
+        import sys
+        sys.path.insert(0, refimport.REF_ROOT) if hasattr(refimport, "REF_ROOT") else sys.path.insert(0, "/root/reference")
+        try:
+            from custom_dataset import RobotDataset
+        finally:
+            sys.path.pop(0)
+        obs = rng.standard_normal((nA * T, 4)).astype(np.float32)
+        ds = RobotDataset(obs, gt_rows, graph_rows, np.zeros(nA * T), np.zeros(nA * T), nA, inW=2, inH=2)
+        assert np.array_equal(ds.graphs, c3) and np.array_equal(ds.gt, c2)
+        assert np.array_equal(gnnfc.graphs_from_recording(graph_rows, nA).numpy(), ds.graphs.astype(np.float32))
+    # positionList fixtures: [E, steps*nA, 2] with index t*nA + r
+    pl = rng.standard_normal((2, 5 * 3, 2))
+    p = gnnfc.positions_from_recording(pl, 3)
+    assert p.shape == (10, 3, 2) and np.allclose(p[6, 2].numpy(), pl[1, 1 * 3 + 2].astype(np.float32))
