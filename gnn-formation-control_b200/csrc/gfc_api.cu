@@ -46,6 +46,7 @@ int get_device_info(DeviceInfo* out) {
 
 int gso_mode_threshold(int mode, double radius, double* thr, bool* norm);  // gfc_gso.cu
 
+static int g_csr_fused = 1;
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // fp32 screening band around the fp64 threshold: the fp32 squared distance differs from the
@@ -467,6 +468,7 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_DISABLE_TCGEN05) { g_disable_tcgen05 = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_PDL) { g_pdl = value ? 1 : 0; return GFC_OK; }
   if (key == 99) { g_wide_no_prefetch = value; return GFC_OK; }
+  if (key == 97) { g_csr_fused = value ? 1 : 0; return GFC_OK; }   // A/B: fused CSR forward vs workspace pipeline
   if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 2; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
   return GFC_ERR_BAD_ARG;
@@ -649,6 +651,9 @@ extern "C" int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const i
   plan_generic(B, N, G, F, K, 1, 0, 0, &g);
   rc = need_ws(fn, workspace, workspace_bytes, g.ws_bytes);
   if (rc) return rc;
+  if (g_csr_fused && csr_fwd_fused_supported(N, G, F, K, nullptr) && aligned16(y))
+    return launch_csr_fwd_fused(x, rowptr, colidx, vals, nnz_stride, h, bias, y, B, N, G, F, K, act, slope,
+                                precision == GFC_PREC_TF32, st);
   float* Zw = reinterpret_cast<float*>(static_cast<char*>(workspace) + g.ws_z);
   const long long C = (long long)K * G;
   rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);

@@ -14,6 +14,11 @@ int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const
 // all K-1 hops of the CSR filter (horner = 0: slot k = hop(slot k-1); 1: slot k += hop(slot k+1), transposed lists)
 int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                     long long nnz_stride, int B, int N, int G, int K, int horner, cudaStream_t st);
+// whole CSR forward of a graph in one CTA (gfc_csr_fused.cu); GFC_ERR_UNSUPPORTED when the state does not fit
+bool csr_fwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes);
+int launch_csr_fwd_fused(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
+                         long long nnz_stride, const float* h, const float* bias, float* y, int B, int N, int G,
+                         int F, int K, int act, float slope, int single, cudaStream_t st);
 int launch_dpre(const float* dY, const float* yout, float* D, long long n, int act, float slope, cudaStream_t st);
 int launch_colsum(const float* D, long long rows, int F, int rows_per_chunk, int nchunks, float* part,
                   cudaStream_t st);
