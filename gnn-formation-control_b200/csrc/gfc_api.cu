@@ -656,9 +656,7 @@ extern "C" int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const i
                                 precision == GFC_PREC_TF32, st);
   float* Zw = reinterpret_cast<float*>(static_cast<char*>(workspace) + g.ws_z);
   const long long C = (long long)K * G;
-  rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);
-  if (rc) return rc;
-  rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, st);
+  rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, x, nullptr, st);
   if (rc) return rc;
   if (g.rows_ok) return rows_fwd(g, static_cast<char*>(workspace), Zw, h, bias, y, act, slope, precision, st);
   return launch_sgemm(Zw, C, 1, h, 1, C, y, F, 0, (long long)B * N, F, C, 1, bias, act, slope, st);
@@ -697,18 +695,14 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
   const long long C = (long long)K * G;
   if (g.rows_ok) {
     if (dH) {
-      rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);
-      if (rc) return rc;
-      rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, st);
+      rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, x, nullptr, st);
   if (rc) return rc;
     }
     rc = rows_bwd(g, wsb, Zw, h, (act != GFC_ACT_NONE) ? y_out : nullptr, dY, dX != nullptr, dH, db, act, slope,
                   precision, nullptr, st);
     if (rc) return rc;
     if (dX) {
-      rc = launch_hops_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, 1, st);
-  if (rc) return rc;
-      rc = launch_xpose_out(Zw, dX, B, N, G, 1, K, st);
+      rc = launch_hops_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, 1, nullptr, dX, st);
       if (rc) return rc;
     }
     return GFC_OK;
@@ -723,9 +717,7 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
     if (rc) return rc;
   }
   if (dH) {
-    rc = launch_xpose_in(x, Zw, B, N, G, 1, K, st);
-    if (rc) return rc;
-    rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, st);
+    rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, x, nullptr, st);
   if (rc) return rc;
     float* part = reinterpret_cast<float*>(wsb + g.ws_dhp);
     rc = launch_sgemm(Dw, 1, F, Zw, C, 1, part, C, (long long)nH, F, (int)C, rows, g.nsplit, nullptr,
@@ -737,9 +729,7 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
   if (dX) {
     rc = launch_sgemm(Dw, F, 1, h, C, 1, Zw, C, 0, rows, (int)C, F, 1, nullptr, GFC_ACT_NONE, 0.f, st);
     if (rc) return rc;
-    rc = launch_hops_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, 1, st);
-  if (rc) return rc;
-    rc = launch_xpose_out(Zw, dX, B, N, G, 1, K, st);
+    rc = launch_hops_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, 1, nullptr, dX, st);
     if (rc) return rc;
   }
   return GFC_OK;

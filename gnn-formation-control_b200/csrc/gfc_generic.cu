@@ -126,27 +126,46 @@ hop_csr_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, const 
 //   forward  (ACCUM = false): slot k = hop(slot k-1),            k = 1 .. K-1   (first = 0,   step = +1)
 //   Horner   (ACCUM = true) : slot k = slot k + hop(slot k+1),   k = K-2 .. 0   (first = K-1, step = -1)
 constexpr int kHopsThreads = 1024, kHopsItems = 8;   // float4 results per thread: N * G <= 32768 floats
+// xin  (forward only): the chain starts from x [B,G,N] itself — transposed into shared memory on the fly and written
+//       to slot `first` of the workspace — instead of from a slot an earlier transposing kernel filled;
+// dxout (Horner only): the final state (slot 0 = dX rows) leaves transposed as dX [B,G,N]; slot 0 is not written.
 template <bool ACCUM>
 __global__ void __launch_bounds__(kHopsThreads, 1)
 hops_csr_smem_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, const int32_t* __restrict__ colidx,
                      const float* __restrict__ vals, long long nnz_stride, int N, int G, int K, int first, int step,
-                     int count) {
-  extern __shared__ __align__(16) float zs[];            // [N][G]
+                     int count, const float* __restrict__ xin, float* __restrict__ dxout) {
+  extern __shared__ __align__(16) float zs[];            // [N][GS]
+  const int GS = G + 4;                                   // padded rows: the transposed passes stay 4-way at worst
   const int b = blockIdx.x, tid = threadIdx.x;
   const int C = K * G, G4 = G >> 2, total = N * G4;
   const int32_t* rp = rowptr + (size_t)b * (N + 1);
   const int32_t* ci = colidx + (size_t)b * nnz_stride;
   const float* vv = vals ? vals + (size_t)b * nnz_stride : nullptr;
   float* Wb = W + (size_t)b * N * C;
-  for (int idx = tid; idx < total; idx += kHopsThreads) {   // source slot -> shared memory
-    const int n = idx / G4, g4 = idx - n * G4;
-    *reinterpret_cast<float4*>(zs + (size_t)n * G + g4 * 4) =
-        *reinterpret_cast<const float4*>(Wb + (size_t)n * C + (size_t)first * G + g4 * 4);
+  if (xin) {                                              // x [G][N] -> state [N][GS]
+    const float* xb = xin + (size_t)b * G * N;
+    for (int idx = tid; idx < G * N; idx += kHopsThreads) {
+      const int gg = idx / N, n = idx - gg * N;
+      zs[(size_t)n * GS + gg] = __ldg(xb + idx);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < total; idx += kHopsThreads) {
+      const int n = idx / G4, g4 = idx - n * G4;
+      *reinterpret_cast<float4*>(Wb + (size_t)n * C + (size_t)first * G + g4 * 4) =
+          *reinterpret_cast<const float4*>(zs + (size_t)n * GS + g4 * 4);
+    }
+  } else {
+    for (int idx = tid; idx < total; idx += kHopsThreads) {   // source slot -> shared memory
+      const int n = idx / G4, g4 = idx - n * G4;
+      *reinterpret_cast<float4*>(zs + (size_t)n * GS + g4 * 4) =
+          *reinterpret_cast<const float4*>(Wb + (size_t)n * C + (size_t)first * G + g4 * 4);
+    }
   }
   __syncthreads();
   int ksrc = first;
   for (int t = 0; t < count; ++t, ksrc += step) {
     const int kdst = ksrc + step;
+    const bool to_dx = dxout != nullptr && t == count - 1;
     float4 acc[kHopsItems];
 #pragma unroll
     for (int it = 0; it < kHopsItems; ++it) {
@@ -160,7 +179,7 @@ hops_csr_smem_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, 
         for (int i = beg; i < end; ++i) {
           const int m = ci[i];
           const float w = vv ? vv[i] : 1.f;
-          const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * G);
+          const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * GS);
           acc[it].x = fmaf(w, z.x, acc[it].x);
           acc[it].y = fmaf(w, z.y, acc[it].y);
           acc[it].z = fmaf(w, z.z, acc[it].z);
@@ -174,11 +193,18 @@ hops_csr_smem_kernel(float* __restrict__ W, const int32_t* __restrict__ rowptr, 
       const int idx = tid + it * kHopsThreads;
       if (idx < total) {
         const int n = idx / G4, g4 = idx - n * G4;
-        *reinterpret_cast<float4*>(zs + (size_t)n * G + g4 * 4) = acc[it];
-        *reinterpret_cast<float4*>(Wb + (size_t)n * C + (size_t)kdst * G + g4 * 4) = acc[it];
+        *reinterpret_cast<float4*>(zs + (size_t)n * GS + g4 * 4) = acc[it];
+        if (!to_dx) *reinterpret_cast<float4*>(Wb + (size_t)n * C + (size_t)kdst * G + g4 * 4) = acc[it];
       }
     }
     __syncthreads();
+  }
+  if (dxout) {                                            // state [N][GS] -> dX [G][N]
+    float* db = dxout + (size_t)b * G * N;
+    for (int idx = tid; idx < G * N; idx += kHopsThreads) {
+      const int gg = idx / N, n = idx - gg * N;
+      db[idx] = zs[(size_t)n * GS + gg];
+    }
   }
 }
 
@@ -312,9 +338,9 @@ int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const
 // the chain of K-1 hops (forward or Horner); falls back to one hop_csr_kernel launch per hop when a graph's state
 // does not fit the shared-memory kernel
 int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                    long long nnz_stride, int B, int N, int G, int K, int horner, cudaStream_t st) {
-  if (K < 2) return GFC_OK;
-  const size_t smem = (size_t)N * G * sizeof(float);
+                    long long nnz_stride, int B, int N, int G, int K, int horner, const float* xin, float* dxout,
+                    cudaStream_t st) {
+  const size_t smem = (size_t)N * (G + 4) * sizeof(float);
   DeviceInfo di;
   int rc = get_device_info(&di);
   if (rc) return rc;
@@ -322,13 +348,20 @@ int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, cons
     const int first = horner ? K - 1 : 0, step = horner ? -1 : 1;
     if (horner) {
       GFC_CUDA_TRY(cudaFuncSetAttribute(hops_csr_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      hops_csr_smem_kernel<true><<<B, kHopsThreads, smem, st>>>(W, rowptr, colidx, vals, nnz_stride, N, G, K, first, step, K - 1);
+      hops_csr_smem_kernel<true><<<B, kHopsThreads, smem, st>>>(W, rowptr, colidx, vals, nnz_stride, N, G, K, first, step,
+                                                               K - 1, nullptr, dxout);
     } else {
       GFC_CUDA_TRY(cudaFuncSetAttribute(hops_csr_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      hops_csr_smem_kernel<false><<<B, kHopsThreads, smem, st>>>(W, rowptr, colidx, vals, nnz_stride, N, G, K, first, step, K - 1);
+      hops_csr_smem_kernel<false><<<B, kHopsThreads, smem, st>>>(W, rowptr, colidx, vals, nnz_stride, N, G, K, first, step,
+                                                                K - 1, xin, nullptr);
     }
     GFC_LAUNCH_CHECK("hops_csr_smem_kernel");
     return GFC_OK;
+  }
+  // per-hop fallback: transposing kernels around the chain
+  if (xin) {
+    rc = launch_xpose_in(xin, W, B, N, G, 1, K, st);
+    if (rc) return rc;
   }
   if (horner) {
     for (int k = K - 2; k >= 0; --k) {
@@ -341,6 +374,7 @@ int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, cons
       if (rc) return rc;
     }
   }
+  if (dxout) return launch_xpose_out(W, dxout, B, N, G, 1, K, st);
   return GFC_OK;
 }
 

@@ -11,9 +11,12 @@ int launch_hop_dense(float* W, const float* S, int B, int N, int G, int E, int K
 int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    long long nnz_stride, int B, int N, int G, int K, int ksrc, int kdst, int accum,
                    cudaStream_t st);
-// all K-1 hops of the CSR filter (horner = 0: slot k = hop(slot k-1); 1: slot k += hop(slot k+1), transposed lists)
+// all K-1 hops of the CSR filter (horner = 0: slot k = hop(slot k-1); 1: slot k += hop(slot k+1), transposed lists).
+// xin != null (forward): the chain starts from x [B,G,N] (slot 0 is filled from it); dxout != null (Horner): the
+// result leaves as dX [B,G,N] — the transposing passes are part of the chain.
 int launch_hops_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
-                    long long nnz_stride, int B, int N, int G, int K, int horner, cudaStream_t st);
+                    long long nnz_stride, int B, int N, int G, int K, int horner, const float* xin, float* dxout,
+                    cudaStream_t st);
 // whole CSR forward of a graph in one CTA (gfc_csr_fused.cu); GFC_ERR_UNSUPPORTED when the state does not fit
 bool csr_fwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes);
 int launch_csr_fwd_fused(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
