@@ -73,6 +73,8 @@ struct GenericPlan {
   int nsplit;          // split of the dH reduction
   int nchunks, rows_per_chunk;  // db partial sums
   size_t ws_s, ws_z, ws_d, ws_dhp, ws_dbp, ws_bytes;
+  int fused_bwd;       // CSR: the whole backward of a graph runs in one CTA (gfc_csr_fused.cu)
+  size_t ws_fdh, ws_fdb;   //   ... its per-graph partials [B][F*C] and [B][F]
   int rows_ok;         // the tap contractions run on the tensor-core tile kernels ("rows" plan, VAR_ROWS)
   TilePlan rows;       //   ... with this plan; its partial buffers / packed taps live at ws_rows
   size_t ws_rows;
@@ -114,6 +116,12 @@ static void plan_generic(int B, int N, int G, int F, int K, int E, int backward,
     g->nchunks = (int)((rows + g->rows_per_chunk - 1) / g->rows_per_chunk);
     if (g->nchunks < 1) g->nchunks = 1;
     g->ws_dbp = off; off += align_up((size_t)g->nchunks * F * sizeof(float), 256);
+  }
+  g->fused_bwd = (backward && E == 1 && !need_s && csr_bwd_fused_supported(N, G, F, K, nullptr)) ? 1 : 0;
+  g->ws_fdh = g->ws_fdb = off;
+  if (g->fused_bwd) {
+    g->ws_fdh = off; off += align_up((size_t)B * F * C * sizeof(float), 256);
+    g->ws_fdb = off; off += align_up((size_t)B * F * sizeof(float), 256);
   }
   g->rows_ok = rows_plan(rows, C, F, backward, &g->rows) ? 1 : 0;
   g->ws_rows = off;
@@ -693,6 +701,17 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
   float* Dw = reinterpret_cast<float*>(wsb + g.ws_d);
   const long long rows = (long long)B * N;
   const long long C = (long long)K * G;
+  if (g_csr_fused && g.fused_bwd && aligned16(dY) && (act == GFC_ACT_NONE || aligned16(y_out))) {
+    // one CTA per graph: V_0 = dY o act'(y), transposed-list hops in shared memory, dX / dH / db from the same state
+    float* dhp = reinterpret_cast<float*>(wsb + g.ws_fdh);
+    float* dbp = reinterpret_cast<float*>(wsb + g.ws_fdb);
+    rc = launch_csr_bwd_fused(x, rowptr_t, colidx_t, vals_t, nnz_stride, h, (act != GFC_ACT_NONE) ? y_out : nullptr, dY,
+                              dX, dH ? dhp : nullptr, db ? dbp : nullptr, B, N, G, F, K, act, slope,
+                              precision == GFC_PREC_TF32, st);
+    if (rc) return rc;
+    if (!dH && !db) return GFC_OK;
+    return launch_reduce_parts(dH ? dhp : nullptr, B, (int)nH, dH, db ? dbp : nullptr, B, F, db, st);
+  }
   if (g.rows_ok) {
     if (dH) {
       rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, x, nullptr, st);

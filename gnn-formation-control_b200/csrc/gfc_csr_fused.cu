@@ -131,6 +131,205 @@ csr_fwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ ro
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// backward, same structure (closed form of the autograd graph, no recomputation of the forward states):
+//   V_0 = dY o act'(y),  V_k = V_{k-1} S^T  (transposed lists),
+//   dX = sum_k V_k H_k^T,   dH_k = V_k^T X,   db = column sums of V_0.
+// The state V_k [N x F] lives in shared memory.  Per tap: (a) dX (+)= V_k H_k^T on the tensor cores, accumulated by
+// read-modify-write of the L2-resident dX tile (feature-major [G][N], 32-byte segments); (b) dH_k: the node
+// dimension is split over the 32 warps (3xTF32 MMAs with the X fragments read from x in L2), partial tiles meet in
+// a shared-memory accumulator through shared atomics; (c) the next state is gathered through the transposed
+// lists.  One partial [F x K*G] (+ db) per graph leaves the CTA; reduce_parts_kernel sums them in a fixed order.
+template <int NTG>   // G / 8
+__global__ void __launch_bounds__(kFusedThreads, 1)
+csr_bwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ rowptr_t,
+                     const int32_t* __restrict__ colidx_t, const float* __restrict__ vals_t, long long nnz_stride,
+                     const float* __restrict__ h, const float* __restrict__ yout, const float* __restrict__ dY,
+                     float* __restrict__ dX, float* __restrict__ dHp, float* __restrict__ dbp,
+                     int N, int G, int F, int K, int act, float slope, int single) {
+  extern __shared__ __align__(16) float smem[];
+  const int FS = F + 4;
+  const int MT = (N + 15) >> 4, KSF = F >> 3, KG = K * G, NTC = KG >> 3, MTF = F >> 4;
+  float* vs = smem;                                                        // [MT*16][FS]
+  float4* Hs = reinterpret_cast<float4*>(smem + (size_t)MT * 16 * FS);     // taps, B fragments of H_k^T (for_bwd)
+  float* dHs = smem + (size_t)MT * 16 * FS + (size_t)KG * F * 2;           // [F][KG] running dH of this graph
+  float* dbs = dHs + (size_t)F * KG;                                       // [F]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int F4 = F >> 2, total = N * F4;
+  const int32_t* rp = rowptr_t + (size_t)b * (N + 1);
+  const int32_t* ci = colidx_t + (size_t)b * nnz_stride;
+  const float* vv = vals_t ? vals_t + (size_t)b * nnz_stride : nullptr;
+  const float* xb = x ? x + (size_t)b * G * N : nullptr;
+  float* dxb = dX ? dX + (size_t)b * G * N : nullptr;
+  const bool want_dh = dHp != nullptr && xb != nullptr, want_db = dbp != nullptr;
+
+  // ---- setup: taps, zeroed accumulators, V_0 = dY o act'(y) (node-major, coalesced), db ---------------------
+  if (dxb)
+    for (int q = tid; q < (KG * F) >> 1; q += kFusedThreads) Hs[q] = pack_one(h, F, KG, 1, q);
+  for (int i = tid; i < F * KG + F; i += kFusedThreads) dHs[i] = 0.f;
+  for (int idx = N * FS + tid; idx < MT * 16 * FS; idx += kFusedThreads) vs[idx] = 0.f;
+  __syncthreads();
+  {
+    const float4* d4 = reinterpret_cast<const float4*>(dY + (size_t)b * N * F);
+    const float4* y4 = (act != GFC_ACT_NONE) ? reinterpret_cast<const float4*>(yout + (size_t)b * N * F) : nullptr;
+    float4 cs = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int idx = tid; idx < total; idx += kFusedThreads) {     // idx % F4 is the same for every pass of a thread
+      const int n = idx / F4, f4 = idx - n * F4;
+      float4 v = __ldg(d4 + idx);
+      if (y4) {
+        const float4 yo = __ldg(y4 + idx);
+        v.x = act_grad(v.x, yo.x, act, slope); v.y = act_grad(v.y, yo.y, act, slope);
+        v.z = act_grad(v.z, yo.z, act, slope); v.w = act_grad(v.w, yo.w, act, slope);
+      }
+      *reinterpret_cast<float4*>(vs + (size_t)n * FS + f4 * 4) = v;
+      cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
+    }
+    if (want_db && (kFusedThreads % F4) == 0) {
+      const int f4 = tid % F4;
+      atomicAdd(dbs + f4 * 4, cs.x); atomicAdd(dbs + f4 * 4 + 1, cs.y);
+      atomicAdd(dbs + f4 * 4 + 2, cs.z); atomicAdd(dbs + f4 * 4 + 3, cs.w);
+    }
+  }
+  __syncthreads();
+
+  for (int k = 0; k < K; ++k) {
+    // ---- (a) dX[rows of this warp][g] (+)= sum_f V_k[row][f] h[f][k*G + g] ----------------------------------
+    if (dxb) {
+      for (int mt = warp; mt < MT; mt += kFusedThreads / 32) {
+        const int r0 = mt * 16 + g, r1 = r0 + 8;
+        float acc[NTG][4];
+#pragma unroll
+        for (int nt = 0; nt < NTG; ++nt) {
+          float* c0 = dxb + (size_t)(nt * 8 + 2 * t) * N;
+          if (k == 0) {
+            acc[nt][0] = acc[nt][1] = acc[nt][2] = acc[nt][3] = 0.f;
+          } else {
+            acc[nt][0] = r0 < N ? c0[r0] : 0.f; acc[nt][1] = r0 < N ? c0[N + r0] : 0.f;
+            acc[nt][2] = r1 < N ? c0[r1] : 0.f; acc[nt][3] = r1 < N ? c0[N + r1] : 0.f;
+          }
+        }
+        const float* va = vs + (size_t)r0 * FS + t;
+        const float4* hp = Hs + (size_t)(k * NTG) * 32 + lane;
+        for (int s = 0; s < KSF; ++s) {
+          uint32_t ahi[4], alo[4];
+          split_tf32(va[s * 8], ahi[0], alo[0]);
+          split_tf32(va[8 * FS + s * 8], ahi[1], alo[1]);
+          split_tf32(va[s * 8 + 4], ahi[2], alo[2]);
+          split_tf32(va[8 * FS + s * 8 + 4], ahi[3], alo[3]);
+#pragma unroll
+          for (int nt = 0; nt < NTG; ++nt) {
+            const float4 bf = hp[((size_t)s * NTC + nt) * 32];
+            mma3(acc[nt], ahi, alo, __float_as_uint(bf.x), __float_as_uint(bf.y), __float_as_uint(bf.z),
+                 __float_as_uint(bf.w), single != 0);
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NTG; ++nt) {
+          float* c0 = dxb + (size_t)(nt * 8 + 2 * t) * N;
+          if (r0 < N) { c0[r0] = acc[nt][0]; c0[N + r0] = acc[nt][1]; }
+          if (r1 < N) { c0[r1] = acc[nt][2]; c0[N + r1] = acc[nt][3]; }
+        }
+      }
+    }
+    // ---- (b) dH[f][k*G + g] += sum_n V_k[n][f] x[g][n]: a warp owns ONE 16 x 8 output tile and a share of the
+    //          node dimension (few partial sums per address meet in the shared accumulator) ---------------------
+    if (want_dh) {
+      const int ntile = MTF * NTG, ngrp = (kFusedThreads / 32) / ntile;
+      const int tile = warp % ntile, grp = warp / ntile;
+      const int mtf = tile / NTG, nt = tile - mtf * NTG;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const float* xc = xb + (size_t)(nt * 8 + g) * N;                // B[k = node][n = g] = x[g][node]
+      for (int s = grp; s < 2 * MT; s += ngrp) {                      // 8 nodes per step
+        const int n0 = s * 8 + t, n1 = n0 + 4;
+        const float* va = vs + (size_t)n0 * FS + mtf * 16 + g;        // A[m = f][k = node] = V[node][f]
+        uint32_t ahi[4], alo[4], bh0, bl0, bh1, bl1;
+        split_tf32(n0 < N ? __ldg(xc + n0) : 0.f, bh0, bl0);
+        split_tf32(n1 < N ? __ldg(xc + n1) : 0.f, bh1, bl1);
+        split_tf32(va[0], ahi[0], alo[0]);
+        split_tf32(va[8], ahi[1], alo[1]);
+        split_tf32(va[4 * FS], ahi[2], alo[2]);
+        split_tf32(va[4 * FS + 8], ahi[3], alo[3]);
+        mma3(acc, ahi, alo, bh0, bh1, bl0, bl1, single != 0);
+      }
+      float* row0 = dHs + (size_t)(mtf * 16 + g) * KG + k * G + nt * 8 + 2 * t;
+      float* row1 = row0 + (size_t)8 * KG;
+      atomicAdd(row0, acc[0]); atomicAdd(row0 + 1, acc[1]);
+      atomicAdd(row1, acc[2]); atomicAdd(row1 + 1, acc[3]);
+    }
+    if (k == K - 1) break;
+    // ---- (c) V_{k+1}[n] = sum_m S[n][m] V_k[m]: transposed lists ----------------------------------------------
+    float4 nxt[kFusedItems];
+#pragma unroll
+    for (int it = 0; it < kFusedItems; ++it) {
+      const int idx = tid + it * kFusedThreads;
+      nxt[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < total) {
+        const int n = idx / F4, f4 = idx - n * F4;
+        const int beg = rp[n], end = rp[n + 1];
+        const float* src = vs + f4 * 4;
+        for (int i = beg; i < end; ++i) {
+          const int m = ci[i];
+          const float w = vv ? vv[i] : 1.f;
+          const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * FS);
+          nxt[it].x = fmaf(w, z.x, nxt[it].x);
+          nxt[it].y = fmaf(w, z.y, nxt[it].y);
+          nxt[it].z = fmaf(w, z.z, nxt[it].z);
+          nxt[it].w = fmaf(w, z.w, nxt[it].w);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < kFusedItems; ++it) {
+      const int idx = tid + it * kFusedThreads;
+      if (idx < total) {
+        const int n = idx / F4, f4 = idx - n * F4;
+        *reinterpret_cast<float4*>(vs + (size_t)n * FS + f4 * 4) = nxt[it];
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (dHp)
+    for (int i = tid; i < F * KG; i += kFusedThreads) dHp[(size_t)b * F * KG + i] = dHs[i];
+  if (want_db)
+    for (int i = tid; i < F; i += kFusedThreads) dbp[(size_t)b * F + i] = dbs[i];
+}
+
+bool csr_bwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes) {
+  if (N < 1 || K < 1 || !(G == 16 || G == 32) || (F & 15) || F > 64) return false;
+  if ((kFusedThreads % (F >> 2)) != 0) return false;
+  if ((kFusedThreads / 32) % ((F >> 4) * (G >> 3)) != 0) return false;   // warps = output tiles x node groups
+  if ((long long)N * F > (long long)kFusedThreads * kFusedItems * 4) return false;
+  const size_t MT = (size_t)(N + 15) >> 4;
+  const size_t bytes = (MT * 16 * (F + 4) + (size_t)K * G * F * 2 + (size_t)F * K * G + F) * sizeof(float);
+  DeviceInfo di;
+  if (get_device_info(&di)) return false;
+  if (bytes + 1024 > (size_t)di.smem_optin) return false;
+  if (smem_bytes) *smem_bytes = bytes;
+  return true;
+}
+
+int launch_csr_bwd_fused(const float* x, const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                         long long nnz_stride, const float* h, const float* yout, const float* dY, float* dX,
+                         float* dHp, float* dbp, int B, int N, int G, int F, int K, int act, float slope, int single,
+                         cudaStream_t st) {
+  size_t smem = 0;
+  if (!csr_bwd_fused_supported(N, G, F, K, &smem)) return GFC_ERR_UNSUPPORTED;
+  if (G == 32) {
+    GFC_CUDA_TRY(cudaFuncSetAttribute(csr_bwd_fused_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    csr_bwd_fused_kernel<4><<<B, kFusedThreads, smem, st>>>(x, rowptr_t, colidx_t, vals_t, nnz_stride, h, yout, dY, dX,
+                                                            dHp, dbp, N, G, F, K, act, slope, single);
+  } else {
+    GFC_CUDA_TRY(cudaFuncSetAttribute(csr_bwd_fused_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    csr_bwd_fused_kernel<2><<<B, kFusedThreads, smem, st>>>(x, rowptr_t, colidx_t, vals_t, nnz_stride, h, yout, dY, dX,
+                                                            dHp, dbp, N, G, F, K, act, slope, single);
+  }
+  GFC_LAUNCH_CHECK("csr_bwd_fused_kernel");
+  return GFC_OK;
+}
+
 bool csr_fwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes) {
   if (N < 1 || K < 1 || (G & 7) || !(F == 16 || F == 32)) return false;   // instantiated output widths
   if ((long long)N * G > (long long)kFusedThreads * kFusedItems * 4) return false;

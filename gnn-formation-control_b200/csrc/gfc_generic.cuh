@@ -22,6 +22,12 @@ bool csr_fwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes);
 int launch_csr_fwd_fused(const float* x, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                          long long nnz_stride, const float* h, const float* bias, float* y, int B, int N, int G,
                          int F, int K, int act, float slope, int single, cudaStream_t st);
+// whole CSR backward of a graph in one CTA; partial dH [B][F*K*G] and db [B][F] for reduce_parts_kernel
+bool csr_bwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes);
+int launch_csr_bwd_fused(const float* x, const int32_t* rowptr_t, const int32_t* colidx_t, const float* vals_t,
+                         long long nnz_stride, const float* h, const float* yout, const float* dY, float* dX,
+                         float* dHp, float* dbp, int B, int N, int G, int F, int K, int act, float slope, int single,
+                         cudaStream_t st);
 int launch_dpre(const float* dY, const float* yout, float* D, long long n, int act, float slope, cudaStream_t st);
 int launch_colsum(const float* D, long long rows, int F, int rows_per_chunk, int nchunks, float* part,
                   cudaStream_t st);
