@@ -520,7 +520,7 @@ def csr_workload(torch, dev, steps=5):
     bytes_per_graph = 2 * (4 * (N + 1) + 4 * nnz) + 4 * N * (3 * G + 2 * F)     # SURVEY §8d, CSR read fwd+bwd
     return dict(workload=w["desc"], value=B / (ms * 1e-3), unit="graphs/s", ms_per_step=ms, steps=steps,
                 mean_degree=nnz / N, algorithmic_GBps=B * bytes_per_graph / (ms * 1e-3) / 1e9,
-                note="forward: one fused kernel per step (one CTA per graph, state in shared memory); backward: shared-memory hop chains + tensor-core tap contraction kernel")
+                note="CSR build + one fused forward kernel + one fused backward kernel per step (one CTA per graph, diffusion state in shared memory)")
 
 
 # ----------------------------------------------------------------------------- reference arm / cpu baseline
