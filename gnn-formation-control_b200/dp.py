@@ -22,12 +22,17 @@ def shard_range(total, rank, world):
 class GradBucket:
     """Flat fp32 bucket over a fixed parameter list; one collective per step."""
 
+    # buckets up to this many floats go through the one-shot peer-memory kernel (latency-bound regime: every rank
+    # pushes its whole bucket to every peer); larger ones through NCCL (bandwidth-optimal rings / NVLS)
+    PEER_MAX_NUMEL = 1 << 16
+
     def __init__(self, params, average=True, process_group=None):
         self.params = [p for p in params if p.requires_grad]
         self.average, self.group = average, process_group
         self.numel = sum(p.numel() for p in self.params)
         dev = self.params[0].device if self.params else torch.device("cpu")
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self._px = None          # PeerExchange, created on the first GPU all-reduce (collective: all ranks together)
 
     def pack(self):
         off = 0
@@ -55,9 +60,15 @@ class GradBucket:
         """sum (or mean) of the bucket over all ranks; async_op-free, stream-ordered."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return self.flat
+        world = dist.get_world_size(self.group)
+        if self.flat.is_cuda and 0 < self.numel <= self.PEER_MAX_NUMEL and dist.get_backend(self.group) == "nccl":
+            if self._px is None:
+                self._px = PeerExchange(self.numel, self.flat.device, self.group)
+            self._px.allreduce_(self.flat, scale=(1.0 / world) if self.average else 1.0)
+            return self.flat
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if self.average:
-            self.flat.div_(dist.get_world_size(self.group))
+            self.flat.div_(world)
         return self.flat
 
     def sync_grads(self):

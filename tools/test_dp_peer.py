@@ -22,6 +22,16 @@ for it in range(20):
     dist.all_gather(allv, got)
     ok &= all(torch.equal(allv[0], a) for a in allv)     # bit-identical on every rank
 if rank == 0: print("peer all-reduce vs NCCL ok:", ok, "err %.2e" % err, flush=True)
+# GradBucket over a module's parameters: small buckets take the fused peer kernel, averages included
+lin = torch.nn.Linear(24, 17).to(dev)
+bucket = gnnfc.GradBucket(lin.parameters(), average=True)
+for p_ in lin.parameters():
+    p_.grad = torch.full_like(p_, float(rank + 1))
+bucket.sync_grads()
+torch.cuda.synchronize()
+want = sum(range(1, world + 1)) / world
+okb = all(bool(torch.allclose(p_.grad, torch.full_like(p_, want))) for p_ in lin.parameters()) and bucket._px is not None
+if rank == 0: print("GradBucket through the peer exchange ok:", okb, flush=True)
 # timing
 for name, fn in (("fused peer exchange", lambda t: px.allreduce_(t)), ("NCCL", lambda t: dist.all_reduce(t))):
     t = torch.randn(n, device=dev)
