@@ -20,7 +20,12 @@ def shard_range(total, rank, world):
 
 
 class GradBucket:
-    """Flat fp32 bucket over a fixed parameter list; one collective per step."""
+    """Flat fp32 bucket over a fixed parameter list; one collective per step.
+
+    On GPUs (NCCL process group) buckets of up to ``PEER_MAX_NUMEL`` floats are all-reduced by the one-shot
+    peer-memory kernel (``PeerExchange``: CUDA symmetric memory over NVLink, created collectively on the first
+    call — every rank must reach its first ``allreduce`` together); larger buckets, CPU tensors and other backends
+    use ``torch.distributed.all_reduce``.  Set ``PEER_MAX_NUMEL = 0`` on the instance to force the latter."""
 
     # buckets up to this many floats go through the one-shot peer-memory kernel (latency-bound regime: every rank
     # pushes its whole bucket to every peer); larger ones through NCCL (bandwidth-optimal rings / NVLS)
