@@ -354,11 +354,11 @@ class GraphFilterBatchGSO(GraphFilterBatch):
         self.B = pos.shape[0]
 
     def forward(self, x):
-        _require_cuda(x, "x")
         # batchLSIGF's asserts (graphML.py:2149-2154)
         assert x.shape[0] == self.B
         assert x.shape[1] == self.G
         assert x.shape[2] == self.N
+        _require_cuda(x, "x")
         src = self._source(x.device)
         ymem = graph_filter(x, self.weight, self.bias, src, self.activation, self.negative_slope, self.precision)
         return ymem.permute(0, 2, 1).to(x.dtype)

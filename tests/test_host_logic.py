@@ -135,3 +135,58 @@ def test_recording_relayout_matches_the_reference_loops():
     pl = rng.standard_normal((2, 5 * 3, 2))
     p = gnnfc.positions_from_recording(pl, 3)
     assert p.shape == (10, 3, 2) and np.allclose(p[6, 2].numpy(), pl[1, 1 * 3 + 2].astype(np.float32))
+
+
+# --------------------------------------------------------------------------- #
+# the other two drop-in layers: GraphFilter (graphML.py:1111) and GraphFilterBatchGSO (graphML.py:2174)
+# --------------------------------------------------------------------------- #
+def test_same_gso_and_batch_gso_layers_surface():
+    m = gnnfc.GraphFilter(4, 8, 3, E=2)
+    assert tuple(m.weight.shape) == (8, 2, 3, 4) and tuple(m.bias.shape) == (8, 1) and m.S is None
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(1, 2, 5, 5))           # rank != 3   (graphML.py:1192)
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(1, 5, 5))              # E mismatch  (graphML.py:1194)
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(2, 5, 4))              # non-square  (graphML.py:1196)
+    m.addGSO(torch.zeros(2, 5, 5))
+    assert m.N == 5 and repr(m).endswith("GSO stored)")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(3, 4, 5))
+
+    g = gnnfc.GraphFilterBatchGSO(4, 8, 3)
+    assert g.extra_repr().endswith("no GSO stored")
+    g.addGSO(torch.zeros(6, 5, 5))                  # 3-d: one edge feature (graphML.py:2231-2233)
+    assert tuple(g.S.shape) == (6, 1, 5, 5) and (g.N, g.B) == (5, 6)
+    assert g.extra_repr().endswith("GSO stored: number_nodes=5, batch_size=6")
+    g.addGSO(torch.zeros(6, 5, 4))                  # any other shape is ignored, the previous GSO stays (:2241-2244)
+    assert tuple(g.S.shape) == (6, 1, 5, 5)
+    S = torch.rand(2, 1, 3, 3)
+    g.addGSO(S)
+    SK = g.SK                                       # matrixPowersBatch (graphML.py:2063): I, S, S^2
+    assert tuple(SK.shape) == (2, 1, 3, 3, 3)
+    assert torch.equal(SK[:, :, 0], torch.eye(3).expand(2, 1, 3, 3)) and torch.equal(SK[:, :, 1], S)
+    assert torch.allclose(SK[:, :, 2], S @ S)
+    with pytest.raises(AssertionError):
+        g(torch.zeros(2, 4, 2))                     # batchLSIGF asserts the node count, no zero-padding (:2154)
+
+
+@pytest.mark.skipif(not refimport.available(), reason="reference tree only exists in the build container")
+def test_new_layers_match_the_live_reference_surface():
+    gml = refimport.graphml()
+    for name, args, S in (("GraphFilter", (6, 5, 3, 2), torch.rand(2, 4, 4)),
+                          ("GraphFilterBatchGSO", (6, 5, 3, 1), torch.rand(7, 4, 4))):
+        torch.manual_seed(9); ref = getattr(gml, name)(*args)
+        torch.manual_seed(9); ours = getattr(gnnfc, name)(*args)
+        assert list(ref.state_dict().keys()) == list(ours.state_dict().keys())
+        assert torch.equal(ref.weight, ours.weight) and torch.equal(ref.bias, ours.bias)      # same init law / stream
+        assert ref.extra_repr() == ours.extra_repr()
+        ref.addGSO(S); ours.addGSO(S)
+        assert ref.extra_repr() == ours.extra_repr() and ref.N == ours.N
+        ours.load_state_dict(ref.state_dict())
+    # the powers attribute
+    torch.manual_seed(1)
+    S = torch.rand(3, 2, 5, 5)
+    ref = gml.GraphFilterBatchGSO(4, 4, 4, 2); ours = gnnfc.GraphFilterBatchGSO(4, 4, 4, 2)
+    ref.addGSO(S); ours.addGSO(S)
+    assert torch.allclose(ref.SK, ours.SK, rtol=1e-6, atol=1e-7)
