@@ -199,6 +199,26 @@ def batch_gso_goldens():
     np.savez_compressed(os.path.join(OUT, "batchgso_e2_4d.npz"), **run(h, b, S, x, dOut, False))
 
 
+def relu_golden():
+    """GraphFilterBatch followed by nn.ReLU, the pairing of decentralplanner.py:215-221 (suhaas_model.py uses
+    LeakyReLU): 5 robots of the expert fixture family shape, 16 -> 24, K = 2"""
+    gml = ri.graphml()
+    rng = np.random.default_rng(99)
+    torch.manual_seed(12)
+    m = gml.GraphFilterBatch(16, 24, 2, 1, bias=True)
+    h, b = m.weight.detach().numpy().copy(), m.bias.detach().numpy().copy()
+    S = (rng.random((9, 1, 5, 5)) < 0.5).astype(np.float32)
+    x = rng.standard_normal((9, 16, 5)).astype(np.float32)
+    dOut = rng.standard_normal((9, 24, 5))
+    xt = torch.from_numpy(x).clone().requires_grad_(True)
+    m.addGSO(torch.from_numpy(S))
+    y = torch.nn.ReLU()(m(xt))
+    (y * torch.from_numpy(dOut)).sum().backward()
+    np.savez_compressed(os.path.join(OUT, "filter_relu.npz"), h=h, b=b, S=S, x=x, dOut=dOut, leaky=np.int32(0),
+                        relu=np.int32(1), y=y.detach().numpy(), dX=xt.grad.numpy().astype(np.float64),
+                        dH=m.weight.grad.numpy().astype(np.float64), db=m.bias.grad.numpy().astype(np.float64))
+
+
 def filter_goldens():
     gml = ri.graphml()
     rng = np.random.default_rng(1234)
@@ -279,5 +299,6 @@ if __name__ == "__main__":
     filter_goldens()
     same_gso_goldens()
     batch_gso_goldens()
+    relu_golden()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

@@ -18,11 +18,12 @@ FILTER_FILES = ["filter_cfg1.npz", "filter_general_e2.npz", "filter_k1_nobias.np
                 "filter_cfg2_symnorm.npz", "filter_cyclic.npz", "filter_cfg4_n12.npz"]
 SAME_GSO_FILES = ["samegso_e2_nin.npz", "samegso_cfg2_f32.npz"]
 BATCH_GSO_FILES = ["batchgso_cfg2_3d.npz", "batchgso_e2_4d.npz"]
+RELU_FILES = ["filter_relu.npz"]
 
 
 def test_golden_inventory(golden_dir):
     have = sorted(os.path.basename(p) for p in glob.glob(os.path.join(golden_dir, "*.npz")))
-    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES)
+    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES + RELU_FILES)
 
 
 @pytest.mark.parametrize("name", GSO_FILES)
@@ -133,6 +134,14 @@ def test_batch_gso_oracle_matches_reference_golden(golden_dir, name):
     assert g["y"].dtype == np.float32
     assert rel_err(y, g["y"]) < 3e-6 and rel_err(dX, g["dX"]) < 3e-6
     assert rel_err(dH, g["dH"]) < 3e-6 and rel_err(db, g["db"]) < 3e-6
+
+
+def test_relu_pairing_oracle_matches_reference_golden(golden_dir):
+    """GraphFilterBatch + nn.ReLU as wired in decentralplanner.py:215-221"""
+    g = np.load(os.path.join(golden_dir, "filter_relu.npz"))
+    y, dX, dH, db = lsigf.filter_fwd_bwd(g["h"], g["S"], g["x"], g["b"], g["dOut"], lsigf.ACT_RELU)
+    assert rel_err(y, g["y"]) < 1e-13
+    assert rel_err(dX, g["dX"]) < 2e-7 and rel_err(dH, g["dH"]) < 2e-7 and rel_err(db, g["db"]) < 2e-7
 
 
 def test_closed_form_gradients_match_autograd():
