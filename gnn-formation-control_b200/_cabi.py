@@ -20,6 +20,8 @@ OPT_SKIP_GRAD_REDUCE = 1
 OPT_DISABLE_TCGEN05 = 2
 OPT_WIDE_FLUSH_EVERY = 3
 OPT_PDL = 4
+OPT_CSR_FUSED = 5
+OPT_WIDE_NO_PREFETCH = 6
 
 GSO_MODES = {"binary_le": GSO_BINARY_LE, "sym_norm_lt": GSO_SYM_NORM_LT, "binary_lt": GSO_BINARY_LT}
 ACTIVATIONS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU}

@@ -475,8 +475,8 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_SKIP_GRAD_REDUCE) { g_skip_grad_reduce = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_DISABLE_TCGEN05) { g_disable_tcgen05 = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_PDL) { g_pdl = value ? 1 : 0; return GFC_OK; }
-  if (key == 99) { g_wide_no_prefetch = value; return GFC_OK; }
-  if (key == 97) { g_csr_fused = value ? 1 : 0; return GFC_OK; }   // A/B: fused CSR forward vs workspace pipeline
+  if (key == GFC_OPT_WIDE_NO_PREFETCH || key == 99) { g_wide_no_prefetch = value; return GFC_OK; }
+  if (key == GFC_OPT_CSR_FUSED) { g_csr_fused = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 2; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
   return GFC_ERR_BAD_ARG;
