@@ -9,11 +9,13 @@ backward, on B200 (BASELINE.json metric).
 One "step" = one pass of the hot path over ONE batch of the workload: positions ->
 GSO (rebuilt on chip), filter forward (+bias, LeakyReLU), filter backward (dX, dH,
 db) from a resident synthetic upstream gradient, deterministic gradient reduction,
-and — for N > 1 — the all-reduce of the flat [dH | db] bucket (NCCL over NVLink).
+and — for N > 1 — the all-reduce of the flat [dH | db] bucket, fused into the gradient-reduction kernel as a one-shot
+exchange over NVLink peer memory (`--nccl`: separate reduction kernel + ncclAllReduce).
 
 Timing: CUDA events on the launching stream around exactly K steps, barrier +
 synchronize on both sides, max over ranks.  Inputs rotate through a ring of
-distinct batches larger than L2 (or a single batch that is itself > L2).
+distinct batches larger than L2 (or a single batch that is itself > L2); the K steps are replayed from CUDA
+graphs of several ring passes each, so the host enqueues far ahead of the device.
 Prints ONE JSON line on rank 0.
 """
 import argparse
