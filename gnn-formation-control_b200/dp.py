@@ -66,11 +66,16 @@ class GradBucket:
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
             return self.flat
         world = dist.get_world_size(self.group)
-        if self.flat.is_cuda and 0 < self.numel <= self.PEER_MAX_NUMEL and dist.get_backend(self.group) == "nccl":
+        if (self._px is not False and self.flat.is_cuda and 0 < self.numel <= self.PEER_MAX_NUMEL
+                and dist.get_backend(self.group) == "nccl"):
             if self._px is None:
-                self._px = PeerExchange(self.numel, self.flat.device, self.group)
-            self._px.allreduce_(self.flat, scale=(1.0 / world) if self.average else 1.0)
-            return self.flat
+                try:
+                    self._px = PeerExchange(self.numel, self.flat.device, self.group)
+                except (ImportError, AttributeError, NotImplementedError):
+                    self._px = False      # no CUDA symmetric memory in this torch build: NCCL below (all ranks alike)
+            if self._px:
+                self._px.allreduce_(self.flat, scale=(1.0 / world) if self.average else 1.0)
+                return self.flat
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
         if self.average:
             self.flat.div_(world)
