@@ -233,12 +233,14 @@ extern "C" int gfc_csr_count(const float* pos, int B, int N, double radius, int 
   double thr; bool norm;
   int rc = mode_threshold(mode, radius, &thr, &norm);
   if (rc) return rc;
-  GFC_REQUIRE(B <= 65535, GFC_ERR_UNSUPPORTED, "gfc_csr_count: B=%d > 65535 graphs per call", B);
   float lo, hi;
   screen_band(thr, &lo, &hi);
-  csr_rows_kernel<false, false><<<dim3((unsigned)((N + 255) / 256), (unsigned)B), 256, 0, (cudaStream_t)stream>>>(
-      pos, N, thr, lo, hi, deg, nullptr, 0, nullptr, nullptr);
-  GFC_LAUNCH_CHECK("csr_rows_kernel<count>");
+  for (int b0 = 0; b0 < B; b0 += 65535) {   // gridDim.y limit: 65535 graphs per launch
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    csr_rows_kernel<false, false><<<dim3((unsigned)((N + 255) / 256), (unsigned)nb), 256, 0, (cudaStream_t)stream>>>(
+        pos + (size_t)b0 * N * 2, N, thr, lo, hi, deg + (size_t)b0 * N, nullptr, 0, nullptr, nullptr);
+    GFC_LAUNCH_CHECK("csr_rows_kernel<count>");
+  }
   return GFC_OK;
 }
 
@@ -262,16 +264,22 @@ extern "C" int gfc_csr_fill(const float* pos, int B, int N, double radius, int m
   double thr; bool norm;
   int rc = mode_threshold(mode, radius, &thr, &norm);
   if (rc) return rc;
-  GFC_REQUIRE(B <= 65535, GFC_ERR_UNSUPPORTED, "gfc_csr_fill: B=%d > 65535 graphs per call", B);
   float lo, hi;
   screen_band(thr, &lo, &hi);
-  const dim3 grid((unsigned)((N + 255) / 256), (unsigned)B);
-  if (norm)
-    csr_rows_kernel<true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, N, thr, lo, hi, nullptr, rowptr,
-                                                                         nnz_stride, colidx, vals);
-  else
-    csr_rows_kernel<true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(pos, N, thr, lo, hi, nullptr, rowptr,
-                                                                          nnz_stride, colidx, vals);
-  GFC_LAUNCH_CHECK("csr_rows_kernel<fill>");
+  for (int b0 = 0; b0 < B; b0 += 65535) {   // gridDim.y limit: 65535 graphs per launch
+    const int nb = B - b0 < 65535 ? B - b0 : 65535;
+    const dim3 grid((unsigned)((N + 255) / 256), (unsigned)nb);
+    const float* p0 = pos + (size_t)b0 * N * 2;
+    const int32_t* rp0 = rowptr + (size_t)b0 * (N + 1);
+    int32_t* ci0 = colidx + (size_t)b0 * nnz_stride;
+    float* v0 = vals ? vals + (size_t)b0 * nnz_stride : nullptr;
+    if (norm)
+      csr_rows_kernel<true, true><<<grid, 256, 0, (cudaStream_t)stream>>>(p0, N, thr, lo, hi, nullptr, rp0, nnz_stride,
+                                                                           ci0, v0);
+    else
+      csr_rows_kernel<true, false><<<grid, 256, 0, (cudaStream_t)stream>>>(p0, N, thr, lo, hi, nullptr, rp0, nnz_stride,
+                                                                            ci0, v0);
+    GFC_LAUNCH_CHECK("csr_rows_kernel<fill>");
+  }
   return GFC_OK;
 }
