@@ -550,7 +550,7 @@ def cpu_reference_step_fn(w, sample_B):
             ht.grad = None; bt.grad = None
             y = lsigf.activation_torch(lsigf.batch_lsigf_torch(ht, St, xt, bt), lsigf.ACT_LEAKY_RELU)
             y.backward(dY)
-            return float(y[0, 0, 0])
+            return float(y.detach()[0, 0, 0])
         with torch.no_grad():
             y = lsigf.activation_torch(lsigf.batch_lsigf_torch(ht, St, x, bt), lsigf.ACT_LEAKY_RELU)
             for _ in range(layers - 1):
@@ -591,13 +591,188 @@ def time_cpu(w, steps, warmup, budget_s):
 
 
 # ----------------------------------------------------------------------------- main
+def config_dict(w, **more):
+    """the keys BOTH arms print (the driver compares them): workload string + shape per GPU"""
+    d = dict(workload=w["desc"], B_per_gpu=w["B"], N=w["N"], G=w["G"], F=w["F"], K=w["K"],
+             gso="position -> GSO rebuilt every step, radius 2, " + w["mode"], activation="leaky_relu(0.01)",
+             train=bool(w["train"]), layers=w.get("layers", 1))
+    d.update(more)
+    return d
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p.get("bf16_tflops_burst", p.get("bf16_tflops", 1639.5))),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", 1375.0)),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1500.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def kernel_flops(w):
+    """algorithmic fp32-equivalent flops per graph of each kernel: dense hops 2(K-1)GN^2, taps 2NKGF"""
+    N, G, F, K = w["N"], w["G"], w["F"], w["K"]
+    hops_g, hops_f, taps = 2 * (K - 1) * G * N * N, 2 * (K - 1) * F * N * N, 2 * N * K * G * F
+    return dict(fwd=hops_g + taps, bwd_dx=hops_f + taps, bwd_dh=hops_g + taps)   # dH kernel: recompute-equivalent hops
+
+
+def per_kernel_times(torch, hp, reps):
+    """average duration of the forward kernel, the dX kernel and the dH/db kernel of ONE batch, each launched back
+    to back over the (rotating) ring through the C ABI with the other outputs switched off (NULL dX / NULL dH, db)."""
+    C = hp.C
+    w = hp.w
+    B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+    out = {}
+
+    def bwd_partial(i, st, want_dx, want_dh):
+        C.check(C.lib.gfc_filter_bwd_pos(C.ptr(hp.x[i]), C.ptr(hp.pos[i]), RADIUS, hp.mode, C.ptr(hp.h),
+                                         C.ptr(hp.y[i]), C.ptr(hp.dY[i]), C.ptr(hp.dX[i]) if want_dx else None,
+                                         C.ptr(hp.dH) if want_dh else None, C.ptr(hp.db) if want_dh else None,
+                                         B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32,
+                                         C.ptr(hp.wsb), hp.nbb, st), "gfc_filter_bwd_pos")
+        return C.last_launch_count()
+
+    calls = dict(fwd=lambda i: hp.fwd(i, hp.stream()))
+    if hp.train:
+        calls["bwd_dx"] = lambda i: bwd_partial(i, hp.stream(), True, False)
+        calls["bwd_dh"] = lambda i: bwd_partial(i, hp.stream(), False, True)
+        C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 1), "gfc_set_option")
+    try:
+        for name, call in calls.items():
+            for i in range(hp.ring):
+                call(i)
+            torch.cuda.synchronize()
+            nl = call(0)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(hp.ring):
+                    call(i)
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record(); torch.cuda.synchronize()
+            out[name] = dict(ms=e0.elapsed_time(e1) / (reps * hp.ring), launches=nl)
+    finally:
+        if hp.train:
+            C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 0), "gfc_set_option")
+    return out
+
+
+def roofline_of(torch, w, hp, cfg_name, step_ms, peaks):
+    """roofline of the dominant kernel (+ the whole step beside it).  Narrow features (G, F < 64): HBM-bound, the
+    dominant kernel is the backward launch.  Wide features: the binding limit in the fp32-parity mode is the tensor
+    pipe (SURVEY §8d table), so `bound` = tensor with USEFUL (algorithmic fp32-equivalent) flops as `achieved`;
+    the HBM fraction of the same kernel and the issued low-precision flops are given beside it."""
+    bpg = bytes_per_graph(w)
+    B = w["B"]
+    ring = hp.ring
+    reps = int(min(2000, max(3, 50e-3 / max(step_ms * 1e-3, 1e-6) / ring)))
+    traffic_tab = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic_tab = json.load(open(tpath))
+    wide = w["G"] >= 64 and w["F"] >= 64
+    if not wide:
+        which = "bwd" if w["train"] else "fwd"
+        k_ms, k_launch = kernel_alone_ms(torch, hp, which, reps)
+        alg = B * bpg[which]
+        ach = alg / (k_ms * 1e-3) / 1e9
+        return dict(bound="hbm", achieved=ach, peak=peaks["hbm"], unit="GB/s", frac=ach / peaks["hbm"],
+                    traffic=traffic_tab.get("%s:%s" % (cfg_name, which)),
+                    kernel=("tc5_n8_bwd_kernel (tcgen05)" if cfg_name.startswith("cfg2") else "%s kernel of %s" % (which, cfg_name)),
+                    kernel_ms=k_ms, algorithmic_bytes_per_launch=alg, launches_in_timed_call=k_launch,
+                    peak_source=peaks["src"] + " hbm_gbs, burst copy",
+                    whole_step=dict(GBps=B * bpg["total"] / (step_ms * 1e-3) / 1e9,
+                                    frac=B * bpg["total"] / (step_ms * 1e-3) / 1e9 / peaks["hbm"]),
+                    how="CUDA events around a graph of %d back-to-back launches over rotating batches x %d replays" % (ring, reps))
+    kt = per_kernel_times(torch, hp, reps)
+    fl = kernel_flops(w)
+    N, G, F = w["N"], w["G"], w["F"]
+    kbytes = dict(fwd=8 * N + 4 * G * N + 4 * F * N, bwd_dx=8 * N + 8 * F * N + 4 * G * N, bwd_dh=8 * N + 4 * F * N + 4 * G * N)
+    dom = max(kt, key=lambda k: kt[k]["ms"])
+    per = {}
+    for k, v in kt.items():
+        tf = B * fl[k] / (v["ms"] * 1e-3) / 1e12
+        gb = B * kbytes[k] / (v["ms"] * 1e-3) / 1e9
+        per[k] = dict(ms=v["ms"], launches=v["launches"], useful_tflops=tf, tensor_frac=tf / peaks["tf_burst"],
+                      algorithmic_GBps=gb, hbm_frac=gb / peaks["hbm"])
+    names = dict(fwd="tc5_wide_kernel<fwd>", bwd_dx="tc5_wide_kernel<dX>", bwd_dh="tc5_wide_dh_kernel")
+    total_fl = sum(fl[k] for k in kt)
+    step_tf = B * total_fl / (step_ms * 1e-3) / 1e12
+    step_gb = B * bpg["total"] / (step_ms * 1e-3) / 1e9
+    return dict(bound="tensor", achieved=per[dom]["useful_tflops"], peak=peaks["tf_burst"], unit="TFLOP/s",
+                frac=per[dom]["tensor_frac"], traffic=traffic_tab.get("%s:%s" % (cfg_name, dom)),
+                kernel=names[dom], kernel_ms=per[dom]["ms"],
+                algorithmic_flops_per_launch=B * fl[dom], algorithmic_bytes_per_launch=B * kbytes[dom],
+                hbm=dict(achieved=per[dom]["algorithmic_GBps"], peak=peaks["hbm"], frac=per[dom]["hbm_frac"]),
+                per_kernel=per,
+                whole_step=dict(useful_tflops=step_tf, tensor_frac=step_tf / peaks["tf_sustained"], GBps=step_gb,
+                                hbm_frac=step_gb / peaks["hbm"]),
+                issued_over_useful=tensor_flops_per_graph(w)[0] / max(tensor_flops_per_graph(w)[1], 1),
+                peak_source=peaks["src"] + ": dense bf16 burst for a kernel timed alone, sustained for the whole step; hbm_gbs",
+                note="achieved = USEFUL fp32-equivalent flops (SURVEY 8d: dense hops 2(K-1)GN^2 + taps 2NKGF per pass) of the "
+                     "dominant kernel / its duration; fp32 parity costs 3 half-precision MMAs per tap product (fp16 hi/lo "
+                     "split), so at most ~1/3 of the dense peak is reachable in this mode",
+                how="CUDA events around %d back-to-back launches x %d replays per kernel, other outputs switched off" % (ring, reps))
+
+
+def dp_check(torch, dist, hp, world):
+    """N > 1: every rank holds the same data (identical seeds), so the exchanged bucket must equal world x the local
+    one, and all ranks must end with bit-identical gradients."""
+    i = 0
+    st = hp.stream()
+    hp.fwd(i, st)
+    hp.bwd(i, st)
+    local = hp.grads.clone()
+    if getattr(hp, "px", None) is not None:
+        hp.bwd_dp(i, st)
+    else:
+        dist.all_reduce(hp.grads)
+    torch.cuda.synchronize()
+    got = hp.grads.clone()
+    den = float((world * local).abs().max())
+    err = float((got - world * local).abs().max()) / max(den, 1e-30)
+    chk = got.double().sum().reshape(1)
+    first = got[:64].clone()
+    allc = [torch.empty_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    allf = [torch.empty_like(first) for _ in range(world)]
+    dist.all_gather(allf, first)
+    same = all(torch.equal(allc[0], c) for c in allc) and all(torch.equal(allf[0], f) for f in allf)
+    ok = bool(err <= 1e-6 and same and torch.isfinite(got).all())
+    if getattr(hp, "px", None) is not None:
+        try:
+            hp.px.status()
+        except Exception:
+            ok = False
+    return dict(ok=ok, max_rel_err_vs_world_x_local=err, bit_identical_across_ranks=bool(same))
+
+
+def side_measurement(torch, dist, name, w2, dev, peaks, cpu_budget):
+    hp2 = HotPath(w2, dev, ring_size(w2))
+    small = w2["B"] * bytes_per_graph(w2)["total"] < L2_BYTES
+    st2 = 400 if small else 20
+    ms2 = timed_steps(torch, hp2, st2, 3, 1, dist, True)
+    step_ms = ms2 / st2
+    rec = dict(workload=w2["desc"], value=w2["B"] * st2 / (ms2 * 1e-3), unit="graphs/s", ms_per_step=step_ms,
+               steps=st2, config=config_dict(w2), roofline=roofline_of(torch, w2, hp2, name, step_ms, peaks))
+    del hp2
+    torch.cuda.empty_cache()
+    cb, _, _ = time_cpu(w2, 50, 1, budget_s=cpu_budget)
+    rec["cpu_baseline"] = cb
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=None)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--config", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--config", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-graph", action="store_true", help="launch every step from Python (no CUDA graph)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: plain NCCL all-reduce instead of the fused peer exchange")
     ap.add_argument("--no-extra", action="store_true", help="skip the side measurements of the other configs")
@@ -616,9 +791,7 @@ def main():
         cb, dt, sb = time_cpu(w, steps, warmup, budget_s=120.0)
         line = dict(metric=METRIC, value=cb["value"], unit="graphs/s", n_gpus=args.gpus, steps=steps, warmup=warmup,
                     ms_per_step=dt * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64",
-                    data="synthetic", impl="reference",
-                    config=dict(workload=w["desc"], B=w["B"], N=w["N"], G=w["G"], F=w["F"], K=w["K"],
-                                sample_graphs_per_step=sb),
+                    data="synthetic", impl="reference", config=config_dict(w),
                     cpu_baseline=cb, gpu_launches=0,
                     e2e=dict(value=cb["value"], unit="graphs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
@@ -632,9 +805,11 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    steps = args.steps or (4000 if w["B"] * bytes_per_graph(w)["total"] < L2_BYTES else 10)
+    small = w["B"] * bytes_per_graph(w)["total"] < L2_BYTES
+    steps = args.steps or (4000 if small else 20)
     warmup = args.warmup if args.warmup is not None else 5
     warmup = max(warmup, 3)
+    peaks = load_peaks()
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -660,31 +835,17 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * w["B"] * steps / (ms_max * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None   # sampled over warm-up + the timed region of the headline
 
-    # roofline of the dominant kernel, timed alone
+    dpc = dp_check(torch, dist, hp, world) if (world > 1 and w["train"]) else None
+
     bpg = bytes_per_graph(w)
-    which = "bwd" if w["train"] else "fwd"
-    reps = max(3, int(50e-3 / max(ms_max / steps * 1e-3, 1e-6) / ring))
-    reps = min(reps, 2000)
-    k_ms, k_launch = kernel_alone_ms(torch, hp, which, reps)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = w["B"] * bpg[which]
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("%s:%s" % (args.config, which))
-    roofline = dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
-                    kernel=("tc5_n8_bwd_kernel<pos> (tcgen05, bf16x3)" if (which == "bwd" and args.config.startswith("cfg2")) else "%s kernel of %s" % (which, args.config)), kernel_ms=k_ms, algorithmic_bytes_per_launch=alg_bytes,
-                    launches_in_timed_call=k_launch, peak_source=peak_src,
-                    how="CUDA events around a graph of %d back-to-back launches over rotating batches x %d replays" % (ring, reps))
+    roofline = roofline_of(torch, w, hp, args.config, ms_max / steps, peaks)
+    del hp
+    torch.cuda.empty_cache()
 
     # end-to-end through the module API with host buffers
-    e2e_n = max(3, min(steps, 200 if w["B"] * bpg["total"] < L2_BYTES else 5))
+    e2e_n = max(3, min(steps, 200 if small else 5))
     e_ms, h2d, d2h, _ = e2e_steps(torch, w, dev, e2e_n, 3, world, dist, use_graph)
     te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -694,36 +855,15 @@ def main():
                api="gnnfc.GraphFilterBatch.addPositions/forward + loss.backward%s; pinned host inputs, H2D double-buffered "
                    "on a copy stream every step, loss copied to pinned host every step and read by the host"
                    % (" captured once with torch.cuda.graph and replayed" if getattr(e2e_steps, "graphed", False) else ""))
+    torch.cuda.empty_cache()
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        for name in ("cfg2_x64", "cfg3", "cfg4", "cfg1"):
+        for name in ("cfg2", "cfg2_x64", "cfg3", "cfg4", "cfg1"):
             if name == args.config:
                 continue
             try:
-                w2 = WORKLOADS[name]
-                hp2 = HotPath(w2, dev, ring_size(w2))
-                small = w2["B"] * bytes_per_graph(w2)["total"] < L2_BYTES
-                st2 = 400 if small else 4
-                ms2 = timed_steps(torch, hp2, st2, 3, 1, dist, True)
-                wk = "bwd" if w2["train"] else "fwd"
-                k2, _ = kernel_alone_ms(torch, hp2, wk, 20 if small else 2)
-                extra[name] = dict(workload=w2["desc"], value=w2["B"] * st2 / (ms2 * 1e-3), unit="graphs/s",
-                                   ms_per_step=ms2 / st2, steps=st2,
-                                   dominant_kernel_GBps=w2["B"] * bytes_per_graph(w2)[wk] / (k2 * 1e-3) / 1e9,
-                                   dominant_kernel_ms=k2)
-                if w2["G"] >= 64 and w2["F"] >= 64:   # tensor-pipe roofline of the tcgen05 wide path
-                    issued, useful = tensor_flops_per_graph(w2)
-                    rate = w2["B"] * st2 / (ms2 * 1e-3)
-                    tpeak = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
-                    sus = float(tpeak.get("bf16_tflops_sustained", 1400.0))
-                    extra[name]["tensor"] = dict(
-                        bound="tensor", issued_bf16_tflops=rate * issued / 1e12, peak_tflops=sus,
-                        frac=rate * issued / 1e12 / sus, useful_fp32_equivalent_tflops=rate * useful / 1e12,
-                        peak_source="measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if tpeak else "fallback",
-                        note="issued = bf16x3 split products (6 MMAs per tap product, 3 per hop product) over the whole step")
-                del hp2
-                torch.cuda.empty_cache()
+                extra[name] = side_measurement(torch, dist, name, WORKLOADS[name], dev, peaks, 4.0)
             except Exception as ex:  # side measurement must never break the headline line
                 extra[name] = dict(error=str(ex)[:200])
         try:
@@ -731,7 +871,6 @@ def main():
         except Exception as ex:
             extra["cfg5"] = dict(error=str(ex)[:200])
 
-    clocks = sampler.stop() if rank == 0 else None
     cpu = None
     if rank == 0 and world == 1:
         cpu, _, _ = time_cpu(w, 50, 1, budget_s=args.cpu_budget)
@@ -739,15 +878,19 @@ def main():
         line = dict(metric=METRIC, value=value, unit="graphs/s", n_gpus=world, steps=steps, warmup=warmup,
                     ms_per_step=ms_max / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="f32", data="synthetic",
-                    config=dict(workload=w["desc"], B_per_gpu=w["B"], N=w["N"], G=w["G"], F=w["F"], K=w["K"],
-                                gso="rebuilt on chip from positions, radius 2, " + w["mode"],
-                                activation="leaky_relu(0.01) fused", precision="fp32-equivalent split products on the tensor cores (3xTF32 / bf16x3, fp32 accumulate), <=1e-5 of the fp64 reference",
-                                upstream_gradient="resident synthetic dY",
-                                l2="inputs rotate through a ring of %d distinct batches = %.0f MB (> 126 MB L2)"
-                                   % (ring, ring * w["B"] * bpg["total"] / 1e6),
-                                launch="CUDA graph replay" if getattr(hp, "graph_used", False) else "python loop",
-                                collective=collective),
+                    config=config_dict(w),
+                    details=dict(global_batch=world * w["B"],
+                                       precision="fp32-equivalent split products on the tensor cores (fp16 hi/lo or bf16x3 / 3xTF32, "
+                                                 "fp32 accumulate), <=1e-5 of the fp64 reference",
+                                       upstream_gradient="resident synthetic dY",
+                                       l2=("one batch = %.0f MB (> 126 MB L2)" % (w["B"] * bpg["total"] / 1e6)) if ring == 1 else
+                                          ("inputs rotate through a ring of %d distinct batches = %.0f MB (> 126 MB L2)"
+                                           % (ring, ring * w["B"] * bpg["total"] / 1e6)),
+                                       launch="CUDA graph replay" if use_graph else "python loop",
+                                       collective=collective),
                     roofline=roofline, cpu_baseline=cpu, e2e=e2e, gpu_launches=launches, clocks=clocks, extra=extra)
+        if dpc is not None:
+            line["dp_check"] = dpc
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgfc.so")
 
-GFC_OK, GFC_ERR_BAD_ARG, GFC_ERR_UNSUPPORTED, GFC_ERR_WORKSPACE, GFC_ERR_CUDA = range(5)
+GFC_OK, GFC_ERR_BAD_ARG, GFC_ERR_UNSUPPORTED, GFC_ERR_WORKSPACE, GFC_ERR_CUDA, GFC_ERR_TIMEOUT = range(6)
 GSO_BINARY_LE, GSO_SYM_NORM_LT, GSO_BINARY_LT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
 PREC_FP32_3XTF32, PREC_TF32 = 0, 1
@@ -22,6 +22,7 @@ OPT_WIDE_FLUSH_EVERY = 3
 OPT_PDL = 4
 OPT_CSR_FUSED = 5
 OPT_WIDE_NO_PREFETCH = 6
+OPT_DP_TIMEOUT_MS = 7
 
 GSO_MODES = {"binary_le": GSO_BINARY_LE, "sym_norm_lt": GSO_SYM_NORM_LT, "binary_lt": GSO_BINARY_LT}
 ACTIVATIONS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU}
@@ -51,6 +52,7 @@ SIGNATURES = {
     "gfc_filter_bwd_pos_dp": (_i, [_p, _p, _d, _i] + [_p] * 5 + [_i] * 5 + [_i, _f, _i, _p, _sz, _p, _p, _i, _i, _f, _p]),
     "gfc_filter_bwd_dp": (_i, [_p] * 7 + [_i] * 6 + [_i, _f, _i, _p, _sz, _p, _p, _i, _i, _f, _p]),
     "gfc_dp_allreduce": (_i, [_p, _p, _i, _p, _p, _i, _i, _f, _p]),
+    "gfc_dp_status": (_i, [_p, _i, ct.POINTER(_i), _p]),
     "gfc_csr_count": (_i, [_p, _i, _i, _d, _i, _p, _p]),
     "gfc_csr_scan": (_i, [_p, _i, _i, _p, _p]),
     "gfc_csr_fill": (_i, [_p, _i, _i, _d, _i, _p, _i64, _p, _p, _p]),

@@ -129,7 +129,10 @@ static void plan_generic(int B, int N, int G, int F, int K, int E, int backward,
   g->ws_bytes = off;
 }
 
-static int check_common(const char* fn, int B, int N, int G, int F, int K, int E, int act, int prec) {
+static int check_common(const char* fn, int B, int N, int G, int F, int K, int E, int act, int prec, float slope = 0.f) {
+  // the backward recovers the activation mask from the sign of the forward OUTPUT (act_grad): valid for slope >= 0 only
+  GFC_REQUIRE(act != GFC_ACT_LEAKY_RELU || slope >= 0.f, GFC_ERR_BAD_ARG, "%s: negative_slope %g < 0 is not supported",
+              fn, (double)slope);
   GFC_REQUIRE(B >= 0 && N > 0 && G > 0 && F > 0 && K > 0 && E > 0, GFC_ERR_BAD_ARG,
               "%s: bad shape B=%d N=%d G=%d F=%d K=%d E=%d", fn, B, N, G, F, K, E);
   GFC_REQUIRE(act >= GFC_ACT_NONE && act <= GFC_ACT_LEAKY_RELU, GFC_ERR_BAD_ARG, "%s: bad activation %d", fn, act);
@@ -212,7 +215,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                            float* y, int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
                            void* ws, size_t ws_bytes, cudaStream_t st) {
   launch_counter() = 0;
-  int rc = check_common(fn, B, N, G, F, K, E, act, prec);
+  int rc = check_common(fn, B, N, G, F, K, E, act, prec, slope);
   if (rc) return rc;
   if (B == 0) return GFC_OK;
   GFC_REQUIRE(x && h && y, GFC_ERR_BAD_ARG, "%s: NULL tensor pointer", fn);
@@ -288,7 +291,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                            int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
                            void* ws, size_t ws_bytes, cudaStream_t st, const DpCtx* dp = nullptr) {
   launch_counter() = 0;
-  int rc = check_common(fn, B, N, G, F, K, E, act, prec);
+  int rc = check_common(fn, B, N, G, F, K, E, act, prec, slope);
   if (rc) return rc;
   const size_t nH = (size_t)F * E * K * G;
   if (B == 0) {
@@ -475,7 +478,8 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_SKIP_GRAD_REDUCE) { g_skip_grad_reduce = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_DISABLE_TCGEN05) { g_disable_tcgen05 = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_PDL) { g_pdl = value ? 1 : 0; return GFC_OK; }
-  if (key == GFC_OPT_WIDE_NO_PREFETCH || key == 99) { g_wide_no_prefetch = value; return GFC_OK; }
+  if (key == GFC_OPT_WIDE_NO_PREFETCH) { g_wide_no_prefetch = value; return GFC_OK; }
+  if (key == GFC_OPT_DP_TIMEOUT_MS) { g_dp_timeout_ms = value > 0 ? value : 10000; return GFC_OK; }
   if (key == GFC_OPT_CSR_FUSED) { g_csr_fused = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 2; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
@@ -554,7 +558,7 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   const char* fn = "gfc_filter_fwd_pos_nm";
   cudaStream_t st = (cudaStream_t)stream;
   launch_counter() = 0;
-  int rc = check_common(fn, B, N, G, F, K, 1, act, precision);
+  int rc = check_common(fn, B, N, G, F, K, 1, act, precision, slope);
   if (rc) return rc;
   if (B == 0) return GFC_OK;
   GFC_REQUIRE(x_nm && pos && h && y, GFC_ERR_BAD_ARG, "%s: NULL pointer", fn);
@@ -650,7 +654,7 @@ extern "C" int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const i
   const char* fn = "gfc_filter_csr_fwd";
   launch_counter() = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = check_common(fn, B, N, G, F, K, 1, act, precision);
+  int rc = check_common(fn, B, N, G, F, K, 1, act, precision, slope);
   if (rc) return rc;
   if (B == 0) return GFC_OK;
   GFC_REQUIRE(x && rowptr && colidx && h && y, GFC_ERR_BAD_ARG, "%s: NULL pointer", fn);
@@ -679,7 +683,7 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
   const char* fn = "gfc_filter_csr_bwd";
   launch_counter() = 0;
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = check_common(fn, B, N, G, F, K, 1, act, precision);
+  int rc = check_common(fn, B, N, G, F, K, 1, act, precision, slope);
   if (rc) return rc;
   const size_t nH = (size_t)F * K * G;
   if (B == 0) {

@@ -30,16 +30,24 @@ __device__ __forceinline__ unsigned long long ld_word(const unsigned long long* 
   return w;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 struct DpPeers {
   unsigned long long* buf[GFC_DP_MAX_WORLD];   // exchange buffer of every rank: {value, epoch} words [2][world][n]
-  unsigned int* sig[GFC_DP_MAX_WORLD];         // per-rank state: epochs [nblocks] (local use only)
+  unsigned int* sig[GFC_DP_MAX_WORLD];         // per-rank state: epochs [nblocks] + one sticky timeout flag (local use only)
 };
 
 constexpr int kDpClasses = 32;   // partial-classes per output: 32 lanes x 32 classes = 1024 threads per CTA
 
 __global__ void __launch_bounds__(32 * kDpClasses)
-reduce_allreduce_kernel(const float* __restrict__ pa, int npa, int na, const float* __restrict__ pb, int npb, int nb,
-                        float* __restrict__ out, const DpPeers peers, int rank, int world, float scale) {
+reduce_allreduce_kernel(const float* pa, int npa, int na, const float* pb, int npb, int nb,
+                        float* out, const DpPeers peers, int rank, int world, float scale,
+                        unsigned long long timeout_ns) {
+  // pa / pb / out carry no __restrict__: gfc_dp_allreduce is documented "in place allowed" (out == pa)
   __shared__ unsigned int s_epoch;
   __shared__ float red[kDpClasses][33];
   // programmatic dependent launch: this grid may be scheduled while the backward kernel drains
@@ -93,7 +101,22 @@ reduce_allreduce_kernel(const float* __restrict__ pa, int npa, int na, const flo
     if (pg < world && i < hi) {      // warp r waits for rank r's 32 words
       const unsigned long long* src = mine + (size_t)pg * n + i;
       unsigned long long w = ld_word(src);
-      while ((unsigned int)(w >> 32) != e) { __nanosleep(20); w = ld_word(src); }
+      if ((unsigned int)(w >> 32) != e) {
+        // bounded wait: a peer that never arrives (crashed rank, ranks that disagreed on the transport) must become
+        // an error, not a hung GPU.  On expiry the element is NaN and the sticky flag behind the epochs is raised
+        // (read back by gfc_dp_status); the kernel always terminates.
+        const unsigned long long t0 = globaltimer_ns();
+        while (true) {
+          __nanosleep(20);
+          w = ld_word(src);
+          if ((unsigned int)(w >> 32) == e) break;
+          if (globaltimer_ns() - t0 > timeout_ns) {
+            atomicExch(epochs + nblocks, 1u + (unsigned int)pg);   // 1 + the rank that was missing
+            w = 0x7fc00000ull;                                     // quiet NaN
+            break;
+          }
+        }
+      }
       red[pg][lane] = __uint_as_float((unsigned int)w);
     }
     __syncthreads();
@@ -105,6 +128,8 @@ reduce_allreduce_kernel(const float* __restrict__ pa, int npa, int na, const flo
     __syncthreads();
   }
 }
+
+int g_dp_timeout_ms = 10000;   // gfc_set_option(GFC_OPT_DP_TIMEOUT_MS)
 
 int dp_blocks(int n) {
   int nb = ceil_div(n, 32);
@@ -135,7 +160,7 @@ int launch_reduce_allreduce(const float* pa, int npa, int na, const float* pb, i
   cfg.attrs = attr;
   cfg.numAttrs = g_pdl ? 1 : 0;
   GFC_CUDA_TRY(cudaLaunchKernelEx(&cfg, reduce_allreduce_kernel, pa, npa, na, pb, npb, nb, out, peers, dp.rank,
-                                  dp.world, dp.scale));
+                                  dp.world, dp.scale, (unsigned long long)g_dp_timeout_ms * 1000000ull));
   GFC_LAUNCH_CHECK("reduce_allreduce_kernel");
   return GFC_OK;
 }
@@ -151,5 +176,20 @@ extern "C" size_t gfc_dp_exchange_bytes(int n, int world) {
 extern "C" size_t gfc_dp_signal_bytes(int n, int world) {
   if (n <= 0 || world <= 0 || world > GFC_DP_MAX_WORLD) return 0;
   (void)world;
-  return align_up((size_t)dp_blocks(n) * sizeof(unsigned int), 256);
+  return align_up((size_t)(dp_blocks(n) + 1) * sizeof(unsigned int), 256);   // epochs + the sticky timeout flag
+}
+
+// Synchronising status query of the exchange: copies this rank's sticky timeout flag back (stream-ordered, then waits
+// for the stream).  GFC_OK, or GFC_ERR_TIMEOUT when some launch gave up on a peer (then *missing_rank names it and
+// the affected bucket elements are NaN).  `n` is the bucket size the signal buffer was sized for.
+extern "C" int gfc_dp_status(const void* my_sig, int n, int* missing_rank, void* stream) {
+  GFC_REQUIRE(my_sig && n > 0, GFC_ERR_BAD_ARG, "gfc_dp_status: bad arguments");
+  unsigned int flag = 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  GFC_CUDA_TRY(cudaMemcpyAsync(&flag, static_cast<const unsigned int*>(my_sig) + dp_blocks(n), sizeof(flag),
+                               cudaMemcpyDeviceToHost, st));
+  GFC_CUDA_TRY(cudaStreamSynchronize(st));
+  if (missing_rank) *missing_rank = flag ? (int)flag - 1 : -1;
+  if (flag) { set_error("gfc_dp_status: the peer exchange timed out waiting for rank %d", (int)flag - 1); return GFC_ERR_TIMEOUT; }
+  return GFC_OK;
 }

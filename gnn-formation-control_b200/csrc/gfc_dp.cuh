@@ -14,6 +14,7 @@ struct DpCtx {
   float scale;             // applied to the summed bucket (1/world for a mean)
 };
 
+extern int g_dp_timeout_ms;   // bounded wait of the exchange poll (default 10 s)
 int dp_blocks(int n);
 // out[0..na) = scale * sum_ranks sum_p pa[p][i];  out[na..na+nb) likewise from pb
 int launch_reduce_allreduce(const float* pa, int npa, int na, const float* pb, int npb, int nb, float* out,

@@ -61,6 +61,25 @@ class GradBucket:
                 p.grad.copy_(g)
             off += n
 
+    def _agree_on_peer_exchange(self, world):
+        """Collective decision, taken once: EVERY rank builds the peer exchange or none uses it.  Construction can
+        fail on some ranks only (no symmetric memory in the torch build, no P2P / NVLink between two devices, IPC
+        disabled, a multi-node group, world > 16); a rank that silently fell back to NCCL while its peers entered the
+        one-shot kernel would leave them waiting for words that never come.  So each rank tries, then the ranks
+        all-reduce an ok flag with MIN and follow the common verdict."""
+        px, err = None, None
+        if world <= PeerExchange.MAX_WORLD:
+            try:
+                px = PeerExchange(self.numel, self.flat.device, self.group)
+            except Exception as ex:   # noqa: BLE001 — any failure means "not on this rank", decided collectively below
+                err = ex
+        ok = torch.tensor([1 if px is not None else 0], dtype=torch.int32, device=self.flat.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            return px
+        self.peer_error = err    # kept for diagnosis; the NCCL path is used by every rank
+        return False
+
     def allreduce(self):
         """sum (or mean) of the bucket over all ranks; async_op-free, stream-ordered."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
@@ -69,10 +88,7 @@ class GradBucket:
         if (self._px is not False and self.flat.is_cuda and 0 < self.numel <= self.PEER_MAX_NUMEL
                 and dist.get_backend(self.group) == "nccl"):
             if self._px is None:
-                try:
-                    self._px = PeerExchange(self.numel, self.flat.device, self.group)
-                except (ImportError, AttributeError, NotImplementedError):
-                    self._px = False      # no CUDA symmetric memory in this torch build: NCCL below (all ranks alike)
+                self._px = self._agree_on_peer_exchange(world)
             if self._px:
                 self._px.allreduce_(self.flat, scale=(1.0 / world) if self.average else 1.0)
                 return self.flat
@@ -103,6 +119,8 @@ class PeerExchange:
     same sizes, the rendezvous maps all of them into every process, and the kernels store into / poll them
     directly over NVLink.  ``world == 1`` (or no process group) needs no mapping: the rank talks to itself."""
 
+    MAX_WORLD = 16   # GFC_DP_MAX_WORLD (csrc/gfc_dp.cuh)
+
     def __init__(self, numel, device, group=None):
         import ctypes as ct
         from . import _cabi as C
@@ -112,8 +130,11 @@ class PeerExchange:
         self.world = dist.get_world_size(group) if init else 1
         nb = C.lib.gfc_dp_exchange_bytes(self.n, self.world)
         ns = C.lib.gfc_dp_signal_bytes(self.n, self.world)
-        assert nb > 0 and ns > 0, "bucket / world size not supported by the peer exchange"
+        if not (nb > 0 and ns > 0):
+            raise ValueError("PeerExchange: bucket of %d floats / world size %d not supported (world <= %d)"
+                             % (self.n, self.world, self.MAX_WORLD))
         self.bytes = nb + ns
+        self._sig_off = nb
         if self.world > 1:
             import torch.distributed._symmetric_memory as symm
             self.mem = symm.empty(self.bytes, dtype=torch.uint8, device=device)
@@ -138,3 +159,15 @@ class PeerExchange:
         C.check(C.lib.gfc_dp_allreduce(C.ptr(flat), C.ptr(flat), self.n, self.buf_ptrs, self.sig_ptrs,
                                        self.rank, self.world, float(scale), st), "gfc_dp_allreduce")
         return flat
+
+    def status(self):
+        """SYNCHRONISING health check: raises GfcError (GFC_ERR_TIMEOUT) if any launch of the exchange gave up waiting
+        for a peer (the affected gradient elements are then NaN).  The kernel itself never hangs (bounded poll,
+        ``GFC_OPT_DP_TIMEOUT_MS``)."""
+        C = self.C
+        sig = C.ct.c_void_p(self.mem.data_ptr() + self._sig_off)
+        missing = C.ct.c_int(-1)
+        st = C.ct.c_void_p(torch.cuda.current_stream(self.mem.device).cuda_stream)
+        with torch.cuda.device(self.mem.device):
+            C.check(C.lib.gfc_dp_status(sig, self.n, C.ct.byref(missing), st), "gfc_dp_status")
+        return True

@@ -177,6 +177,8 @@ class GraphFilterBatch(nn.Module):
         self._src = None
         assert activation in C.ACTIVATIONS, "activation must be one of %r" % list(C.ACTIVATIONS)
         assert precision in C.PRECISIONS, "precision must be one of %r" % list(C.PRECISIONS)
+        # the backward recovers the activation mask from the sign of the forward output: needs slope >= 0
+        assert negative_slope >= 0, "negative_slope must be >= 0"
         self.activation, self.negative_slope = activation, negative_slope
         self.precision, self.reference_dtype = precision, reference_dtype
         self.weight = nn.parameter.Parameter(torch.Tensor(F, E, K, G))

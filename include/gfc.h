@@ -47,7 +47,8 @@ enum {
   GFC_ERR_BAD_ARG = 1,     /* null pointer / non-positive size / bad enum      */
   GFC_ERR_UNSUPPORTED = 2, /* shape outside what the kernels cover             */
   GFC_ERR_WORKSPACE = 3,   /* workspace missing or too small                   */
-  GFC_ERR_CUDA = 4         /* a CUDA call failed; text in gfc_last_error()     */
+  GFC_ERR_CUDA = 4,        /* a CUDA call failed; text in gfc_last_error()     */
+  GFC_ERR_TIMEOUT = 5      /* gfc_dp_status: the peer exchange gave up on a rank */
 };
 
 /* position -> GSO rule */
@@ -201,6 +202,12 @@ int gfc_dp_allreduce(const float* in, float* out, int n,
                      void* const* peer_buf, void* const* peer_sig,
                      int rank, int world, float scale, void* stream);
 
+/* The exchange never hangs the device: a rank that waits longer than GFC_OPT_DP_TIMEOUT_MS (default 10 000 ms)
+ * for a peer's words writes NaN into the affected bucket elements, raises a sticky flag in its signal buffer and
+ * returns.  gfc_dp_status copies that flag back (it SYNCHRONISES `stream`): GFC_OK, or GFC_ERR_TIMEOUT with
+ * *missing_rank = the rank that did not arrive.  my_sig = this rank's own signal buffer, n = the bucket size.   */
+int gfc_dp_status(const void* my_sig, int n, int* missing_rank, void* stream);
+
 /* ---- introspection used by bench.py / tests -------------------------------- *
  * Which kernel family a shape dispatches to: 1 = fused shared-memory tile
  * kernel, 2 = workspace pipeline (dense hops), 0 = unsupported.               */
@@ -217,7 +224,8 @@ enum {
   GFC_OPT_WIDE_FLUSH_EVERY = 3, /* tiles chained into the TMEM dH accumulators between drains (default 2) */
   GFC_OPT_PDL = 4, /* 1 (default): the cfg2-shape kernels and the gradient reduction use programmatic dependent launch */
   GFC_OPT_CSR_FUSED = 5, /* 1 (default): one-CTA-per-graph fused CSR forward / backward kernels; 0: workspace pipeline (A/B) */
-  GFC_OPT_WIDE_NO_PREFETCH = 6 /* 1: tcgen05 wide kernels skip the L2 bulk prefetch of the next tiles (experiment; default 0) */
+  GFC_OPT_WIDE_NO_PREFETCH = 6, /* 1: tcgen05 wide kernels skip the L2 bulk prefetch of the next tiles (experiment; default 0) */
+  GFC_OPT_DP_TIMEOUT_MS = 7 /* bound of the peer-exchange poll in milliseconds (default 10000), see gfc_dp_status */
 };
 int gfc_set_option(int key, int value);
 /* Debug aid: a device buffer of >= 1184*16 int64 in which the fused tile kernels stamp the SM
