@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libgfc.so")
 GFC_OK, GFC_ERR_BAD_ARG, GFC_ERR_UNSUPPORTED, GFC_ERR_WORKSPACE, GFC_ERR_CUDA, GFC_ERR_TIMEOUT = range(6)
 GSO_BINARY_LE, GSO_SYM_NORM_LT, GSO_BINARY_LT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
-PREC_FP32_3XTF32, PREC_TF32 = 0, 1
+PREC_FP32_3XTF32, PREC_TF32, PREC_F16 = 0, 1, 2
 OPT_SKIP_GRAD_REDUCE = 1
 OPT_DISABLE_TCGEN05 = 2
 OPT_WIDE_FLUSH_EVERY = 3
@@ -26,7 +26,7 @@ OPT_DP_TIMEOUT_MS = 7
 
 GSO_MODES = {"binary_le": GSO_BINARY_LE, "sym_norm_lt": GSO_SYM_NORM_LT, "binary_lt": GSO_BINARY_LT}
 ACTIVATIONS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU}
-PRECISIONS = {"fp32": PREC_FP32_3XTF32, "3xtf32": PREC_FP32_3XTF32, "tf32": PREC_TF32}
+PRECISIONS = {"fp32": PREC_FP32_3XTF32, "3xtf32": PREC_FP32_3XTF32, "tf32": PREC_TF32, "f16": PREC_F16}
 
 _p, _i, _f, _d, _sz, _i64 = ct.c_void_p, ct.c_int, ct.c_float, ct.c_double, ct.c_size_t, ct.c_int64
 

@@ -136,7 +136,8 @@ static int check_common(const char* fn, int B, int N, int G, int F, int K, int E
   GFC_REQUIRE(B >= 0 && N > 0 && G > 0 && F > 0 && K > 0 && E > 0, GFC_ERR_BAD_ARG,
               "%s: bad shape B=%d N=%d G=%d F=%d K=%d E=%d", fn, B, N, G, F, K, E);
   GFC_REQUIRE(act >= GFC_ACT_NONE && act <= GFC_ACT_LEAKY_RELU, GFC_ERR_BAD_ARG, "%s: bad activation %d", fn, act);
-  GFC_REQUIRE(prec == GFC_PREC_FP32_3XTF32 || prec == GFC_PREC_TF32, GFC_ERR_BAD_ARG, "%s: bad precision %d", fn, prec);
+  GFC_REQUIRE(prec == GFC_PREC_FP32_3XTF32 || prec == GFC_PREC_TF32 || prec == GFC_PREC_F16, GFC_ERR_BAD_ARG,
+              "%s: bad precision %d", fn, prec);
   return GFC_OK;
 }
 
@@ -153,7 +154,7 @@ static int rows_fwd(const GenericPlan& g, char* wsb, const float* Zw, const floa
   TileArgs a{};
   a.S = Zw;   // one dummy weight per row (K = 1: no hop ever reads it)
   a.x = Zw; a.h = h; a.bias = bias; a.y = y;
-  a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+  a.act = act; a.slope = slope; a.single_pass = (prec != GFC_PREC_FP32_3XTF32);
   a.vec_ok = aligned16(Zw) && aligned16(y);
   a.p = p;
   if (!p.h_smem) {
@@ -177,7 +178,7 @@ static int rows_bwd(const GenericPlan& g, char* wsb, float* Zw, const float* h, 
   a.dX = want_u ? Zw : nullptr;
   a.dHp = dH ? reinterpret_cast<float*>(wsb + g.ws_rows + p.ws_dhp) : nullptr;
   a.dbp = db ? reinterpret_cast<float*>(wsb + g.ws_rows + p.ws_dbp) : nullptr;
-  a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+  a.act = act; a.slope = slope; a.single_pass = (prec != GFC_PREC_FP32_3XTF32);
   a.vec_ok = aligned16(Zw) && aligned16(dY) && (!yout || aligned16(yout));
   a.p = p;
   int rc;
@@ -196,18 +197,37 @@ static int rows_bwd(const GenericPlan& g, char* wsb, float* Zw, const float* h, 
 }
 
 // ---- tcgen05 wide path eligibility -------------------------------------------------
-static bool use_wide(const GsoSrc& gs, bool norm, int N, int G, int F, int K, int mode, int prec) {
-  return !g_disable_tcgen05 && gs.kind == GSRC_POS && !norm && prec == GFC_PREC_FP32_3XTF32 &&
-         wide_supported(N, G, F, K, mode);
+// positions (binary or sym-norm rule), G, F in {64,128}, N <= 128, fp16 headroom c (K-1) <= 21
+static bool use_wide(const GsoSrc& gs, int N, int G, int F, int K, int mode, int prec) {
+  (void)prec;
+  return !g_disable_tcgen05 && gs.kind == GSRC_POS && wide_supported(N, G, F, K, mode);
 }
-static size_t wide_ws_extra(int B, int N, int G, int F, int K, int backward) {
-  size_t n = (wide_supported(N, G, F, K, 0) || wide_supported(N, G, F, K, 1)) ? wide_pack_bytes(G, F, K) : 0;
-  if (backward && wide_dh_supported(N, G, F, K)) {
-    const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
-    n += align_up(np * F * K * G * sizeof(float), 256) + align_up(np * F * sizeof(float), 256);
-    n += align_up((size_t)B * N * F * sizeof(float), 256);   // dY o act'(y), handed from the dX kernel to the dH kernel
+static int wide_planes(int prec) { return prec == GFC_PREC_FP32_3XTF32 ? 2 : 1; }
+// workspace behind the tile plan's own: [packed taps | amax (256 B) | dH partials | db partials | dY o act'(y)]
+struct WideWs {
+  size_t pack, amax, dhp, dbp, dpre, bytes;
+};
+static WideWs wide_ws(int B, int N, int G, int F, int K, int backward) {
+  WideWs o{};
+  size_t off = 0;
+  if (wide_supported(N, G, F, K, 0) || wide_supported(N, G, F, K, 1)) {
+    o.pack = off; off += wide_pack_bytes(G, F, K);
+    o.amax = off; off += 256;
+    o.dhp = o.dbp = o.dpre = off;
+    if (backward && wide_dh_supported(N, G, F, K)) {
+      const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
+      o.dhp = off; off += align_up(np * F * K * G * sizeof(float), 256);
+      o.dbp = off; off += align_up(np * F * sizeof(float), 256);
+      o.dpre = off; off += align_up((size_t)B * N * F * sizeof(float), 256);   // dY o act'(y), handed from the dX kernel to the dH kernel
+    }
   }
-  return n;
+  o.bytes = off;
+  return o;
+}
+static size_t wide_ws_extra(int B, int N, int G, int F, int K, int backward) { return wide_ws(B, N, G, F, K, backward).bytes; }
+static void fill_wide_graph(WideGraph& g, const GsoSrc& gs, const TileArgs& a, bool norm) {
+  g = WideGraph{};
+  g.pos = gs.pos; g.thr = a.thr; g.thr_lo = a.thr_lo; g.thr_hi = a.thr_hi; g.norm = norm ? 1 : 0;
 }
 
 // ---- forward ------------------------------------------------------------------
@@ -233,20 +253,22 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     TileArgs a{};
     a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
     a.x = x; a.h = h; a.bias = bias; a.y = y;
-    a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+    a.act = act; a.slope = slope; a.single_pass = (prec != GFC_PREC_FP32_3XTF32);
     a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
-    if (use_wide(gs, norm, N, G, F, K, 0, prec) && a.vec_ok && aligned16(gs.pos)) {
-      // tcgen05 / TMEM path: bf16x3 planes, hops and taps on the tensor cores
-      uint16_t* hp = reinterpret_cast<uint16_t*>(static_cast<char*>(ws) + p.ws_bytes);
-      rc = launch_wide_pack(h, G, F, K, 0, hp, st);
+    if (use_wide(gs, N, G, F, K, 0, prec) && a.vec_ok && aligned16(gs.pos)) {
+      // tcgen05 / TMEM path: fp16 hi/lo planes, hops and taps on the tensor cores
+      const WideWs wws = wide_ws(B, N, G, F, K, 0);
+      unsigned char* hp = reinterpret_cast<unsigned char*>(ws) + p.ws_bytes + wws.pack;
+      const int cs = wide_cshift(N, norm), np = wide_planes(prec);
+      rc = launch_wide_pack(h, G, F, K, 0, cs, np, hp, st);
       if (rc) return rc;
       WideArgs wa{};
-      wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
-      wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K;
-      wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
-      return launch_wide(wa, G, F, 0, st);
+      fill_wide_graph(wa.g, gs, a, norm);
+      wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
+      wa.act = act; wa.slope = slope;
+      return launch_wide(wa, G, F, 0, np, st);
     }
     if (!p.h_smem) {
       float4* hp = reinterpret_cast<float4*>(static_cast<char*>(ws) + p.ws_hpack);
@@ -322,51 +344,62 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     a.x = x; a.h = h; a.yout = yout; a.dY = dY; a.dX = dX;
     a.dHp = dH ? reinterpret_cast<float*>(wsb + p.ws_dhp) : nullptr;
     a.dbp = db ? reinterpret_cast<float*>(wsb + p.ws_dbp) : nullptr;
-    a.act = act; a.slope = slope; a.single_pass = (prec == GFC_PREC_TF32);
+    a.act = act; a.slope = slope; a.single_pass = (prec != GFC_PREC_FP32_3XTF32);
     a.vec_ok = aligned16(dY) && (!x || aligned16(x)) && (!yout || aligned16(yout)) &&
                (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
-    float* wide_dpre = nullptr;
-    if (dX && use_wide(gs, norm, N, G, F, K, 1, prec) && a.vec_ok && aligned16(gs.pos) && aligned16(dX)) {
-      // dX on the tcgen05 path (V_k = P^k (dY o act'), dX = sum_k V_k H_k); dH / db below
-      uint16_t* hp = reinterpret_cast<uint16_t*>(wsb + p.ws_bytes);
-      rc = launch_wide_pack(h, G, F, K, 1, hp, st);
-      if (rc) return rc;
-      WideArgs wa{};
-      wa.pos = gs.pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
-      wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
-      wa.B = B; wa.N = N; wa.K = K; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
-      if (dH && act != GFC_ACT_NONE && wide_dh_supported(N, G, F, K)) {
-        const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
-        wide_dpre = reinterpret_cast<float*>(wsb + p.ws_bytes + wide_pack_bytes(G, F, K) +
-                                             align_up(np * nH * sizeof(float), 256) + align_up(np * F * sizeof(float), 256));
-        wa.d_out = wide_dpre;
+    if (use_wide(gs, N, G, F, K, 1, prec) && a.vec_ok && aligned16(gs.pos) && (!dX || aligned16(dX)) &&
+        (!dH || wide_dh_supported(N, G, F, K))) {
+      // tcgen05 path: dX kernel (V_k = P^k (dY o act'), dX = sum_k V_k H_k) and dH / db kernel (accumulators in
+      // tensor memory across all tiles of a CTA)
+      const WideWs wws = wide_ws(B, N, G, F, K, 1);
+      char* wb = wsb + p.ws_bytes;
+      const int cs = wide_cshift(N, norm), np = wide_planes(prec);
+      float* amax = reinterpret_cast<float*>(wb + wws.amax);
+      float* wide_dpre = nullptr;
+      const bool want_grads = dH != nullptr;   // db alone is served below by the tile kernels
+      if (!want_grads && db && !dX) goto tile_path;
+      if (want_grads) GFC_CUDA_TRY(cudaMemsetAsync(amax, 0, 2 * sizeof(float), st));
+      if (dX) {
+        unsigned char* hp = reinterpret_cast<unsigned char*>(wb + wws.pack);
+        rc = launch_wide_pack(h, G, F, K, 1, cs, np, hp, st);
+        if (rc) return rc;
+        WideArgs wa{};
+        fill_wide_graph(wa.g, gs, a, norm);
+        wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
+        wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs; wa.act = act; wa.slope = slope;
+        if (want_grads) {
+          wa.amax = amax;   // max |dY o act'(y)| of the batch: by-product of the tile scales
+          if (act != GFC_ACT_NONE) { wide_dpre = reinterpret_cast<float*>(wb + wws.dpre); wa.d_out = wide_dpre; }
+        }
+        rc = launch_wide(wa, G, F, 1, np, st);
+        if (rc) return rc;
+        a.dX = nullptr;
+        if (!dH && !db) return GFC_OK;
       }
-      rc = launch_wide(wa, G, F, 1, st);
-      if (rc) return rc;
-      a.dX = nullptr;
-      if (!dH && !db) return GFC_OK;
+      if (want_grads) {
+        const int npart = wide_dh_nparts(B, N, F, K);
+        float* dhp = reinterpret_cast<float*>(wb + wws.dhp);
+        float* dbp = reinterpret_cast<float*>(wb + wws.dbp);
+        // launch-wide operand scales: max |x| always, max |dY| (x max(1, slope)) when the dX kernel did not run
+        const float vbound = (act == GFC_ACT_LEAKY_RELU && slope > 1.f) ? slope : 1.f;
+        rc = launch_wide_absmax(x, (size_t)B * G * N, dX ? nullptr : dY, (size_t)B * N * F, vbound, amax, st);
+        if (rc) return rc;
+        WideDhArgs da{};
+        fill_wide_graph(da.g, gs, a, norm);
+        da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre; da.amax = amax;
+        da.dHp = dhp; da.dbp = db ? dbp : nullptr;
+        da.B = B; da.N = N; da.K = K; da.cshift = cs; da.act = act; da.slope = slope;
+        GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)npart * nH * sizeof(float), st));   // partials are accumulated with red.add
+        rc = launch_wide_dh(da, G, F, np, st);
+        if (rc) return rc;
+        if (g_skip_grad_reduce) return GFC_OK;
+        if (dp) return launch_reduce_allreduce(dhp, npart, (int)nH, dbp, npart, F, dH, *dp, st);
+        return launch_reduce_parts(dhp, npart, (int)nH, dH, db ? dbp : nullptr, npart, F, db, st);
+      }
     }
-    if (dH && use_wide(gs, norm, N, G, F, K, 1, prec) && wide_dh_supported(N, G, F, K) && a.vec_ok &&
-        aligned16(gs.pos) && !a.dX) {
-      // dH / db on the tcgen05 path: accumulators stay in tensor memory across all tiles of a CTA
-      const int np = wide_dh_nparts(B, N, F, K);
-      char* base = wsb + p.ws_bytes + wide_pack_bytes(G, F, K);
-      float* dhp = reinterpret_cast<float*>(base);
-      float* dbp = reinterpret_cast<float*>(base + align_up((size_t)np * nH * sizeof(float), 256));
-      WideDhArgs da{};
-      da.pos = gs.pos; da.thr = a.thr; da.thr_lo = a.thr_lo; da.thr_hi = a.thr_hi;
-      da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre;
-      da.dHp = dhp; da.dbp = db ? dbp : nullptr;
-      da.B = B; da.N = N; da.K = K; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
-      GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)np * nH * sizeof(float), st));   // partials are accumulated with red.add
-      rc = launch_wide_dh(da, G, F, st);
-      if (rc) return rc;
-      if (g_skip_grad_reduce) return GFC_OK;
-      if (dp) return launch_reduce_allreduce(dhp, np, (int)nH, dbp, np, F, dH, *dp, st);
-      return launch_reduce_parts(dhp, np, (int)nH, dH, db ? dbp : nullptr, np, F, db, st);
-    }
+  tile_path:
     if (!p.h_smem && a.dX) {
       float4* hp = reinterpret_cast<float4*>(wsb + p.ws_hpack);
       rc = launch_pack_taps(h, F, p.KG, 1, hp, st);
@@ -566,8 +599,8 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   rc = gso_mode_threshold(mode, radius, &thr, &norm);
   if (rc) return rc;
   GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
-  GFC_REQUIRE(use_wide(gs, norm, N, G, F, K, 0, precision) && aligned16(x_nm) && aligned16(y) && aligned16(pos),
-              GFC_ERR_UNSUPPORTED, "%s: node-major input needs the tcgen05 wide path (binary GSO, G, F in {64,128}, "
+  GFC_REQUIRE(use_wide(gs, N, G, F, K, 0, precision) && aligned16(x_nm) && aligned16(y) && aligned16(pos),
+              GFC_ERR_UNSUPPORTED, "%s: node-major input needs the tcgen05 wide path (positions, G, F in {64,128}, "
               "N <= 128, 16-byte aligned tensors); transpose to [B,G,N] and call gfc_filter_fwd_pos", fn);
   TilePlan p;
   GFC_REQUIRE(plan_tile(B, N, G, F, K, 0, GSRC_POS, &p), GFC_ERR_UNSUPPORTED, "%s: shape not covered", fn);
@@ -575,14 +608,16 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   if (rc) return rc;
   TileArgs a{};
   set_thresholds(a, thr, norm);
-  uint16_t* hp = reinterpret_cast<uint16_t*>(static_cast<char*>(workspace) + p.ws_bytes);
-  rc = launch_wide_pack(h, G, F, K, 0, hp, st);
+  const WideWs wws = wide_ws(B, N, G, F, K, 0);
+  unsigned char* hp = reinterpret_cast<unsigned char*>(workspace) + p.ws_bytes + wws.pack;
+  const int cs = wide_cshift(N, norm), np = wide_planes(precision);
+  rc = launch_wide_pack(h, G, F, K, 0, cs, np, hp, st);
   if (rc) return rc;
   WideArgs wa{};
-  wa.pos = pos; wa.thr = a.thr; wa.thr_lo = a.thr_lo; wa.thr_hi = a.thr_hi;
-  wa.in = x_nm; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K;
-  wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
-  return launch_wide(wa, G, F, 2, st);
+  fill_wide_graph(wa.g, gs, a, norm);
+  wa.in = x_nm; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
+  wa.act = act; wa.slope = slope;
+  return launch_wide(wa, G, F, 2, np, st);
 }
 
 extern "C" int gfc_filter_bwd(const float* x, const float* S, const float* h, const float* y_out,
@@ -665,7 +700,7 @@ extern "C" int gfc_filter_csr_fwd(const float* x, const int32_t* rowptr, const i
   if (rc) return rc;
   if (g_csr_fused && csr_fwd_fused_supported(N, G, F, K, nullptr) && aligned16(y))
     return launch_csr_fwd_fused(x, rowptr, colidx, vals, nnz_stride, h, bias, y, B, N, G, F, K, act, slope,
-                                precision == GFC_PREC_TF32, st);
+                                precision != GFC_PREC_FP32_3XTF32, st);
   float* Zw = reinterpret_cast<float*>(static_cast<char*>(workspace) + g.ws_z);
   const long long C = (long long)K * G;
   rc = launch_hops_csr(Zw, rowptr, colidx, vals, nnz_stride, B, N, G, K, 0, x, nullptr, st);
@@ -711,7 +746,7 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
     float* dbp = reinterpret_cast<float*>(wsb + g.ws_fdb);
     rc = launch_csr_bwd_fused(x, rowptr_t, colidx_t, vals_t, nnz_stride, h, (act != GFC_ACT_NONE) ? y_out : nullptr, dY,
                               dX, dH ? dhp : nullptr, db ? dbp : nullptr, B, N, G, F, K, act, slope,
-                              precision == GFC_PREC_TF32, st);
+                              precision != GFC_PREC_FP32_3XTF32, st);
     if (rc) return rc;
     if (!dH && !db) return GFC_OK;
     return launch_reduce_parts(dH ? dhp : nullptr, B, (int)nH, dH, db ? dbp : nullptr, B, F, db, st);

@@ -13,6 +13,7 @@
 // because a core matrix is 8 x 16 B either way.  panel_bytes = rows*16 + 16 (the 16-byte pad
 // staggers the panels over the shared-memory banks for the CUDA-core writers).
 #pragma once
+#include <cuda_fp16.h>
 #include "gfc_common.cuh"
 
 namespace gfc {
@@ -274,6 +275,53 @@ __device__ __forceinline__ void split_bf16x3(float x, uint32_t& p0, uint32_t& p1
 }
 // two fp32 bit patterns -> one word of two bf16 (upper halves); `a` at the lower address
 __device__ __forceinline__ uint32_t pack_bf16_hi(uint32_t a, uint32_t b) { return __byte_perm(a, b, 0x7632); }
+
+// ---- fp16 operands (kind::f16 with a_format = b_format = F16), fp32 accumulate ------------------------
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4)                          // c_format  = F32
+         | (0u << 7)                        // a_format  = F16
+         | (0u << 10)                       // b_format  = F16
+         | ((uint32_t)a_mn_major << 15)     // a_major   (0 = K, 1 = MN)
+         | ((uint32_t)b_mn_major << 16)     // b_major
+         | ((uint32_t)(N >> 3) << 17)       // n_dim
+         | ((uint32_t)(M >> 4) << 24);      // m_dim
+}
+// Two (already scaled) fp32 values -> one word of two fp16: `a` in the low half (lower address).  hi = RN(x),
+// lo = RN(x - hi): x = hi + lo to 2^-22 |x| while lo is a normal fp16 (|x| >= 2^-3), to 2^-25 absolute below
+// (fp16 subnormals are exact multiples of 2^-24 and run at full rate on the tensor core).
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// 8 consecutive channels of one row (already scaled) -> one 16-byte chunk in each of the NP fp16 planes
+template <int NP>
+__device__ __forceinline__ void store_chunk_f16(unsigned char* plane0, int plane_bytes, const float (&v)[8]) {
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (NP == 2) split_f16x2(v[2 * i], v[2 * i + 1], hi[i], lo[i]);
+    else hi[i] = pack_f16x2(v[2 * i], v[2 * i + 1]);
+  }
+  *reinterpret_cast<uint4*>(plane0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  if (NP == 2) *reinterpret_cast<uint4*>(plane0 + plane_bytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+// power-of-two scale that brings a tensor of maximum magnitude m (bit pattern mbits, m >= 0) just below
+// 2^top:  m * s in [2^(top-1), 2^top).  Returns s; *inv = 1/s.  m = 0 (or tiny / huge) clamps to a finite s.
+__device__ __forceinline__ float pow2_scale(uint32_t mbits, int top, float* inv) {
+  int e = (int)((mbits >> 23) & 0xffu);            // m in [2^(e-127), 2^(e-126))
+  int se = 127 + top - (e - 126);                  // biased exponent of s
+  if (e == 0) se = 127;                            // zero / denormal input: leave it alone
+  se = se < 1 ? 1 : (se > 253 ? 253 : se);
+  *inv = __uint_as_float((uint32_t)(254 - se) << 23);
+  return __uint_as_float((uint32_t)se << 23);
+}
 
 // shared-memory matrix descriptor (no swizzle) from byte offsets
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {

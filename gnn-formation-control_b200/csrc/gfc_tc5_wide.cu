@@ -1,26 +1,36 @@
 // gfc_tc5_wide.cu — warp-specialised tcgen05 / TMEM kernels of the fused graph filter for
-// wide feature counts (64..128 channels), GSO rebuilt on chip from positions.
+// wide feature counts (64..128 channels).
 //
 // One persistent CTA per SM works on tiles of 128 packed rows r = (graph j, node n).  ALL the
 // arithmetic of BatchLSIGF (utils/graphUtils/graphML.py:2342-2366) runs on the 5th-generation
 // tensor cores with fp32 accumulators in tensor memory:
-//   * the diffusion state W_k [128 rows x CIN channels] lives in shared memory as THREE bf16
-//     planes (successive truncation, W = p0 + p1 + p2 to 2^-24) in the UMMA canonical no-swizzle
-//     layout, split into two channel slabs that are processed as two independent chains;
-//   * the hop  W_{k+1} = P W_k  (graphML.py:2349-2352) is an MMA with the block-diagonal 0/1
-//     matrix P of the tile's graphs (exact in bf16) as A operand and the three planes of W_k
-//     as MN-major B operands: the result in TMEM is the exact fp32 hop;
-//   * the tap contraction  OUT += W_k H_k  (graphML.py:2361-2362) is the 6-term product of the
-//     bf16x3 planes (error ~2^-23, fp32-equivalent); the taps stream through a ring of
-//     shared-memory stages filled by the TMA engine (cp.async.bulk) from a pre-packed copy;
-//   * worker warps read the hop result back (tcgen05.ld), split it into planes for the next
-//     tap, and run the epilogue (bias + activation, or the dX transpose) of tile t while the
-//     issuing thread already feeds the tensor core with tile t+1.
+//   * the diffusion state W_k [128 rows x CIN channels] lives in shared memory as TWO fp16 planes
+//     (hi = RN(x), lo = RN(x - hi): x = hi + lo to 2^-22) in the UMMA canonical no-swizzle layout,
+//     split into two channel slabs that are processed as two independent chains.  fp16 has 11
+//     significant bits against bf16's 8, so a two-plane split already carries fp32-class accuracy
+//     and a product needs 3 MMAs (hi hi + hi lo + lo hi, dropped term 2^-22) where the bf16x3 split
+//     of round 1 needed 6.  fp16's narrow exponent range is handled by exact power-of-two scales:
+//     a per-tile scale s (tile maximum -> 2^14), and a per-hop headroom 2^-c (c = ceil(log2(N-1))
+//     for a 0/1 GSO, 0 for the row-normalised one) that is compensated EXACTLY inside the packed
+//     taps (H_k is stored as H_k t_h 2^(c k)), so every W_k sits at the top of the fp16 range;
+//   * the hop  W_{k+1} = P W_k  (graphML.py:2349-2352) is an MMA with the block-diagonal matrix P of the
+//     tile's graphs as A operand from TENSOR MEMORY (0/1 entries: exact) and the two planes of W_k as
+//     MN-major B operands; the result in TMEM is the exact fp32 hop;
+//   * the tap contraction  OUT += W_k H_k  (graphML.py:2361-2362) is the 3-term product of the fp16
+//     planes; the taps stream through a ring of shared-memory stages filled by the TMA engine
+//     (cp.async.bulk) from a pre-packed, pre-scaled L2-resident copy;
+//   * worker warps read the hop result back (tcgen05.ld), split it into planes for the next tap, and
+//     run the epilogue (unscale, bias + activation, or the dX transpose) of tile t while the issuing
+//     thread already feeds the tensor core with tile t+1.
+// Sym-norm GSO (multirobotsim_dcenlocal.py:306-315), S = D^-1/2 A D^-1/2: carried as What_k = D^-1/2 W_k, so
+// What_{k+1} = D^-1 (A What_k) and y = D^1/2 sum_k What_k H_k — P stays 0/1 (exact) and the weights are
+// fp32 row scalings in the workers; there is no growth per hop (c = 0).
 // MODE 0: forward,  IN = x [B,G,N],  OUT = y [B,N,F]   (CIN = G, COUT = F)
 // MODE 2: forward with the input given node-major, IN = x [B,N,G] (a previous layer's output), OUT = y [B,N,F]
 // MODE 1: backward dX: V_0 = dY o act'(y), V_k = P V_{k-1}, dX = sum_k V_k H_k^T-contraction
 //         (IN = dY [B,N,F], OUT = dX [B,G,N]; CIN = F, COUT = G) — the closed form of the autograd
-//         graph of graphML.py:2342-2366 for a symmetric 0/1 GSO.
+//         graph of graphML.py:2342-2366 for a symmetric GSO.
+// NP = 1 keeps only the hi plane (1 MMA per product, ~2^-11 relative: the stated looser bound of GFC_PREC_F16).
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <type_traits>
@@ -31,31 +41,37 @@
 
 namespace gfc {
 using tc5::make_desc;
-using tc5::store_chunk3;
+using tc5::store_chunk_f16;
 
-template <int CIN, int COUT>
+constexpr int kWideTop = 14;        // operand maxima are scaled to [2^13, 2^14): two bits below the fp16 overflow
+constexpr int kPackHeader = 256;    // bytes in front of the packed tap planes: float[0] = 1 / t_h
+
+template <int CIN, int COUT, int NP>
 struct WideLayout {
   static constexpr int ROWS = 128;
   static constexpr int CS = CIN / 2;                 // channels per slab
   static constexpr int CPT = CS / 2;                 // state columns per worker thread
-  static constexpr int NCH = CS / 8;                 // 16-byte chunks (8 bf16) per row and slab
+  static constexpr int NCH = CS / 8;                 // 16-byte chunks (8 fp16) per row and slab
   static constexpr int PW = ROWS * 16;               // bytes between chunks (one chunk column of all rows)
-  static constexpr int PLANE = NCH * PW;             // one bf16 plane of a slab
-  static constexpr int SLAB = 3 * PLANE;
-  static constexpr int STAGE = COUT * 96;            // taps of 16 channels: 3 planes x 2 chunks x COUT x 16 B
-  static constexpr int NSTAGE = 6;
+  static constexpr int PLANE = NCH * PW;             // one fp16 plane of a slab
+  static constexpr int SLAB = NP * PLANE;
+  static constexpr int STAGE = COUT * 32 * NP;       // taps of 16 channels: NP planes x 2 chunks x COUT x 16 B
+  static constexpr int NSTAGE = 8;
   static constexpr int KSTEPS = CS / 16;             // tap MMA k-steps (= ring stages) per phase
   static constexpr int OFF_W = 0;
   static constexpr int OFF_RING = OFF_W + 2 * SLAB;
   static constexpr int OFF_STAGE = (OFF_RING + NSTAGE * STAGE + 1023) / 1024 * 1024;   // 2 TMA store staging buffers [128 rows x 32 cols] fp32, 128B swizzle
   static constexpr int OFF_BIAS = OFF_STAGE + 2 * ROWS * 128;
-  static constexpr int OFF_SP = OFF_BIAS + COUT * 4;         // float2 positions of the tile rows
-  static constexpr int OFF_BAR = OFF_SP + 2 * ROWS * 8;     // (two position buffers, alternating per tile)
+  static constexpr int OFF_SP = OFF_BIAS + COUT * 4;         // float2 positions of the tile rows (two buffers, alternating per tile)
+  static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;      // int [2 buffers][2 halves][128]: partial row degrees (sym-norm)
+  static constexpr int OFF_TAB = OFF_DEG + 2 * 2 * ROWS * 4; // float [3][128]: d^-1/2, 1/d, d^1/2 by degree
+  static constexpr int OFF_MAX = OFF_TAB + 3 * 128 * 4;      // uint [8]: per-warp tile maxima
+  static constexpr int OFF_BAR = OFF_MAX + 32;
   static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 1 + 2 + 2;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr int TM_OUT = 0;                   // two output accumulators [128 x COUT]
   static constexpr int TM_HOP = 2 * COUT;            // two hop accumulators   [128 x CS]
-  static constexpr int TM_P = 2 * COUT + 2 * CS;     // two buffers of the block-diagonal 0/1 hop matrix P, bf16 [128 lanes x 128 k] = 64 columns each
+  static constexpr int TM_P = 2 * COUT + 2 * CS;     // two buffers of the block-diagonal hop matrix P, fp16 [128 lanes x 128 k] = 64 columns each
   static constexpr int TM_USED = 2 * COUT + 2 * CS + 128;
   static constexpr int TM_COLS = TM_USED <= 32 ? 32 : TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
   static_assert(CIN % 32 == 0 && CIN >= 32 && CIN <= 128, "CIN in {32,64,96,128}");
@@ -74,20 +90,12 @@ int g_wide_no_prefetch = 0;    // experiment switch
 static __device__ __noinline__ bool wide_adjacent_exact(float ax, float ay, float bx, float by, double thr) {
   return sqdist64(ax, ay, bx, by) <= thr;
 }
-__device__ __forceinline__ bool wide_adjacent(float2 a, float2 b, double thr, float thr_lo, float thr_hi) {
-  const float dx = a.x - b.x, dy = a.y - b.y;
-  const float s = fmaf(dx, dx, dy * dy);
-  if (s < thr_lo) return true;
-  if (s > thr_hi) return false;
-  return wide_adjacent_exact(a.x, a.y, b.x, b.y, thr);
-}
 
-// adjacency of tile row `pr` (position `me`) with the 8 tile rows c0..c0+7: fp32 bit patterns 1.0f / 0.
+// adjacency of tile row `pr` (position `me`) with the 8 tile rows c0..c0+7 as a bit mask.
 // All 8 squared distances are formed first (8 independent shared-memory loads); the exact fp64 rule only
 // runs for the rare pairs inside the fp32 rounding band.
-__device__ __forceinline__ void adjacency8(uint32_t (&e)[8], const float2* __restrict__ sp, float2 me, int pr,
-                                           int c0, int c_lo, int c_hi, int rows_used, double thr, float thr_lo,
-                                           float thr_hi) {
+__device__ __forceinline__ uint32_t adjacency8(const float2* __restrict__ sp, float2 me, int pr, int c0, int c_lo,
+                                               int c_hi, int rows_used, double thr, float thr_lo, float thr_hi) {
   float sv[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
@@ -95,12 +103,12 @@ __device__ __forceinline__ void adjacency8(uint32_t (&e)[8], const float2* __res
     const float dx = me.x - o.x, dy = me.y - o.y;
     sv[i] = fmaf(dx, dx, dy * dy);
   }
-  uint32_t band = 0;
+  uint32_t bits = 0, band = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int c = c0 + i;
     const bool ok = (c >= c_lo) && (c < c_hi) && (c != pr) && (pr < rows_used) && (c < rows_used);
-    e[i] = (ok && sv[i] < thr_lo) ? 0x3f800000u : 0u;
+    if (ok && sv[i] < thr_lo) bits |= 1u << i;
     if (ok && sv[i] >= thr_lo && sv[i] <= thr_hi) band |= 1u << i;
   }
   if (band) {
@@ -108,10 +116,15 @@ __device__ __forceinline__ void adjacency8(uint32_t (&e)[8], const float2* __res
     for (int i = 0; i < 8; ++i) {
       if (band & (1u << i)) {
         const float2 o = sp[c0 + i];
-        e[i] = wide_adjacent_exact(me.x, me.y, o.x, o.y, thr) ? 0x3f800000u : 0u;
+        if (wide_adjacent_exact(me.x, me.y, o.x, o.y, thr)) bits |= 1u << i;
       }
     }
   }
+  return bits;
+}
+// two adjacency bits -> one word of two fp16 (1.0 = 0x3c00), bit `lo` at the lower address
+__device__ __forceinline__ uint32_t p_word(uint32_t bits, int lo) {
+  return (((bits >> lo) & 1u) ? 0x3c00u : 0u) | (((bits >> (lo + 1)) & 1u) ? 0x3c000000u : 0u);
 }
 
 // Predicated read-only loads as volatile asm: issued exactly where written (never sunk to the first use)
@@ -149,14 +162,27 @@ __device__ __forceinline__ float ldg_cg(const float* p) {
 }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-template <int CIN, int COUT, int MODE>
+// d^-1/2, 1/d, d^1/2 by degree (isolated node: 1, 0, 1 — its row of S is zero, multirobotsim_dcenlocal.py:309-313)
+__device__ __forceinline__ void fill_degree_tables(float* tab, int tid, int nthreads) {
+  for (int d = tid; d < 128; d += nthreads) {
+    const float fd = (float)d;
+    tab[d] = d ? 1.f / sqrtf(fd) : 1.f;
+    tab[128 + d] = d ? 1.f / fd : 0.f;
+    tab[256 + d] = d ? sqrtf(fd) : 1.f;
+  }
+}
+
+template <int CIN, int COUT, int MODE, int NP>
 __global__ void __launch_bounds__(kWideThreads, 1)
 tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUtensorMap tmap_out) {
-  using L = WideLayout<CIN, COUT>;
+  using L = WideLayout<CIN, COUT, NP>;
   extern __shared__ __align__(128) unsigned char wsmem[];
   unsigned char* Wb = wsmem + L::OFF_W;
   unsigned char* Rb = wsmem + L::OFF_RING;
   float2* sp_all = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
+  int* sdeg = reinterpret_cast<int*>(wsmem + L::OFF_DEG);
+  float* dtab = reinterpret_cast<float*>(wsmem + L::OFF_TAB);
+  uint32_t* smax = reinterpret_cast<uint32_t*>(wsmem + L::OFF_MAX);
   unsigned char* stage_out = wsmem + L::OFF_STAGE;
   float* sbias = reinterpret_cast<float*>(wsmem + L::OFF_BIAS);
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsmem + L::OFF_BAR);
@@ -171,6 +197,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
+  const bool norm = w.g.norm != 0;
   // a CTA owns a CONTIGUOUS range of tiles: its streams stay inside a few 2 MB pages for many tiles (strided
   // assignment made every CTA touch new pages of every array at every tile: TLB-miss storms at tile boundaries)
   const int tiles_per_cta = (w.ntiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -179,6 +206,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 
   // ---- one-time setup -------------------------------------------------------------------------
   for (int i = tid; i < COUT; i += kWideThreads) sbias[i] = (MODE != 1 && w.bias) ? __ldg(w.bias + i) : 0.f;
+  fill_degree_tables(dtab, tid, kWideThreads);
   if (tid == 0) {
     for (int i = 0; i < L::NSTAGE; ++i) { tc5::mbar_init(&h_full[i], 1); tc5::mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
@@ -197,21 +225,18 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
 
-  // NOTE on code size: every role's per-tile code is executed once per ~15 us while the other roles run
+  // NOTE on code size: every role's per-tile code is executed once per ~10 us while the other roles run
   // their own loops, so the instruction caches only hold it if it is small.  Loops are deliberately kept
   // rolled (one copy of the plane-split / pair-test / MMA-issue code each) unless a register array forces
   // unrolling; barrier parities are bit masks so that they can be indexed at run time.
   if (warp == 0) {
     // =========================== MMA issuer (one elected thread) ===============================
     if (tc5::elect_one()) {
-      constexpr uint32_t kIdescTap = tc5::idesc_bf16(128, COUT, 0, 0);
-      constexpr uint32_t kIdescHop = tc5::idesc_bf16(128, L::CS, 0, 1);
+      constexpr uint32_t kIdescTap = tc5::idesc_f16(128, COUT, 0, 0);
+      constexpr uint32_t kIdescHop = tc5::idesc_f16(128, L::CS, 0, 1);
       const uint32_t w_addr = tc5::smem_u32(Wb), r_addr = tc5::smem_u32(Rb);
       uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0;
       int st = 0;
-      int nstamp = 0;
-      const bool dbg = w.dbg != nullptr && blockIdx.x == 0;
-#define GFC_WSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
       const int hop_ksteps = (w.gpc * N + 15) >> 4;
       int it = 0;
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
@@ -222,10 +247,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 #pragma unroll 1
         for (int ph = 0; ph < 2 * K; ++ph) {
           const int k = ph >> 1, s = ph & 1;
-          GFC_WSTAMP(100 + s);
           tc5::mbar_wait(&w_ready[s], (par_wr >> s) & 1); par_wr ^= 1u << s;
           tc5::fence_after_sync();
-          GFC_WSTAMP(110 + s);
           const uint32_t ws = w_addr + s * L::SLAB;
           if (k + 1 < K) {
             // hop: D_hop[s] = P * W_k[slab s]   (A = P from tensor memory, B = state planes MN-major)
@@ -233,41 +256,35 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
             uint32_t acc = 0;
 #pragma unroll 1
             for (int j = 0; j < hop_ksteps; ++j) {
-              const uint32_t pa = tmem + L::TM_P + ob * 64 + j * 8;   // 16 source rows = 8 columns of bf16 pairs
+              const uint32_t pa = tmem + L::TM_P + ob * 64 + j * 8;   // 16 source rows = 8 columns of fp16 pairs
 #pragma unroll
-              for (int pl = 0; pl < 3; ++pl) {
+              for (int pl = 0; pl < NP; ++pl) {
                 tc5::mma_bf16_ts(d_hop, pa, make_desc(ws + pl * L::PLANE + j * 256, 128, L::PW), kIdescHop, acc);
                 acc = 1;
               }
             }
           }
-          // taps: D_out += W_k[slab s] * H_k[slab s]   (6-term bf16x3 product)
+          // taps: D_out += W_k[slab s] * H_k[slab s]   (hi hi + hi lo + lo hi)
 #pragma unroll 1
           for (int i = 0; i < L::KSTEPS; ++i) {
-            if (i == 0) GFC_WSTAMP(120 + s);
             tc5::mbar_wait(&h_full[st], par_hf);
             tc5::fence_after_sync();
-            GFC_WSTAMP(130 + i);
             const uint32_t hs = r_addr + st * L::STAGE;
             const uint32_t wa = ws + i * 2 * L::PW;
             const uint64_t a0 = make_desc(wa, L::PW, 128);
-            const uint64_t a1 = make_desc(wa + L::PLANE, L::PW, 128);
-            const uint64_t a2 = make_desc(wa + 2 * L::PLANE, L::PW, 128);
             const uint64_t b0 = make_desc(hs, COUT * 16, 128);
-            const uint64_t b1 = make_desc(hs + COUT * 32, COUT * 16, 128);
-            const uint64_t b2 = make_desc(hs + COUT * 64, COUT * 16, 128);
             const uint32_t first = (ph == 0 && i == 0) ? 0u : 1u;
             tc5::mma_bf16_ss(d_out, a0, b0, kIdescTap, first);
-            tc5::mma_bf16_ss(d_out, a0, b1, kIdescTap, 1u);
-            tc5::mma_bf16_ss(d_out, a1, b0, kIdescTap, 1u);
-            tc5::mma_bf16_ss(d_out, a1, b1, kIdescTap, 1u);
-            tc5::mma_bf16_ss(d_out, a0, b2, kIdescTap, 1u);
-            tc5::mma_bf16_ss(d_out, a2, b0, kIdescTap, 1u);
+            if (NP == 2) {
+              const uint64_t a1 = make_desc(wa + L::PLANE, L::PW, 128);
+              const uint64_t b1 = make_desc(hs + COUT * 32, COUT * 16, 128);
+              tc5::mma_bf16_ss(d_out, a0, b1, kIdescTap, 1u);
+              tc5::mma_bf16_ss(d_out, a1, b0, kIdescTap, 1u);
+            }
             tc5::mma_commit(&h_empty[st]);
             if (++st == L::NSTAGE) { st = 0; par_hf ^= 1; }
           }
           tc5::mma_commit(&mma_done[s]);
-          GFC_WSTAMP(140 + s);
         }
         tc5::mma_commit(&out_full[ob]);
       }
@@ -281,13 +298,13 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       bool primed = false;   // the first NSTAGE fills need no wait
       int filled = 0;
       const int stages_per_tile = K * (CIN / 16);
+      const unsigned char* hsrc = w.hpack + kPackHeader;
       for (int tile = t_begin; tile < t_end; ++tile) {
 #pragma unroll 1
         for (int u = 0; u < stages_per_tile; ++u) {
           if (primed) { tc5::mbar_wait(&h_empty[st], par_he); }
           tc5::mbar_arrive_expect_tx(&h_full[st], L::STAGE);
-          tc5::bulk_g2s(Rb + st * L::STAGE, reinterpret_cast<const unsigned char*>(w.hpack) + (size_t)u * L::STAGE,
-                        L::STAGE, &h_full[st]);
+          tc5::bulk_g2s(Rb + st * L::STAGE, hsrc + (size_t)u * L::STAGE, L::STAGE, &h_full[st]);
           if (++st == L::NSTAGE) { st = 0; if (primed) par_he ^= 1; }
           if (!primed && ++filled == L::NSTAGE) primed = true;
         }
@@ -297,21 +314,24 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
   } else {
     // =========================== workers ======================================================
     const int wt = tid - 64;                 // 0..255
+    const int ww = warp - 2;
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;        // which half of a slab's columns
+    const int half = ww >> 2;                // which half of a slab's columns
     const int r = q * 32 + lane;             // tile row owned by this thread (= its TMEM lane)
     const int jr = r / N, nr = r - jr * N;   // (graph, node) of the row
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
-    float xin[L::CPT];
+    const float inv_th = __ldg(reinterpret_cast<const float*>(w.hpack));   // 1 / (tap scale)
+    const float hop_down = __uint_as_float((uint32_t)(127 - w.cshift) << 23);   // 2^-c
+    float xin0[L::CPT], xin1[L::CPT];
     float2 mypos = make_float2(0.f, 0.f);
     uint32_t par_md = 0, par_ofl = 0;
-    int nstamp = 0;
-    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
-#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2048 + 2 * nstamp] = clock64(); w.dbg[2048 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+    // per-tile scalars of the LIVE tile (the one whose MMAs run) and of the NEXT one (being prepared)
+    float inv_live = 1.f, wbf_live = hop_down, rowf_live = 1.f;
+    float scale_next = 1.f, inv_next = 1.f, wbf_next = hop_down, rowf_next = 1.f;
 
     // Operands of the next tile.  Early in the current tile one thread asks the TMA engine to pull the
-    // (contiguous) input tile into L2; the register loads then happen slab by slab right before the slab is
-    // written (short live ranges, L2-hit latency hidden behind the P build / the wait for the slab).
+    // (contiguous) input tile into L2; the register loads then happen late in the tile (L2-hit latency hidden
+    // behind the last taps).
     auto prefetch_tile = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
@@ -324,10 +344,10 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
       if (wt < 128)   // rows 0..127 in thread order wt: position of row wt
-        mypos = (wt < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + wt)
+        mypos = (wt < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wt)
                                   : make_float2(0.f, 0.f);
     };
-    auto load_slab = [&](int tile, int s) {
+    auto load_slab = [&](int tile, int s, float (&xin)[L::CPT]) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
       const bool valid = r < gcount * N;
@@ -338,10 +358,9 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         for (int i = 0; i < L::CPT; ++i) xin[i] = ldg_f32(src + (size_t)i * N, valid);
       } else {
         // dY / y are row-major [rows x CIN]: a warp instruction reads whole 16-byte pieces of RPI consecutive rows
-        // (4 full lines) instead of 32 scattered ones; the halves of a bf16 chunk meet by a lane-pair shuffle
+        // (4 full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle
         // at store time.  Warp ww owns rows 16 ww .. 16 ww + 15, lane = (row offset, piece).
         constexpr int PPR = L::CS / 4, RPI = 32 / PPR;
-        const int ww = warp - 2;
         const int rows_used = gcount * N;
 #pragma unroll
         for (int i = 0; i < L::CPT / 4; ++i) {
@@ -362,20 +381,20 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         }
       }
     };
-    // registers of load_slab -> the three bf16 planes of W_0[slab s]
-    auto store_slab = [&](int s) {
+    // registers of load_slab -> the fp16 planes of W_0[slab s] (scaled by the tile scale, D^-1/2 for sym-norm)
+    auto store_slab = [&](int s, const float (&xin)[L::CPT], int pbuf) {
       if (MODE == 0) {
         unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
+        const float f0 = scale_next * rowf_next;   // rowf_next = d^-1/2 of this thread's row (1 when not normalised)
 #pragma unroll
         for (int c = 0; c < L::CPT / 8; ++c) {
           float v[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = xin[c * 8 + i];
-          store_chunk3(base + c * L::PW, L::PLANE, v);
+          for (int i = 0; i < 8; ++i) v[i] = xin[c * 8 + i] * f0;
+          store_chunk_f16<NP>(base + c * L::PW, L::PLANE, v);
         }
       } else {
         constexpr int PPR = L::CS / 4, RPI = 32 / PPR;
-        const int ww = warp - 2;
         const int pi = lane % PPR;
         const bool odd = pi & 1;
 #pragma unroll
@@ -389,11 +408,13 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
+          const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+          float f0 = scale_next;
+          if (norm) f0 *= dtab[sdeg[(pbuf * 2 + 0) * L::ROWS + row] + sdeg[(pbuf * 2 + 1) * L::ROWS + row]];
           float v[8];
 #pragma unroll
-          for (int e = 0; e < 4; ++e) { v[e] = odd ? rcv[e] : own[e]; v[4 + e] = odd ? own[e] : rcv[e]; }
-          const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
-          store_chunk3(Wb + s * L::SLAB + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
+          for (int e = 0; e < 4; ++e) { v[e] = (odd ? rcv[e] : own[e]) * f0; v[4 + e] = (odd ? own[e] : rcv[e]) * f0; }
+          store_chunk_f16<NP>(Wb + s * L::SLAB + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
         }
       }
     };
@@ -406,6 +427,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 
     // P[r][c] = 1 iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
     // TMEM lane r; the two warps of a quadrant interleave 4-chunk groups of source rows.  Chunks t0..t1-1 of 8.
+    int degcnt = 0;
     auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
       const float2* sp = sp_all + pbuf * L::ROWS;
       const int gcount = min(w.gpc, w.B - tile * w.gpc);
@@ -416,18 +438,17 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 #pragma unroll 1
       for (int t = t0; t < t1; ++t) {
         const int qc = (t >> 2) * 8 + half * 4 + (t & 3);   // chunk of 8 source rows = 4 TMEM columns
-        uint32_t e[8];
-        if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
-          adjacency8(e, sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.thr, w.thr_lo, w.thr_hi);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) e[i] = 0u;
-        }
-        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, tc5::pack_bf16_hi(e[0], e[1]), tc5::pack_bf16_hi(e[2], e[3]),
-                      tc5::pack_bf16_hi(e[4], e[5]), tc5::pack_bf16_hi(e[6], e[7]));
+        uint32_t bits = 0;
+        if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
+          bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+        degcnt += __popc(bits);
+        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0), p_word(bits, 2), p_word(bits, 4),
+                      p_word(bits, 6));
       }
     };
-    auto publish_p = [&]() {
+    auto publish_p = [&](int pbuf) {
+      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;   // read after the tile-maximum barrier below
+      degcnt = 0;
       tc5::tmem_st_wait();
       tc5::fence_before_sync();
       __syncwarp();
@@ -456,7 +477,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         }
         if (!live || K == 1) {
           if (K > 1) build_p_part(next, pbuf, 0, 8);
-          publish_p();
+          publish_p(pbuf);
         }
       }
       // ---- write-backs of the K-1 hops ------------------------------------------------------------------
@@ -464,15 +485,14 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       bool slab0_loaded = false;
 #pragma unroll 1
       for (int ph = 0; ph < nwb; ++ph) {
-        // next tile's slab 0: requested two write-backs ahead of its use (memory latency behind the last taps)
-        if (has_next && !slab0_loaded && ph + 2 >= nwb) { load_slab(next, 0); slab0_loaded = true; }
+        // next tile's inputs: requested two write-backs ahead of their use (memory latency behind the last taps)
+        if (has_next && !slab0_loaded && ph + 2 >= nwb) { load_slab(next, 0, xin0); load_slab(next, 1, xin1); slab0_loaded = true; }
         {
           const int s = ph & 1;
-          GFC_KSTAMP(200 + s);
           tc5::mbar_wait(&mma_done[s], (par_md >> s) & 1); par_md ^= 1u << s;
           tc5::fence_after_sync();
-          GFC_KSTAMP(210 + s);
-          // hop result (exact fp32) -> three bf16 planes of W_{k+1}[slab s], 8 columns at a time
+          // hop result (exact fp32, scaled units) -> fp16 planes of W_{k+1}[slab s], 8 columns at a time;
+          // wbf = 2^-c (x 1/d of this row for sym-norm)
           const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + half * L::CPT;
           unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
 #pragma unroll 1
@@ -482,31 +502,46 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
             tc5::tmem_ld_wait();
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
-            store_chunk3(base + c * L::PW, L::PLANE, f);
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * wbf_live;
+            store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
           }
-          GFC_KSTAMP(220 + s);
           publish(&w_ready[s]);
-          GFC_KSTAMP(230 + s);
         }
         if (has_next && ph < 2) {   // K > 1 here
           build_p_part(next, pbuf, 4 * ph, 4 * ph + 4);
-          if (ph == 1) publish_p();
+          if (ph == 1) publish_p(pbuf);
         }
       }
+      // ---- next tile: inputs -> registers, tile maximum -> power-of-two scale ------------------------------
+      if (has_next) {
+        if (!slab0_loaded) { load_slab(next, 0, xin0); load_slab(next, 1, xin1); }
+        float m = 0.f;
+#pragma unroll
+        for (int i = 0; i < L::CPT; ++i) m = fmaxf(m, fmaxf(fabsf(xin0[i]), fabsf(xin1[i])));
+        const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like uints
+        if (lane == 0) smax[ww] = mw;
+        worker_bar();
+        uint32_t mt = smax[0];
+#pragma unroll
+        for (int i = 1; i < kWorkerWarps; ++i) mt = max(mt, smax[i]);
+        if (w.amax && wt == 0) atomicMax(reinterpret_cast<unsigned int*>(w.amax) + (MODE == 1 ? 1 : 0), mt);
+        scale_next = tc5::pow2_scale(mt, kWideTop, &inv_next);
+        wbf_next = hop_down; rowf_next = 1.f;
+        float sq = 1.f;
+        if (norm) {   // K > 1: the degrees of `next` were stored by publish_p before the barrier above
+          const int d = sdeg[(pbuf * 2 + 0) * L::ROWS + r] + sdeg[(pbuf * 2 + 1) * L::ROWS + r];
+          rowf_next = dtab[d]; wbf_next = hop_down * dtab[128 + d]; sq = dtab[256 + d];
+        }
+        inv_next *= sq;   // epilogue factor of this thread's row: 1/s (x d^1/2)
+      }
       // ---- the live tile's slabs become free one by one: next tile's state W_0 ---------------------------
-      GFC_KSTAMP(240);
-      if (has_next && !slab0_loaded) load_slab(next, 0);
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        if (has_next && s == 1) load_slab(next, 1);   // in flight while the last tap of slab 1 finishes
         if (live) { tc5::mbar_wait(&mma_done[s], (par_md >> s) & 1); par_md ^= 1u << s; }
-        GFC_KSTAMP(250 + s);
         if (has_next) {
-          store_slab(s);
+          if (s == 0) store_slab(0, xin0, pbuf); else store_slab(1, xin1, pbuf);
           publish(&w_ready[s]);
         }
-        GFC_KSTAMP(260 + s);
       }
       // ---- epilogue of the live tile (the issuer is already working on the next one) -------------------
       if (live) {
@@ -515,7 +550,6 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         const int ob = it & 1;
         tc5::mbar_wait(&out_full[ob], (par_ofl >> ob) & 1); par_ofl ^= 1u << ob;
         tc5::fence_after_sync();
-        GFC_KSTAMP(271);
         if constexpr (MODE != 1) {
           // y tile through swizzled staging buffers and the TMA store engine: full 128-byte lines
 #pragma unroll 1
@@ -533,10 +567,10 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
             for (int i4 = 0; i4 < 4; ++i4) {
               const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i4 * 4);
               float4 o;
-              o.x = apply_act(__uint_as_float(v[i4 * 4 + 0]) + bb.x, w.act, w.slope);
-              o.y = apply_act(__uint_as_float(v[i4 * 4 + 1]) + bb.y, w.act, w.slope);
-              o.z = apply_act(__uint_as_float(v[i4 * 4 + 2]) + bb.z, w.act, w.slope);
-              o.w = apply_act(__uint_as_float(v[i4 * 4 + 3]) + bb.w, w.act, w.slope);
+              o.x = apply_act(__uint_as_float(v[i4 * 4 + 0]) * inv_live * inv_th + bb.x, w.act, w.slope);
+              o.y = apply_act(__uint_as_float(v[i4 * 4 + 1]) * inv_live * inv_th + bb.y, w.act, w.slope);
+              o.z = apply_act(__uint_as_float(v[i4 * 4 + 2]) * inv_live * inv_th + bb.z, w.act, w.slope);
+              o.w = apply_act(__uint_as_float(v[i4 * 4 + 3]) * inv_live * inv_th + bb.w, w.act, w.slope);
               const int cc = half * 4 + i4;
               *reinterpret_cast<float4*>(srow + ((cc ^ (r & 7)) << 4)) = o;
             }
@@ -559,20 +593,21 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
             if (valid) {
               float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
 #pragma unroll
-              for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]);
+              for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]) * inv_live * inv_th;
             }
           }
         }
         tc5::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc5::mbar_arrive(&out_free[ob]);
-        GFC_KSTAMP(270);
       }
       if (!has_next) break;
       tile = next;
       next += 1;
       ++it;
+      inv_live = inv_next; wbf_live = wbf_next; rowf_live = rowf_next;
     }
+    (void)rowf_live;
   }
   if (tid == 64) tc5::tma_store_wait_all();
   tc5::fence_before_sync();
@@ -585,15 +620,19 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
 // (the same gradient as sum_rows D[r][f] Z_k[r][g] with Z_k = P^k X, because P is symmetric; it needs no
 // recomputation of the diffusion states).  A CTA owns the feature slice fh (FH columns of f) for the
 // whole kernel and keeps its K x [G x FH] accumulators in tensor memory across its tiles:
-//   * X^T (lanes = g, columns = tile rows, bf16x3 planes) is the A operand, stored into TMEM by the workers
+//   * X^T (lanes = g, columns = tile rows, fp16 hi/lo planes) is the A operand, stored into TMEM by the workers
 //     straight from x's native [B,G,N] layout (tcgen05.st);
-//   * V_k lives in shared memory as bf16x3 planes, in a ring of three buffers (tap k of a tile uses buffer
+//   * V_k lives in shared memory as fp16 planes, in a ring of three buffers (tap k of a tile uses buffer
 //     (base + k) % 3, so the next tile's V_0 can be written while the last taps still run); it is the MN-major
 //     B operand of both the dH product and the hop;
-//   * P (block-diagonal 0/1, exact in bf16) is double-buffered in shared memory (K-major A operand of the hop).
+//   * P (block-diagonal 0/1) is double-buffered in shared memory (K-major A operand of the hop).
 // One chain per tile: hop(k) -> [write-back(k) by the workers || dH(k) on the tensor core] -> hop(k+1) ...
+// The accumulators sum over MANY tiles, so the fp16 operand scales are launch-wide constants here: S_x from
+// max |x|, S_v from max |dY o act'(y)| over the whole batch (amax: a by-product of the dX kernel / a small
+// reduction kernel), V_k carried as V_k S_v 2^(-c k); accumulator k is unscaled by 2^(c k) / (S_x S_v) when it
+// is drained.  Sym-norm: Vhat_k = D^-1/2 V_k (Vhat_{k+1} = D^-1 A Vhat_k) against Xhat = D^1/2 X.
 // =====================================================================================================
-template <int G, int F, int FH>
+template <int G, int F, int FH, int NP>
 struct DhLayout {
   static constexpr int ROWS = 128;
   static constexpr int NFH = F / FH;
@@ -601,31 +640,35 @@ struct DhLayout {
   static constexpr int NCH = FH / 8;
   static constexpr int PW = ROWS * 16;
   static constexpr int PLANE = NCH * PW;
-  static constexpr int VBUF = 3 * PLANE;
+  static constexpr int VBUF = NP * PLANE;
   static constexpr int P_BYTES = (ROWS / 8) * PW;
   static constexpr int OFF_V = 0;
   static constexpr int OFF_P = OFF_V + 3 * VBUF;
   static constexpr int OFF_SP = OFF_P + 2 * P_BYTES;
-  static constexpr int OFF_DB = OFF_SP + 2 * ROWS * 8;
+  static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;
+  static constexpr int OFF_TAB = OFF_DEG + 2 * 2 * ROWS * 4;
+  static constexpr int OFF_DB = OFF_TAB + 3 * 128 * 4;
   static constexpr int OFF_BAR = OFF_DB + FH * 4;
   static constexpr int NBAR = 6;
   static constexpr int BYTES_MIN = OFF_BAR + NBAR * 8 + 16;
   static constexpr int BYTES = BYTES_MIN < 120 * 1024 ? 120 * 1024 : BYTES_MIN;   // one CTA per SM (TMEM is taken whole)
-  static constexpr int TM_X = 0;                     // 3 planes x 64 columns (128 rows, two per column)
-  static constexpr int TM_ACC = 192;                 // acc(k) at TM_ACC + k*FH, hop result at TM_ACC + K*FH
+  static constexpr int TM_X = 0;                     // NP planes x 64 columns (128 rows, two per column)
+  static constexpr int TM_ACC = NP * 64;             // acc(k) at TM_ACC + k*FH, hop result at TM_ACC + K*FH
   static_assert(FH % 32 == 0 && F % FH == 0 && CPT % 8 == 0, "feature slice");
   static_assert(G == 128 || G == 64 || G == 32, "G");
   static_assert(BYTES <= 227 * 1024, "shared memory");
 };
 
-template <int G, int F, int FH>
+template <int G, int F, int FH, int NP>
 __global__ void __launch_bounds__(kWideThreads, 1)
 tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
-  using L = DhLayout<G, F, FH>;
+  using L = DhLayout<G, F, FH, NP>;
   extern __shared__ __align__(128) unsigned char wsmem[];
   unsigned char* Vb = wsmem + L::OFF_V;
   unsigned char* Pb = wsmem + L::OFF_P;
   float2* sp_all = reinterpret_cast<float2*>(wsmem + L::OFF_SP);
+  int* sdeg = reinterpret_cast<int*>(wsmem + L::OFF_DEG);
+  float* dtab = reinterpret_cast<float*>(wsmem + L::OFF_TAB);
   float* dbs = reinterpret_cast<float*>(wsmem + L::OFF_DB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsmem + L::OFF_BAR);
   uint64_t* v_ready = bars;          // workers -> issuer: the next V buffer is written
@@ -640,6 +683,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
+  const bool norm = w.g.norm != 0;
   const int fh = blockIdx.x % L::NFH, part = blockIdx.x / L::NFH, nparts = gridDim.x / L::NFH;
   const int TM_HOP = L::TM_ACC + K * FH;
   // contiguous tile range per CTA group (see tc5_wide_kernel)
@@ -649,6 +693,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 
   for (int i = tid; i < 2 * L::P_BYTES / 16; i += kWideThreads) reinterpret_cast<uint4*>(Pb)[i] = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < FH; i += kWideThreads) dbs[i] = 0.f;
+  fill_degree_tables(dtab, tid, kWideThreads);
   if (tid == 0) {
     tc5::mbar_init(v_ready, kWorkerWarps);
     tc5::mbar_init(hop_done, 1);
@@ -668,27 +713,20 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   if (warp == 0) {
     // =========================== MMA issuer (one elected thread) ===============================
     if (tc5::elect_one()) {
-      constexpr uint32_t kIdesc = tc5::idesc_bf16(128, FH, 0, 1);   // B = V planes, MN-major
+      constexpr uint32_t kIdesc = tc5::idesc_f16(128, FH, 0, 1);   // B = V planes, MN-major
       const uint32_t v_addr = tc5::smem_u32(Vb), p_addr = tc5::smem_u32(Pb);
       uint32_t par_vr = 0, par_v0 = 0, par_pr = 0, par_xr = 0;
       const int ksteps = (w.gpc * N + 15) >> 4;
       int it = 0, vbase = 0;
-      int nstamp = 0;
-      const bool dbg = w.dbg != nullptr && blockIdx.x == 0;
-#define GFC_DSTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
-        GFC_DSTAMP(300);
         tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
-        GFC_DSTAMP(301);
         const bool fresh = (it % w.flush_every) == 0;   // the workers drained the accumulators before x_ready
         const uint32_t pa = p_addr + (it & 1) * L::P_BYTES;
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
-          GFC_DSTAMP(310);
           if (k == 0) { tc5::mbar_wait(v0_ready, par_v0); par_v0 ^= 1; }
           else { tc5::mbar_wait(v_ready, par_vr); par_vr ^= 1; }
           tc5::fence_after_sync();
-          GFC_DSTAMP(311);
           const uint32_t vs = v_addr + ((vbase + k) % 3) * L::VBUF;
           if (k + 1 < K) {
             // hop: D_hop = P * V_k
@@ -697,32 +735,28 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
             for (int j = 0; j < ksteps; ++j) {
               const uint64_t da = make_desc(pa + j * 2 * L::PW, L::PW, 128);
 #pragma unroll
-              for (int pl = 0; pl < 3; ++pl) {
+              for (int pl = 0; pl < NP; ++pl) {
                 tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdesc, acc);
                 acc = 1;
               }
             }
             tc5::mma_commit(hop_done);
-            GFC_DSTAMP(312);
           }
-          if (k == 0) { tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1; tc5::fence_after_sync(); GFC_DSTAMP(313); }
-          // dH: acc(k)[g][f] += X^T[g][rows] * V_k[rows][f]   (6-term bf16x3 product, A from tensor memory)
+          if (k == 0) { tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1; tc5::fence_after_sync(); }
+          // dH: acc(k)[g][f] += X^T[g][rows] * V_k[rows][f]   (hi hi + hi lo + lo hi, A from tensor memory)
           const uint32_t d_acc = tmem + L::TM_ACC + k * FH;
 #pragma unroll 1
           for (int j = 0; j < ksteps; ++j) {
             const uint32_t xa = tmem + L::TM_X + j * 8;
             const uint64_t b0 = make_desc(vs + j * 256, 128, L::PW);
-            const uint64_t b1 = make_desc(vs + L::PLANE + j * 256, 128, L::PW);
-            const uint64_t b2 = make_desc(vs + 2 * L::PLANE + j * 256, 128, L::PW);
             const uint32_t first = (fresh && j == 0) ? 0u : 1u;
             tc5::mma_bf16_ts(d_acc, xa, b0, kIdesc, first);
-            tc5::mma_bf16_ts(d_acc, xa, b1, kIdesc, 1u);
-            tc5::mma_bf16_ts(d_acc, xa + 64, b0, kIdesc, 1u);
-            tc5::mma_bf16_ts(d_acc, xa + 64, b1, kIdesc, 1u);
-            tc5::mma_bf16_ts(d_acc, xa, b2, kIdesc, 1u);
-            tc5::mma_bf16_ts(d_acc, xa + 128, b0, kIdesc, 1u);
+            if (NP == 2) {
+              const uint64_t b1 = make_desc(vs + L::PLANE + j * 256, 128, L::PW);
+              tc5::mma_bf16_ts(d_acc, xa, b1, kIdesc, 1u);
+              tc5::mma_bf16_ts(d_acc, xa + 64, b0, kIdesc, 1u);
+            }
           }
-          GFC_DSTAMP(314);
         }
         tc5::mma_commit(item_done);
         vbase = (vbase + K) % 3;
@@ -745,9 +779,13 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};     // column sums of V_0 (columns 4*(lane % PPR) .. +3)
     float2 mypos = make_float2(0.f, 0.f);
     uint32_t par_hd = 0, par_id = 0;
-    int nstamp = 0;
-    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
-#define GFC_ESTAMP(tag) do { if (dbg && nstamp < 1000) { w.dbg[2048 + 2 * nstamp] = clock64(); w.dbg[2048 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+    // launch-wide operand scales (powers of two) from the batch maxima
+    float inv_sx, inv_sv;
+    const int xtop = norm ? kWideTop - 4 : kWideTop;   // Xhat = D^1/2 X grows by < 2^3.5 (N <= 128)
+    const float s_x = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax)), xtop, &inv_sx);
+    const float s_v = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax + 1)), kWideTop, &inv_sv);
+    const float hop_down = __uint_as_float((uint32_t)(127 - w.cshift) << 23);   // 2^-c
+    float wbf_live = hop_down, wbf_next = hop_down;
 
     auto publish = [&](uint64_t* bar) {
       tc5::fence_proxy_async();
@@ -759,7 +797,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
       if (wt < 128)
-        mypos = (wt < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.pos) + (size_t)b0 * N + wt) : make_float2(0.f, 0.f);
+        mypos = (wt < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wt) : make_float2(0.f, 0.f);
     };
     auto prefetch_tile = [&](int tile) {
       const int b0 = tile * w.gpc;
@@ -774,7 +812,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     };
     // X^T operand: x[(b0 + j), g, n] -> TMEM lane g, column (tile row / 2).  The 16x256b store shape lets a
     // thread own 4 consecutive tile rows (one float4 of x) of the feature lanes  16 h + t/4  and  16 h + t/4 + 8:
-    // a warp load instruction then touches 8 lines instead of 32.  xt[16 P + 8 e + 4 u + i]: part P = 2 h + e
+    // a warp load instruction then touches 8 lines instead of 32.  xt[16 P + 8 u + 4 gs + i]: part P = 2 h + e
     // (e selects rho in {2e, 2e+1}), u = rho & 1 ... see store_xt for the register order of the store.
     auto load_xt_part = [&](int tile, auto part_c) {
       constexpr int PART = decltype(part_c)::value;
@@ -808,30 +846,43 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       else if (slot == 2) load_xt_part(tile, std::integral_constant<int, 2>{});
       else load_xt_part(tile, std::integral_constant<int, 3>{});
     };
-    auto store_xt = [&]() {
+    auto store_xt = [&](int pbuf) {
       if (q * 32 < G) {   // warp-uniform: this quadrant holds real feature lanes
+        // row factors of the 16 tile rows this thread touches: S_x (x d^1/2 for sym-norm); row = hf*64 + 16 rho + 4 (lane&3) + i
+        float rf[4][4];
+#pragma unroll
+        for (int rho = 0; rho < 4; ++rho) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float f0 = s_x;
+            if (norm) {
+              const int row = hf * 64 + 16 * rho + 4 * (lane & 3) + i;
+              f0 *= dtab[256 + sdeg[(pbuf * 2 + 0) * L::ROWS + row] + sdeg[(pbuf * 2 + 1) * L::ROWS + row]];
+            }
+            rf[rho][i] = f0;
+          }
+        }
 #pragma unroll
         for (int h16 = 0; h16 < 2; ++h16) {
-          uint32_t p0[16], p1[16], p2[16];
+          uint32_t p0[16], p1[16];
 #pragma unroll
           for (int rho = 0; rho < 4; ++rho) {
 #pragma unroll
             for (int gs = 0; gs < 2; ++gs) {
               const float* src = &xt[16 * (2 * h16 + (rho >> 1)) + 8 * (rho & 1) + 4 * gs];
-              uint32_t a0, a1, a2, b0, b1, b2, c0, c1, c2, d0, d1, d2;
-              tc5::split_bf16x3(src[0], a0, a1, a2);
-              tc5::split_bf16x3(src[1], b0, b1, b2);
-              tc5::split_bf16x3(src[2], c0, c1, c2);
-              tc5::split_bf16x3(src[3], d0, d1, d2);
-              p0[4 * rho + 2 * gs] = tc5::pack_bf16_hi(a0, b0); p0[4 * rho + 2 * gs + 1] = tc5::pack_bf16_hi(c0, d0);
-              p1[4 * rho + 2 * gs] = tc5::pack_bf16_hi(a1, b1); p1[4 * rho + 2 * gs + 1] = tc5::pack_bf16_hi(c1, d1);
-              p2[4 * rho + 2 * gs] = tc5::pack_bf16_hi(a2, b2); p2[4 * rho + 2 * gs + 1] = tc5::pack_bf16_hi(c2, d2);
+              const float a = src[0] * rf[rho][0], b = src[1] * rf[rho][1], c = src[2] * rf[rho][2], d = src[3] * rf[rho][3];
+              if (NP == 2) {
+                tc5::split_f16x2(a, b, p0[4 * rho + 2 * gs], p1[4 * rho + 2 * gs]);
+                tc5::split_f16x2(c, d, p0[4 * rho + 2 * gs + 1], p1[4 * rho + 2 * gs + 1]);
+              } else {
+                p0[4 * rho + 2 * gs] = tc5::pack_f16x2(a, b);
+                p0[4 * rho + 2 * gs + 1] = tc5::pack_f16x2(c, d);
+              }
             }
           }
           const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * h16) << 16) + L::TM_X + hf * 32;
           tc5::tmem_st_16x256b_x4(ta, p0);
-          tc5::tmem_st_16x256b_x4(ta + 64, p1);
-          tc5::tmem_st_16x256b_x4(ta + 128, p2);
+          if (NP == 2) tc5::tmem_st_16x256b_x4(ta + 64, p1);
         }
         tc5::tmem_st_wait();
       }
@@ -864,7 +915,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
       }
     };
-    auto store_v0 = [&](unsigned char* vbuf) {
+    auto store_v0 = [&](unsigned char* vbuf, int pbuf) {
       const int pi = lane % PPR;
       const bool odd = pi & 1;
 #pragma unroll
@@ -881,14 +932,17 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
+        const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+        float f0 = s_v;
+        if (norm) f0 *= dtab[sdeg[(pbuf * 2 + 0) * L::ROWS + row] + sdeg[(pbuf * 2 + 1) * L::ROWS + row]];
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { v[e] = odd ? rcv[e] : own[e]; v[4 + e] = odd ? own[e] : rcv[e]; }
-        const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
-        store_chunk3(vbuf + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
+        for (int e = 0; e < 4; ++e) { v[e] = (odd ? rcv[e] : own[e]) * f0; v[4 + e] = (odd ? own[e] : rcv[e]) * f0; }
+        store_chunk_f16<NP>(vbuf + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
       }
     };
     // P[r][c] (smem, K-major A operand): chunks t0..t1-1 of the 8 this thread owns
+    int degcnt = 0;
     auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
       const float2* sp = sp_all + pbuf * L::ROWS;
       unsigned char* pb = Pb + pbuf * L::P_BYTES;
@@ -900,24 +954,30 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         for (int t = t0; t < t1; ++t) {
           const int qc = 2 * t + hf;
           if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
-            uint32_t e[8];
-            adjacency8(e, sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.thr, w.thr_lo, w.thr_hi);
+            const uint32_t bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+            degcnt += __popc(bits);
             *reinterpret_cast<uint4*>(pb + qc * L::PW + r * 16) =
-                make_uint4(tc5::pack_bf16_hi(e[0], e[1]), tc5::pack_bf16_hi(e[2], e[3]), tc5::pack_bf16_hi(e[4], e[5]),
-                           tc5::pack_bf16_hi(e[6], e[7]));
+                make_uint4(p_word(bits, 0), p_word(bits, 2), p_word(bits, 4), p_word(bits, 6));
           }
         }
       }
+    };
+    auto publish_p = [&](int pbuf) {
+      sdeg[(pbuf * 2 + hf) * L::ROWS + r] = degcnt;
+      degcnt = 0;
+      publish(p_ready);
     };
     // Drain the TMEM accumulators into this CTA group's partial buffer (zeroed by the host, L2-resident, every
     // address owned by exactly one thread of one CTA) with fire-and-forget reductions: no read latency, and the
     // per-address order is this thread's program order, so the result is deterministic.  The tensor core's fp32
     // accumulation truncates, so the error grows with the number of MMAs chained into one accumulator;
-    // draining every `flush_every` tiles bounds it.
+    // draining every `flush_every` tiles bounds it.  Accumulator k is in units S_x S_v 2^(-c k).
     float* dst = w.dHp + (size_t)part * F * K * G;
     auto flush = [&]() {
       tc5::fence_after_sync();
       if (q * 32 < G) {
+        float unscale = inv_sx * inv_sv;
+        const float up = __uint_as_float((uint32_t)(127 + w.cshift) << 23);   // 2^c
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
 #pragma unroll 1
@@ -929,9 +989,10 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
             if (g_ok) {
               float* d0 = dst + (size_t)(fh * FH + col) * K * G + k * G + r;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) red_add_f32(d0 + (size_t)i * K * G, __uint_as_float(v[i]));
+              for (int i = 0; i < 8; ++i) red_add_f32(d0 + (size_t)i * K * G, __uint_as_float(v[i]) * unscale);
             }
           }
+          unscale *= up;
         }
       }
       tc5::fence_before_sync();
@@ -940,6 +1001,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     // One leading iteration (it == -1) prepares the first tile; afterwards iteration `it` serves tile `tile`
     // (write-backs) and prepares `next`.
     int tile = t_begin, next = t_begin, it = -1, vbase = 0, n_items = 0;
+    (void)tile;
     if (next < t_end) load_pos(next);
     while (true) {
       const bool live = it >= 0;
@@ -965,10 +1027,8 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         // next tile's V_0 pieces: requested two write-backs ahead of their use so that the (long) memory latency
         // overlaps the remaining taps of the live tile
         if (has_next && !v0_loaded && k + 2 >= nwb) { load_v0(next); v0_loaded = true; }
-        GFC_ESTAMP(400);
         tc5::mbar_wait(hop_done, par_hd); par_hd ^= 1;
         tc5::fence_after_sync();
-        GFC_ESTAMP(401);
         unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (hf * (L::CPT / 8)) * L::PW + r * 16;
         const uint32_t taddr = tm_lane + TM_HOP + hf * L::CPT;
 #pragma unroll 1
@@ -978,49 +1038,47 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
           tc5::tmem_ld_wait();
           float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]);
-          store_chunk3(base + c * L::PW, L::PLANE, f);
+          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * wbf_live;
+          store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
         }
         publish(v_ready);
-        GFC_ESTAMP(402);
         if (has_next) {
           if (K > 1 && k < 2) {
             build_p_part(next, pbuf, 4 * k, 4 * k + 4);
             if (k == 1 || nwb == 1) {
               if (nwb == 1) build_p_part(next, pbuf, 4, 8);
-              publish(p_ready); p_done = true;
+              publish_p(pbuf); p_done = true;
             }
           }
           if (xt_slot < 2) load_xt_slot(next, xt_slot++);   // half of X^T early; the rest once V_0's registers are free
         }
-        GFC_ESTAMP(403);
       }
       if (has_next) {
-        if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 8); publish(p_ready); }
+        if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 8); publish_p(pbuf); }
+        if (norm) {   // every thread's partial degrees of `next` are visible after this barrier
+          worker_bar();
+          const int d = sdeg[(pbuf * 2 + 0) * L::ROWS + r] + sdeg[(pbuf * 2 + 1) * L::ROWS + r];
+          wbf_next = hop_down * dtab[128 + d];
+        }
         // V_0 of the next tile goes into the ring buffer after the live tile's last one (free: its last reader
         // was tap K-3 of the live tile, which completed before the hop result of tap K-2 was signalled)
-        GFC_ESTAMP(404);
         if (!v0_loaded) load_v0(next);
-        GFC_ESTAMP(405);
-        store_v0(Vb + ((vbase + (live ? K : 0)) % 3) * L::VBUF);
+        store_v0(Vb + ((vbase + (live ? K : 0)) % 3) * L::VBUF, pbuf);
         publish(v0_ready);
-        GFC_ESTAMP(406);
         while (xt_slot < 4) load_xt_slot(next, xt_slot++);   // latency hides behind the last tap's MMAs / the drain
       }
       if (live) {
         tc5::mbar_wait(item_done, par_id); par_id ^= 1;   // every dH product of the live tile has completed
-        GFC_ESTAMP(407);
         ++n_items;
         if (!has_next || (n_items % w.flush_every) == 0) flush();
-        GFC_ESTAMP(408);
         vbase = (vbase + K) % 3;
       }
-      if (has_next) store_xt();
-      GFC_ESTAMP(409);
+      if (has_next) store_xt(pbuf);
       if (!has_next) break;
       tile = next;
       next += 1;
       ++it;
+      wbf_live = wbf_next;
     }
     if (w.dbp) {
 #pragma unroll
@@ -1034,46 +1092,109 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   if (warp == 1) tc5::tmem_dealloc(tmem, 512);
 }
 
-// ---- tap packing: bf16x3 planes in ring-stage order ----------------------------------------------
+// ---- tap packing: fp16 planes in ring-stage order, pre-scaled --------------------------------------
 // stage u = k * (CIN/16) + c16 holds channels [16 c16, 16 c16 + 16) of tap k:
 //   byte(plane, cc, n, e) = plane*COUT*32 + cc*COUT*16 + n*16 + e*2   with channel = 16 c16 + 8 cc + e
 // MODE 0: B[n = f][channel = g] = h[f][k*G + g];  MODE 1: B[n = g][channel = f] = h[f][k*G + g]
+// value stored = h t_h 2^(c k), t_h the power of two that puts max |h| 2^(c (K-1)) just below 2^14 (every CTA
+// recomputes the maximum: 64 K floats from L2).  Header float[0] = 1 / t_h.
 __global__ void __launch_bounds__(256)
-wide_pack_taps_kernel(const float* __restrict__ h, int G, int F, int K, int mode, uint16_t* __restrict__ out) {
+wide_pack_taps_kernel(const float* __restrict__ h, int G, int F, int K, int mode, int cshift, int planes,
+                      unsigned char* __restrict__ outb) {
+  __shared__ uint32_t swmax[8];
+  const int total = K * G * F;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) m = fmaxf(m, fabsf(__ldg(h + i)));
+  const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) swmax[threadIdx.x >> 5] = mw;
+  __syncthreads();
+  uint32_t mt = swmax[0];
+  for (int i = 1; i < 8; ++i) mt = max(mt, swmax[i]);
+  float inv_th;
+  int top = kWideTop - cshift * (K - 1);
+  if (top < -8) top = -8;                      // beyond the guaranteed range the small taps lose low bits, nothing overflows
+  const float t_h = tc5::pow2_scale(mt, top, &inv_th);
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<float*>(outb)[0] = inv_th;
+  uint16_t* out = reinterpret_cast<uint16_t*>(outb + kPackHeader);
   const int CIN = mode == 0 ? G : F, COUT = mode == 0 ? F : G;
-  const int total = K * CIN * COUT;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int k = idx / (CIN * COUT), rem = idx - k * CIN * COUT;
     const int ch = rem / COUT, n = rem - ch * COUT;
     const int f = mode == 0 ? n : ch, g = mode == 0 ? ch : n;
-    const float v = h[(size_t)f * K * G + k * G + g];
-    uint32_t p0, p1, p2;
-    tc5::split_bf16x3(v, p0, p1, p2);
+    const float v = h[(size_t)f * K * G + k * G + g] * t_h * __uint_as_float((uint32_t)(127 + cshift * k) << 23);
+    const __half hi = __float2half_rn(v);
     const int c16 = ch >> 4, cc = (ch >> 3) & 1, e = ch & 7;
-    const size_t stage = (size_t)(k * (CIN / 16) + c16) * (COUT * 48);   // in uint16 units (96 B * COUT / 2)
+    const size_t stage = (size_t)(k * (CIN / 16) + c16) * (COUT * 16 * planes);   // in uint16 units
     const size_t o = stage + (size_t)cc * COUT * 8 + (size_t)n * 8 + e;
-    out[o] = (uint16_t)(p0 >> 16);
-    out[o + (size_t)COUT * 16] = (uint16_t)(p1 >> 16);
-    out[o + (size_t)COUT * 32] = (uint16_t)(p2 >> 16);
+    out[o] = __half_as_ushort(hi);
+    if (planes == 2) out[o + (size_t)COUT * 16] = __half_as_ushort(__float2half_rn(v - __half2float(hi)));
   }
 }
 
-int launch_wide_pack(const float* h, int G, int F, int K, int mode, uint16_t* out, cudaStream_t st) {
+int launch_wide_pack(const float* h, int G, int F, int K, int mode, int cshift, int planes, unsigned char* out,
+                     cudaStream_t st) {
   const int total = K * G * F;
-  int grid = ceil_div(total, 256);
-  if (grid > 592) grid = 592;
-  wide_pack_taps_kernel<<<grid, 256, 0, st>>>(h, G, F, K, mode, out);
+  int grid = ceil_div(total, 256 * 4);
+  if (grid > 148) grid = 148;
+  wide_pack_taps_kernel<<<grid, 256, 0, st>>>(h, G, F, K, mode, cshift, planes, out);
   GFC_LAUNCH_CHECK("wide_pack_taps_kernel");
   return GFC_OK;
+}
+
+// batch maxima for the launch-wide operand scales of the dH kernel
+__global__ void __launch_bounds__(512)
+wide_absmax_kernel(const float* __restrict__ a, size_t n_a, const float* __restrict__ b, size_t n_b, float bscale,
+                   float* __restrict__ amax) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+  const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  for (int which = 0; which < 2; ++which) {
+    const float* p = which ? b : a;
+    const size_t n = which ? n_b : n_a;
+    if (!p) continue;
+    float m = 0.f;
+    const bool vec = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
+    for (size_t i = i0; i < n; i += stride) {
+      if (vec && i + 4 <= n) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p + i));
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      } else {
+        for (size_t j = i; j < n && j < i + 4; ++j) m = fmaxf(m, fabsf(__ldg(p + j)));
+      }
+    }
+    if (which) m *= bscale;
+    const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0 && mw) atomicMax(reinterpret_cast<unsigned int*>(amax) + which, mw);
+  }
+}
+
+int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax, cudaStream_t st) {
+  if (!a && !b) return GFC_OK;
+  DeviceInfo di;
+  int rc = get_device_info(&di);
+  if (rc) return rc;
+  const size_t n = n_a > n_b ? n_a : n_b;
+  size_t want = (n + 2047) / 2048;
+  int grid = (int)(want < (size_t)di.sm_count * 4 ? (want ? want : 1) : (size_t)di.sm_count * 4);
+  wide_absmax_kernel<<<grid, 512, 0, st>>>(a, n_a, b, n_b, bscale, amax);
+  GFC_LAUNCH_CHECK("wide_absmax_kernel");
+  return GFC_OK;
+}
+
+int wide_cshift(int N, int norm) {
+  if (norm) return 0;               // row-normalised form: |D^-1 A W| <= max |W|
+  int c = 0;
+  while ((1 << c) < N - 1) ++c;     // a node has at most N-1 neighbours: |P W| <= (N-1) max |W|
+  return c;
 }
 
 bool wide_supported(int N, int G, int F, int K, int mode) {
   const int CIN = mode == 0 ? G : F, COUT = mode == 0 ? F : G;
   if (N < 1 || N > 128 || K < 1 || K > 16) return false;
+  if (wide_cshift(N, 0) * (K - 1) > 21) return false;   // fp16 headroom: beyond it the guaranteed 1e-5 is lost
   return (CIN == 128 || CIN == 64) && (COUT == 128 || COUT == 64);
 }
 
-size_t wide_pack_bytes(int G, int F, int K) { return align_up((size_t)K * G * F * 6, 256); }
+size_t wide_pack_bytes(int G, int F, int K) { return align_up((size_t)kPackHeader + (size_t)K * G * F * 4, 256); }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 static int encode_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
@@ -1097,19 +1218,17 @@ static int encode_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uin
   return GFC_OK;
 }
 
-template <int CIN, int COUT, int MODE>
+template <int CIN, int COUT, int MODE, int NP>
 static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
-  using L = WideLayout<CIN, COUT>;
+  using L = WideLayout<CIN, COUT, NP>;
   WideArgs a = a0;
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
-  a.tma_out = 0;
   if (MODE != 1) {   // y viewed as [B*N rows, COUT cols]; one box = [gpc*N rows x 32 cols]
     int rc = encode_tmap_2d(&tmap, a.out, COUT, (uint64_t)a.B * a.N, 32, (uint32_t)(a.gpc * a.N));
     if (rc) return rc;
-    a.tma_out = 1;
   }
-  auto kern = tc5_wide_kernel<CIN, COUT, MODE>;
+  auto kern = tc5_wide_kernel<CIN, COUT, MODE, NP>;
   GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -1120,43 +1239,45 @@ static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   return GFC_OK;
 }
 
-int launch_wide(const WideArgs& a0, int G, int F, int mode, cudaStream_t st) {
+int launch_wide(const WideArgs& a0, int G, int F, int mode, int planes, cudaStream_t st) {
   WideArgs a = a0;
   a.no_prefetch = g_wide_no_prefetch;
   a.gpc = 128 / a.N;
   if (a.gpc > a.B) a.gpc = a.B;
   a.ntiles = ceil_div(a.B, a.gpc);
+  if (a.K == 1) a.g.norm = 0;   // no hop: the GSO is never used
   const int CIN = mode != 1 ? G : F, COUT = mode != 1 ? F : G;
-#define GFC_WIDE_CASE(ci, co)                                                   \
-  if (CIN == ci && COUT == co)                                                  \
-    return mode == 0 ? launch_wide_t<ci, co, 0>(a, st)                          \
-         : mode == 1 ? launch_wide_t<ci, co, 1>(a, st) : launch_wide_t<ci, co, 2>(a, st);
-  GFC_WIDE_CASE(128, 128)
-  GFC_WIDE_CASE(64, 64)
-  GFC_WIDE_CASE(128, 64)
-  GFC_WIDE_CASE(64, 128)
+#define GFC_WIDE_CASE(ci, co, np)                                                     \
+  if (CIN == ci && COUT == co && planes == np)                                        \
+    return mode == 0 ? launch_wide_t<ci, co, 0, np>(a, st)                            \
+         : mode == 1 ? launch_wide_t<ci, co, 1, np>(a, st) : launch_wide_t<ci, co, 2, np>(a, st);
+  GFC_WIDE_CASE(128, 128, 2)
+  GFC_WIDE_CASE(64, 64, 2)
+  GFC_WIDE_CASE(128, 64, 2)
+  GFC_WIDE_CASE(64, 128, 2)
+  GFC_WIDE_CASE(128, 128, 1)
 #undef GFC_WIDE_CASE
-  set_error("launch_wide: unsupported channel counts %d -> %d", CIN, COUT);
+  set_error("launch_wide: unsupported channel counts %d -> %d (planes %d)", CIN, COUT, planes);
   return GFC_ERR_UNSUPPORTED;
 }
 
 
-template <int G, int F, int FH>
-static int launch_wide_dh_t(const WideDhArgs& a0, int* nparts_out, cudaStream_t st) {
-  using L = DhLayout<G, F, FH>;
+template <int G, int F, int FH, int NP>
+static int launch_wide_dh_t(const WideDhArgs& a0, cudaStream_t st) {
+  using L = DhLayout<G, F, FH, NP>;
   WideDhArgs a = a0;
-  auto kern = tc5_wide_dh_kernel<G, F, FH>;
+  auto kern = tc5_wide_dh_kernel<G, F, FH, NP>;
   GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
   kern<<<a.nparts * L::NFH, kWideThreads, L::BYTES, st>>>(a);
   GFC_LAUNCH_CHECK("tc5_wide_dh_kernel");
-  if (nparts_out) *nparts_out = a.nparts;
   return GFC_OK;
 }
 
-// feature slice: the K+1 [128 x FH] fp32 regions (K accumulators + the hop result) share 320 TMEM columns
+// feature slice: the K+1 [128 x FH] fp32 regions (K accumulators + the hop result) share the 384 TMEM columns
+// next to the two X^T planes
 static int dh_slice(int F, int K) {
-  if ((K + 1) * 64 <= 320 && F % 64 == 0) return 64;
-  if ((K + 1) * 32 <= 320 && F % 32 == 0) return 32;
+  if ((K + 1) * 64 <= 384 && F % 64 == 0) return 64;
+  if ((K + 1) * 32 <= 384 && F % 32 == 0) return 32;
   return 0;
 }
 
@@ -1164,6 +1285,7 @@ bool wide_dh_supported(int N, int G, int F, int K) {
   if (N < 1 || N > 128 || K < 1) return false;
   if (!(G == 128 || G == 64)) return false;
   if (!(F == 128 || F == 64)) return false;
+  if (wide_cshift(N, 0) * (K - 1) > 21) return false;
   return dh_slice(F, K) != 0;
 }
 
@@ -1181,7 +1303,7 @@ int wide_dh_nparts(int B, int N, int F, int K) {
   return np;
 }
 
-int launch_wide_dh(const WideDhArgs& a0, int G, int F, cudaStream_t st) {
+int launch_wide_dh(const WideDhArgs& a0, int G, int F, int planes, cudaStream_t st) {
   WideDhArgs a = a0;
   a.gpc = 128 / a.N;
   if (a.gpc > a.B) a.gpc = a.B;
@@ -1189,18 +1311,20 @@ int launch_wide_dh(const WideDhArgs& a0, int G, int F, cudaStream_t st) {
   a.nparts = wide_dh_nparts(a.B, a.N, F, a.K);
   if (a.flush_every <= 0) a.flush_every = g_wide_flush_every;
   a.no_prefetch = g_wide_no_prefetch;
+  if (a.K == 1) a.g.norm = 0;
   const int fhs = dh_slice(F, a.K);
-#define GFC_DH_CASE(g, f, s) if (G == g && F == f && fhs == s) return launch_wide_dh_t<g, f, s>(a, nullptr, st);
-  GFC_DH_CASE(128, 128, 64)
-  GFC_DH_CASE(128, 128, 32)
-  GFC_DH_CASE(64, 64, 64)
-  GFC_DH_CASE(64, 64, 32)
-  GFC_DH_CASE(128, 64, 64)
-  GFC_DH_CASE(128, 64, 32)
-  GFC_DH_CASE(64, 128, 64)
-  GFC_DH_CASE(64, 128, 32)
+#define GFC_DH_CASE(g, f, s, np) if (G == g && F == f && fhs == s && planes == np) return launch_wide_dh_t<g, f, s, np>(a, st);
+  GFC_DH_CASE(128, 128, 64, 2)
+  GFC_DH_CASE(128, 128, 32, 2)
+  GFC_DH_CASE(64, 64, 64, 2)
+  GFC_DH_CASE(64, 64, 32, 2)
+  GFC_DH_CASE(128, 64, 64, 2)
+  GFC_DH_CASE(128, 64, 32, 2)
+  GFC_DH_CASE(64, 128, 64, 2)
+  GFC_DH_CASE(64, 128, 32, 2)
+  GFC_DH_CASE(128, 128, 64, 1)
 #undef GFC_DH_CASE
-  set_error("launch_wide_dh: unsupported shape G=%d F=%d K=%d", G, F, a.K);
+  set_error("launch_wide_dh: unsupported shape G=%d F=%d K=%d (planes %d)", G, F, a.K, planes);
   return GFC_ERR_UNSUPPORTED;
 }
 

@@ -4,53 +4,71 @@
 
 namespace gfc {
 
-struct WideArgs {
-  const float* pos;        // [B,N,2]
+// Graph source of a wide kernel: positions (the GSO is rebuilt on chip, bit-exact radius rule) or a dense
+// per-graph GSO S [B,N,N] read from HBM (the reference's own addGSO call, graphML.py:2449-2456).
+struct WideGraph {
+  const float* pos;        // [B,N,2] or null
   double thr;              // squared-distance threshold, fp64 rule (gfc_gso.cu)
   float thr_lo, thr_hi;    // fp32 screening band
+  int norm;                // positions: D^-1/2 A D^-1/2 (multirobotsim_dcenlocal.py:306-315) applied as row scalings
+  const float* S;          // dense [B,N,N] fp32 or null (then `pos`)
+  long long s_bstride;     // floats between consecutive graphs of S (0: one GSO shared by the whole batch)
+  int s_transpose;         // dense: the hop uses S^T (forward: z_{k+1} = z_k S) or S (backward)
+  const float* s_bound;    // dense: device float >= max row/column abs sum of any S_b (growth bound per hop)
+};
+
+struct WideArgs {
+  WideGraph g;
   const float* in;         // MODE 0: x [B,G,N];  MODE 1: dY [B,N,F];  MODE 2: x [B,N,G]
   const float* yout;       // MODE 1: forward output [B,N,F] (activation mask) or null
-  const uint16_t* hpack;   // taps as bf16x3 planes in ring-stage order (wide_pack_taps_kernel)
+  const unsigned char* hpack;  // packed taps: 256-byte header {1/t_h, ...} + fp16 planes in ring-stage order
   const float* bias;       // MODE 0: [F] or null
   float* out;              // MODE 0: y [B,N,F];  MODE 1: dX [B,G,N]
   float* d_out;            // MODE 1, optional: dY o act'(y) [B,N,F] written for the dH kernel (else null)
+  float* amax;             // optional device float[2]: running max |x| (MODE 0/2 -> [0]) / max |dY o act'| (MODE 1 -> [1])
   int B, N, K;
+  int cshift;              // per-hop headroom bits: W_k is carried as W_k 2^(-cshift k), the taps as H_k 2^(+cshift k)
   int gpc, ntiles;         // filled by launch_wide
   int act;
   float slope;
   int no_prefetch;         // experiment: skip the L2 bulk prefetch
-  int tma_out;             // filled by launch_wide: the y tile leaves through the TMA store engine
-  long long* dbg;          // optional clock stamps of CTA 0 (issuer at [0..), worker warp 2 at [2048..)), else null
 };
 
 struct WideDhArgs {
-  const float* pos;
-  double thr;
-  float thr_lo, thr_hi;
+  WideGraph g;
   const float* x;          // [B,G,N]
   const float* dY;         // [B,N,F]
   const float* yout;       // [B,N,F] forward output (activation mask) or null
   const float* dpre;       // optional [B,N,F]: dY o act'(y) already formed by the dX kernel (then dY / yout are not read)
-  float* dHp;              // [nparts][F*K*G] per-CTA-group partial gradients (every element written)
+  const float* amax;       // device float[2]: {max |x|, max |dY o act'|} over the WHOLE batch (launch-wide operand scales)
+  float* dHp;              // [nparts][F*K*G] per-CTA-group partial gradients (zeroed by the caller, accumulated with red.add)
   float* dbp;              // [nparts][F] or null
   int B, N, K;
+  int cshift;
   int gpc, ntiles, nparts; // filled by launch_wide_dh
   int flush_every;         // tiles chained into the TMEM accumulators between drains (0 = default)
-  int no_prefetch;         // experiment: skip the L2 bulk prefetch
-  long long* dbg;          // optional clock stamps of CTA 0
+  int no_prefetch;
   int act;
   float slope;
 };
 extern int g_wide_flush_every;
 extern int g_wide_no_prefetch;
+
+// per-hop headroom (bits) of the fp16 operand scaling for an N-node 0/1 GSO (0 for the row-normalised form), and
+// whether (N, K) keeps the guaranteed fp32-class accuracy (cshift * (K-1) <= 21)
+int wide_cshift(int N, int norm);
 bool wide_dh_supported(int N, int G, int F, int K);
 int wide_dh_nparts(int B, int N, int F, int K);   // number of partial buffers launch_wide_dh writes
-int launch_wide_dh(const WideDhArgs& a, int G, int F, cudaStream_t st);
+int launch_wide_dh(const WideDhArgs& a, int G, int F, int planes, cudaStream_t st);
 
 // mode 0 = forward, 1 = backward dX, 2 = forward with node-major input x [B,N,G] (launch_wide only; pack / support as mode 0)
 bool wide_supported(int N, int G, int F, int K, int mode);
 size_t wide_pack_bytes(int G, int F, int K);
-int launch_wide_pack(const float* h, int G, int F, int K, int mode, uint16_t* out, cudaStream_t st);
-int launch_wide(const WideArgs& a, int G, int F, int mode, cudaStream_t st);
+// taps -> fp16 planes (hi [, lo]) in ring-stage order, scaled by t_h 2^(cshift k); header[0] = 1 / t_h
+int launch_wide_pack(const float* h, int G, int F, int K, int mode, int cshift, int planes, unsigned char* out,
+                     cudaStream_t st);
+int launch_wide(const WideArgs& a, int G, int F, int mode, int planes, cudaStream_t st);
+// amax[0] = max |a| (n_a floats), amax[1] = max |b| * bscale (n_b floats); either pointer may be null (slot left as is)
+int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax, cudaStream_t st);
 
 }  // namespace gfc

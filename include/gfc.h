@@ -64,7 +64,9 @@ enum { GFC_ACT_NONE = 0, GFC_ACT_RELU = 1, GFC_ACT_LEAKY_RELU = 2 };
 /* arithmetic of the tap contraction (the diffusion hops are always fp32 FMA)  */
 enum {
   GFC_PREC_FP32_3XTF32 = 0, /* tensor cores, hi/lo split, fp32-equivalent (<=1e-5) */
-  GFC_PREC_TF32 = 1         /* single pass tf32, looser bound (~1e-3), opt-in       */
+  GFC_PREC_TF32 = 1,        /* single pass tf32, looser bound (~1e-3), opt-in       */
+  GFC_PREC_F16 = 2          /* single fp16 plane on the tcgen05 wide path (1 MMA per product, stated bound 2e-3);
+                               shapes outside that path run as GFC_PREC_TF32         */
 };
 
 int gfc_version(void);
