@@ -267,7 +267,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       WideArgs wa{};
       fill_wide_graph(wa.g, gs, a, norm);
       wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
-      wa.act = act; wa.slope = slope;
+      wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
       return launch_wide(wa, G, F, 0, np, st);
     }
     if (!p.h_smem) {

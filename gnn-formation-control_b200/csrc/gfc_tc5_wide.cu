@@ -50,24 +50,25 @@ template <int CIN, int COUT, int NP>
 struct WideLayout {
   static constexpr int ROWS = 128;
   static constexpr int CS = CIN / 2;                 // channels per slab
-  static constexpr int CPT = CS / 2;                 // state columns per worker thread
+  static constexpr int CPT = CS / 4;                 // state columns per worker thread (4 column quarters)
   static constexpr int NCH = CS / 8;                 // 16-byte chunks (8 fp16) per row and slab
   static constexpr int PW = ROWS * 16;               // bytes between chunks (one chunk column of all rows)
   static constexpr int PLANE = NCH * PW;             // one fp16 plane of a slab
   static constexpr int SLAB = NP * PLANE;
   static constexpr int STAGE = COUT * 32 * NP;       // taps of 16 channels: NP planes x 2 chunks x COUT x 16 B
-  static constexpr int NSTAGE = 8;
-  static constexpr int KSTEPS = CS / 16;             // tap MMA k-steps (= ring stages) per phase
-  static constexpr int OFF_W = 0;
-  static constexpr int OFF_RING = OFF_W + 2 * SLAB;
-  static constexpr int OFF_STAGE = (OFF_RING + NSTAGE * STAGE + 1023) / 1024 * 1024;   // 2 TMA store staging buffers [128 rows x 32 cols] fp32, 128B swizzle
-  static constexpr int OFF_BIAS = OFF_STAGE + 2 * ROWS * 128;
+  static constexpr int KSTEPS = CS / 16;             // tap MMA k-steps per phase
+  static constexpr int PHASE = KSTEPS * STAGE;       // taps of one phase (tap k, slab s): one ring stage, ONE barrier wait
+  static constexpr int NSTAGE = 2;
+  static constexpr int OFF_W = 0;                    // state planes: [slab][buffer] — double buffered, so the write-back of
+  static constexpr int OFF_RING = OFF_W + 4 * SLAB;  //   W_{k+1} only waits for hop k, not for the taps that still read W_k
+  static constexpr int OFF_STAGE = (OFF_RING + NSTAGE * PHASE + 1023) / 1024 * 1024;   // TMA store staging buffer [128 rows x 32 cols] fp32, 128B swizzle
+  static constexpr int OFF_BIAS = OFF_STAGE + ROWS * 128;
   static constexpr int OFF_SP = OFF_BIAS + COUT * 4;         // float2 positions of the tile rows (two buffers, alternating per tile)
-  static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;      // int [2 buffers][2 halves][128]: partial row degrees (sym-norm)
-  static constexpr int OFF_TAB = OFF_DEG + 2 * 2 * ROWS * 4; // float [3][128]: d^-1/2, 1/d, d^1/2 by degree
-  static constexpr int OFF_MAX = OFF_TAB + 3 * 128 * 4;      // uint [8]: per-warp tile maxima
-  static constexpr int OFF_BAR = OFF_MAX + 32;
-  static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 1 + 2 + 2;
+  static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;      // int [2 buffers][4 quarters][128]: partial row degrees (sym-norm)
+  static constexpr int OFF_TAB = OFF_DEG + 2 * 4 * ROWS * 4; // float [3][128]: d^-1/2, 1/d, d^1/2 by degree
+  static constexpr int OFF_MAX = OFF_TAB + 3 * 128 * 4;      // uint [16]: per-warp tile maxima
+  static constexpr int OFF_BAR = OFF_MAX + 64;
+  static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 2 + 1 + 2 + 2;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr int TM_OUT = 0;                   // two output accumulators [128 x COUT]
   static constexpr int TM_HOP = 2 * COUT;            // two hop accumulators   [128 x CS]
@@ -75,13 +76,22 @@ struct WideLayout {
   static constexpr int TM_USED = 2 * COUT + 2 * CS + 128;
   static constexpr int TM_COLS = TM_USED <= 32 ? 32 : TM_USED <= 64 ? 64 : TM_USED <= 128 ? 128 : TM_USED <= 256 ? 256 : 512;
   static_assert(CIN % 32 == 0 && CIN >= 32 && CIN <= 128, "CIN in {32,64,96,128}");
-  static_assert(COUT % 16 == 0 && COUT >= 16 && COUT <= 128, "COUT multiple of 16, <= 128");
+  static_assert(COUT % 32 == 0 && COUT >= 32 && COUT <= 128, "COUT multiple of 32, <= 128");
   static_assert(CPT % 8 == 0, "whole chunks per worker thread");
   static_assert(BYTES <= 227 * 1024, "shared memory");
 };
+// row degree of tile row `row` from the four partial counts
+__device__ __forceinline__ int row_degree(const int* sdeg, int pbuf, int row) {
+  const int* p = sdeg + pbuf * 4 * 128 + row;
+  return p[0] + p[128] + p[256] + p[384];
+}
 
-constexpr int kWideThreads = 320;   // warp 0: MMA issuer, warp 1: TMA producer + TMEM owner, warps 2..9: workers
-constexpr int kWorkerWarps = 8;
+// warp 0: MMA issuer, warp 1: TMA producer + TMEM owner, warps 2..17: workers.  The workers' code (TMEM read-back,
+// plane split, pair tests) is a chain of dependent instructions; with 8 worker warps (2 per scheduler) the round-2
+// profile showed 36 % issue slots used at 7 cycles per issued instruction and the tensor pipe 32 % busy, so the
+// worker set is 16 warps (4 per scheduler, 4 column quarters per TMEM lane quadrant).
+constexpr int kWideThreads = 576;
+constexpr int kWorkerWarps = 16;
 int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
 int g_wide_no_prefetch = 0;    // experiment switch
 
@@ -93,38 +103,35 @@ static __device__ __noinline__ bool wide_adjacent_exact(float ax, float ay, floa
 
 // adjacency of tile row `pr` (position `me`) with the 8 tile rows c0..c0+7 as a bit mask.
 // All 8 squared distances are formed first (8 independent shared-memory loads); the exact fp64 rule only
-// runs for the rare pairs inside the fp32 rounding band.
+// runs for the rare pairs inside the fp32 rounding band.  Candidates: same graph [c_lo, c_hi), real rows, not pr itself.
 __device__ __forceinline__ uint32_t adjacency8(const float2* __restrict__ sp, float2 me, int pr, int c0, int c_lo,
                                                int c_hi, int rows_used, double thr, float thr_lo, float thr_hi) {
-  float sv[8];
+  const int lo = max(c_lo, c0) - c0, hi = min(min(c_hi, rows_used), c0 + 8) - c0;
+  if (hi <= lo || pr >= rows_used) return 0u;
+  uint32_t valid = ((1u << hi) - 1u) & ~((1u << lo) - 1u);
+  if ((unsigned)(pr - c0) < 8u) valid &= ~(1u << (pr - c0));
+  uint32_t in = 0, out = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const float2 o = sp[c0 + i];
     const float dx = me.x - o.x, dy = me.y - o.y;
-    sv[i] = fmaf(dx, dx, dy * dy);
+    const float sv = fmaf(dx, dx, dy * dy);
+    in |= (sv < thr_lo ? 1u : 0u) << i;
+    out |= (sv > thr_hi ? 1u : 0u) << i;
   }
-  uint32_t bits = 0, band = 0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int c = c0 + i;
-    const bool ok = (c >= c_lo) && (c < c_hi) && (c != pr) && (pr < rows_used) && (c < rows_used);
-    if (ok && sv[i] < thr_lo) bits |= 1u << i;
-    if (ok && sv[i] >= thr_lo && sv[i] <= thr_hi) band |= 1u << i;
-  }
-  if (band) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (band & (1u << i)) {
-        const float2 o = sp[c0 + i];
-        if (wide_adjacent_exact(me.x, me.y, o.x, o.y, thr)) bits |= 1u << i;
-      }
-    }
+  uint32_t bits = in & valid;
+  uint32_t band = valid & ~in & ~out;
+  while (band) {
+    const int i = __ffs(band) - 1;
+    band &= band - 1;
+    const float2 o = sp[c0 + i];
+    if (wide_adjacent_exact(me.x, me.y, o.x, o.y, thr)) bits |= 1u << i;
   }
   return bits;
 }
-// two adjacency bits -> one word of two fp16 (1.0 = 0x3c00), bit `lo` at the lower address
-__device__ __forceinline__ uint32_t p_word(uint32_t bits, int lo) {
-  return (((bits >> lo) & 1u) ? 0x3c00u : 0u) | (((bits >> (lo + 1)) & 1u) ? 0x3c000000u : 0u);
+// two adjacency bits -> one word of two fp16 (pv = the fp16 pattern of an edge, 2^-c), bit `lo` at the lower address
+__device__ __forceinline__ uint32_t p_word(uint32_t bits, int lo, uint32_t pv) {
+  return ((bits >> lo) & 1u) * pv + ((bits >> (lo + 1)) & 1u) * (pv << 16);
 }
 
 // Predicated read-only loads as volatile asm: issued exactly where written (never sunk to the first use)
@@ -160,7 +167,13 @@ __device__ __forceinline__ float ldg_cg(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// act(v) = v > 0 ? v : v * neg   (neg: 1 none, 0 relu, slope leaky) == max(v, v neg) for neg <= 1, min(v, v neg) otherwise
+__device__ __forceinline__ float act_fast(float v, float neg, bool use_min) {
+  const float t = v * neg;
+  return use_min ? fminf(v, t) : fmaxf(v, t);
+}
 
 // d^-1/2, 1/d, d^1/2 by degree (isolated node: 1, 0, 1 — its row of S is zero, multirobotsim_dcenlocal.py:309-313)
 __device__ __forceinline__ void fill_degree_tables(float* tab, int tid, int nthreads) {
@@ -172,6 +185,15 @@ __device__ __forceinline__ void fill_degree_tables(float* tab, int tid, int nthr
   }
 }
 
+// Pipeline of one tile (K taps, two channel slabs s = 0, 1; phase ph = 2 k + s), tensor-pipe order:
+//   hop(k,0) taps(k,0) hop(k,1) taps(k,1) hop(k+1,0) ...
+// hop(k,s) reads W_k[s] (buffer b) and commits hop_done[s]; the workers then write W_{k+1}[s] into buffer 1-b while
+// taps(k,s), hop(k,1-s) and taps(k,1-s) execute — about 2000 tensor-pipe cycles of slack for one write-back.
+// Barriers:  w_ready[s]  workers -> issuer   W_k[s] written (K per tile: the W_0 store and K-1 write-backs)
+//            hop_done[s] issuer  -> workers  hop(k,s) complete (K-1 per tile)
+//            w0_free[s]  issuer  -> workers  taps(K-2,s) complete: W_{K-2}[s]'s buffer may take the next tile's W_0
+//            h_full/h_empty[2]   TMA producer <-> issuer, one stage = all tap planes of a phase
+//            p_ready, out_full[2], out_free[2] as before (P and OUT double buffered across tiles)
 template <int CIN, int COUT, int MODE, int NP>
 __global__ void __launch_bounds__(kWideThreads, 1)
 tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUtensorMap tmap_out) {
@@ -189,8 +211,9 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
   uint64_t* h_full = bars;                      // [NSTAGE]
   uint64_t* h_empty = bars + L::NSTAGE;         // [NSTAGE]
   uint64_t* w_ready = bars + 2 * L::NSTAGE;     // [2]
-  uint64_t* mma_done = w_ready + 2;             // [2]
-  uint64_t* p_ready = mma_done + 2;             // [1]
+  uint64_t* hop_done = w_ready + 2;             // [2]
+  uint64_t* w0_free = hop_done + 2;             // [2]
+  uint64_t* p_ready = w0_free + 2;              // [1]
   uint64_t* out_full = p_ready + 1;             // [2]
   uint64_t* out_free = out_full + 2;            // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_free + 2);
@@ -211,7 +234,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
     for (int i = 0; i < L::NSTAGE; ++i) { tc5::mbar_init(&h_full[i], 1); tc5::mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       tc5::mbar_init(&w_ready[i], kWorkerWarps);
-      tc5::mbar_init(&mma_done[i], 1);
+      tc5::mbar_init(&hop_done[i], 1);
+      tc5::mbar_init(&w0_free[i], 1);
       tc5::mbar_init(&out_full[i], 1);
       tc5::mbar_init(&out_free[i], kWorkerWarps);
     }
@@ -225,121 +249,144 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
 
-  // NOTE on code size: every role's per-tile code is executed once per ~10 us while the other roles run
-  // their own loops, so the instruction caches only hold it if it is small.  Loops are deliberately kept
-  // rolled (one copy of the plane-split / pair-test / MMA-issue code each) unless a register array forces
-  // unrolling; barrier parities are bit masks so that they can be indexed at run time.
   if (warp == 0) {
     // =========================== MMA issuer (one elected thread) ===============================
+    // The issuing thread is a single instruction stream: everything per MMA beyond the instruction itself (descriptor
+    // arithmetic, barrier polls) is serial latency in front of the tensor pipe.  Descriptors therefore advance by
+    // adding constants to their low word, the tap loop is unrolled, and a phase polls two barriers in all.
     if (tc5::elect_one()) {
       constexpr uint32_t kIdescTap = tc5::idesc_f16(128, COUT, 0, 0);
       constexpr uint32_t kIdescHop = tc5::idesc_f16(128, L::CS, 0, 1);
       const uint32_t w_addr = tc5::smem_u32(Wb), r_addr = tc5::smem_u32(Rb);
-      uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0;
+      uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0, wbuf = 0;
       int st = 0;
       const int hop_ksteps = (w.gpc * N + 15) >> 4;
       int it = 0;
+      int nstamp = 0;
+      const bool dbg = w.dbg != nullptr && blockIdx.x == 0;
+#ifdef GFC_WIDE_TIMELINE
+#define GFC_WSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#else
+#define GFC_WSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
+#endif
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const int ob = it & 1;
-        if (it >= 2) { tc5::mbar_wait(&out_free[ob], (par_of >> ob) & 1); par_of ^= 1u << ob; }
+        GFC_WSTAMP(1);
         tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
+        GFC_WSTAMP(3);
         const uint32_t d_out = tmem + L::TM_OUT + ob * COUT;
 #pragma unroll 1
         for (int ph = 0; ph < 2 * K; ++ph) {
           const int k = ph >> 1, s = ph & 1;
+          GFC_WSTAMP(100 + ph);
           tc5::mbar_wait(&w_ready[s], (par_wr >> s) & 1); par_wr ^= 1u << s;
           tc5::fence_after_sync();
-          const uint32_t ws = w_addr + s * L::SLAB;
+          GFC_WSTAMP(200 + ph);
+          const uint32_t ws = w_addr + (2 * s + ((wbuf >> s) & 1)) * L::SLAB;
+          wbuf ^= 1u << s;
           if (k + 1 < K) {
             // hop: D_hop[s] = P * W_k[slab s]   (A = P from tensor memory, B = state planes MN-major)
             const uint32_t d_hop = tmem + L::TM_HOP + s * L::CS;
+            uint32_t pa = tmem + L::TM_P + ob * 64;          // 16 source rows = 8 columns of fp16 pairs
+            uint64_t bd = make_desc(ws, 128, L::PW);
             uint32_t acc = 0;
 #pragma unroll 1
             for (int j = 0; j < hop_ksteps; ++j) {
-              const uint32_t pa = tmem + L::TM_P + ob * 64 + j * 8;   // 16 source rows = 8 columns of fp16 pairs
-#pragma unroll
-              for (int pl = 0; pl < NP; ++pl) {
-                tc5::mma_bf16_ts(d_hop, pa, make_desc(ws + pl * L::PLANE + j * 256, 128, L::PW), kIdescHop, acc);
-                acc = 1;
-              }
+              tc5::mma_bf16_ts(d_hop, pa, bd, kIdescHop, acc);
+              if (NP == 2) tc5::mma_bf16_ts(d_hop, pa, bd + (L::PLANE >> 4), kIdescHop, 1u);
+              acc = 1;
+              pa += 8; bd += 256 >> 4;
             }
+            tc5::mma_commit(&hop_done[s]);
           }
+          if (ph == 0 && it >= 2) { tc5::mbar_wait(&out_free[ob], (par_of >> ob) & 1); par_of ^= 1u << ob; }
           // taps: D_out += W_k[slab s] * H_k[slab s]   (hi hi + hi lo + lo hi)
-#pragma unroll 1
-          for (int i = 0; i < L::KSTEPS; ++i) {
-            tc5::mbar_wait(&h_full[st], par_hf);
-            tc5::fence_after_sync();
-            const uint32_t hs = r_addr + st * L::STAGE;
-            const uint32_t wa = ws + i * 2 * L::PW;
-            const uint64_t a0 = make_desc(wa, L::PW, 128);
-            const uint64_t b0 = make_desc(hs, COUT * 16, 128);
-            const uint32_t first = (ph == 0 && i == 0) ? 0u : 1u;
-            tc5::mma_bf16_ss(d_out, a0, b0, kIdescTap, first);
-            if (NP == 2) {
-              const uint64_t a1 = make_desc(wa + L::PLANE, L::PW, 128);
-              const uint64_t b1 = make_desc(hs + COUT * 32, COUT * 16, 128);
-              tc5::mma_bf16_ss(d_out, a0, b1, kIdescTap, 1u);
-              tc5::mma_bf16_ss(d_out, a1, b0, kIdescTap, 1u);
+          tc5::mbar_wait(&h_full[st], (par_hf >> st) & 1); par_hf ^= 1u << st;
+          tc5::fence_after_sync();
+          {
+            uint64_t a0 = make_desc(ws, L::PW, 128);
+            uint64_t b0 = make_desc(r_addr + st * L::PHASE, COUT * 16, 128);
+#pragma unroll
+            for (int i = 0; i < L::KSTEPS; ++i) {
+              tc5::mma_bf16_ss(d_out, a0, b0, kIdescTap, (ph == 0 && i == 0) ? 0u : 1u);
+              if (NP == 2) {
+                tc5::mma_bf16_ss(d_out, a0, b0 + ((COUT * 32) >> 4), kIdescTap, 1u);
+                tc5::mma_bf16_ss(d_out, a0 + (L::PLANE >> 4), b0, kIdescTap, 1u);
+              }
+              a0 += (2 * L::PW) >> 4; b0 += L::STAGE >> 4;
             }
-            tc5::mma_commit(&h_empty[st]);
-            if (++st == L::NSTAGE) { st = 0; par_hf ^= 1; }
           }
-          tc5::mma_commit(&mma_done[s]);
+          tc5::mma_commit(&h_empty[st]);
+          st ^= 1;
+          if (k == K - 2) tc5::mma_commit(&w0_free[s]);
+          GFC_WSTAMP(300 + ph);
         }
         tc5::mma_commit(&out_full[ob]);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    // =========================== tap producer (TMA bulk copies) ===============================
+    // =========================== tap producer (TMA bulk copies) + L2 prefetch of the inputs ===========
     if (tc5::elect_one()) {
       int st = 0;
       uint32_t par_he = 0;
-      bool primed = false;   // the first NSTAGE fills need no wait
       int filled = 0;
-      const int stages_per_tile = K * (CIN / 16);
       const unsigned char* hsrc = w.hpack + kPackHeader;
+      auto prefetch_tile = [&](int tile) {
+        if (tile >= t_end || w.no_prefetch) return;
+        const int b0 = tile * w.gpc;
+        const int gcount = min(w.gpc, w.B - b0);
+        const uint32_t bytes = (uint32_t)gcount * (uint32_t)N * CIN * 4u;   // multiple of 16 (CIN % 32 == 0)
+        const size_t off = (size_t)b0 * N * CIN;
+        tc5::bulk_prefetch_l2(w.in + off, bytes);
+        if (MODE == 1 && w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + off, bytes);
+      };
+      prefetch_tile(t_begin); prefetch_tile(t_begin + 1);
       for (int tile = t_begin; tile < t_end; ++tile) {
+        prefetch_tile(tile + 2);   // the workers read a tile's inputs near the end of the tile before it
 #pragma unroll 1
-        for (int u = 0; u < stages_per_tile; ++u) {
-          if (primed) { tc5::mbar_wait(&h_empty[st], par_he); }
-          tc5::mbar_arrive_expect_tx(&h_full[st], L::STAGE);
-          tc5::bulk_g2s(Rb + st * L::STAGE, hsrc + (size_t)u * L::STAGE, L::STAGE, &h_full[st]);
-          if (++st == L::NSTAGE) { st = 0; if (primed) par_he ^= 1; }
-          if (!primed && ++filled == L::NSTAGE) primed = true;
+        for (int ph = 0; ph < 2 * K; ++ph) {
+          if (filled >= L::NSTAGE) { tc5::mbar_wait(&h_empty[st], (par_he >> st) & 1); par_he ^= 1u << st; }
+          else ++filled;
+          tc5::mbar_arrive_expect_tx(&h_full[st], L::PHASE);
+          const unsigned char* src = hsrc + (size_t)ph * L::PHASE;   // phases are contiguous in the packed taps
+#pragma unroll
+          for (int i = 0; i < L::KSTEPS; ++i)
+            tc5::bulk_g2s(Rb + st * L::PHASE + i * L::STAGE, src + (size_t)i * L::STAGE, L::STAGE, &h_full[st]);
+          st ^= 1;
         }
       }
     }
     __syncwarp();
   } else {
     // =========================== workers ======================================================
-    const int wt = tid - 64;                 // 0..255
-    const int ww = warp - 2;
+    const int wt = tid - 64;                 // 0..511
+    const int ww = warp - 2;                 // 0..15
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int half = ww >> 2;                // which half of a slab's columns
+    const int qtr = ww >> 2;                 // which quarter of a slab's columns
     const int r = q * 32 + lane;             // tile row owned by this thread (= its TMEM lane)
     const int jr = r / N, nr = r - jr * N;   // (graph, node) of the row
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     const float inv_th = __ldg(reinterpret_cast<const float*>(w.hpack));   // 1 / (tap scale)
-    const float hop_down = __uint_as_float((uint32_t)(127 - w.cshift) << 23);   // 2^-c
+    // an edge of P carries the per-hop headroom 2^-c (exact in fp16), so the hop result needs no rescaling
+    const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;
+    const float act_neg = w.act == GFC_ACT_NONE ? 1.f : (w.act == GFC_ACT_RELU ? 0.f : w.slope);
+    const bool act_min = act_neg > 1.f;
     float xin0[L::CPT], xin1[L::CPT];
     float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_md = 0, par_ofl = 0;
-    // per-tile scalars of the LIVE tile (the one whose MMAs run) and of the NEXT one (being prepared)
-    float inv_live = 1.f, wbf_live = hop_down, rowf_live = 1.f;
-    float scale_next = 1.f, inv_next = 1.f, wbf_next = hop_down, rowf_next = 1.f;
+    uint32_t par_hd = 0, par_ofl = 0, par_w0 = 0, wbuf = 0;
+    // per-tile scalars: of the tile whose epilogue is pending (prev), of the LIVE tile (its MMAs run) and of the
+    // NEXT one (being prepared)
+    float inv_prev = 1.f, inv_live = 1.f, wbf_live = 1.f;
+    float scale_next = 1.f, inv_next = 1.f, wbf_next = 1.f, rowf_next = 1.f;
+    int nstamp = 0;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+#ifdef GFC_WIDE_TIMELINE
+#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[4096 + 2 * nstamp] = clock64(); w.dbg[4096 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#else
+#define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
+#endif
 
-    // Operands of the next tile.  Early in the current tile one thread asks the TMA engine to pull the
-    // (contiguous) input tile into L2; the register loads then happen late in the tile (L2-hit latency hidden
-    // behind the last taps).
-    auto prefetch_tile = [&](int tile) {
-      const int b0 = tile * w.gpc;
-      const int gcount = min(w.gpc, w.B - b0);
-      const uint32_t bytes = (uint32_t)gcount * (uint32_t)N * CIN * 4u;   // multiple of 16 (CIN % 32 == 0)
-      const size_t off = (size_t)b0 * N * CIN;
-      tc5::bulk_prefetch_l2(w.in + off, bytes);
-      if (MODE == 1 && w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + off, bytes);
-    };
     auto load_pos = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
@@ -347,24 +394,25 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         mypos = (wt < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wt)
                                   : make_float2(0.f, 0.f);
     };
+    // MODE 1 / 2: dY / y are row-major [rows x CIN]: a warp instruction reads whole 16-byte pieces of RPI consecutive
+    // rows (4 full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle at
+    // store time.  Warp ww owns rows 8 ww .. 8 ww + 7, lane = (row offset, piece).
+    constexpr int PPR = L::CS / 4, RPI = 32 / PPR, NPC = L::CPT / 4;   // pieces per row, rows per instruction, pieces per thread
+    static_assert(NPC % 2 == 0 && RPI * NPC == 8, "piece mapping");
     auto load_slab = [&](int tile, int s, float (&xin)[L::CPT]) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
-      const bool valid = r < gcount * N;
-      const int c0 = s * L::CS + half * L::CPT;
       if (MODE == 0) {
+        const bool valid = r < gcount * N;
+        const int c0 = s * L::CS + qtr * L::CPT;
         const float* src = w.in + ((size_t)(b0 + jr) * CIN + c0) * N + nr;
 #pragma unroll
-        for (int i = 0; i < L::CPT; ++i) xin[i] = ldg_f32(src + (size_t)i * N, valid);
+        for (int i = 0; i < L::CPT; ++i) { xin[i] = ldg_f32(src, valid); src += N; }
       } else {
-        // dY / y are row-major [rows x CIN]: a warp instruction reads whole 16-byte pieces of RPI consecutive rows
-        // (4 full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle
-        // at store time.  Warp ww owns rows 16 ww .. 16 ww + 15, lane = (row offset, piece).
-        constexpr int PPR = L::CS / 4, RPI = 32 / PPR;
         const int rows_used = gcount * N;
 #pragma unroll
-        for (int i = 0; i < L::CPT / 4; ++i) {
-          const int row = 16 * ww + RPI * i + lane / PPR;
+        for (int i = 0; i < NPC; ++i) {
+          const int row = 8 * ww + RPI * i + lane / PPR;
           const bool ok = row < rows_used;
           const size_t off = ((size_t)b0 * N + row) * CIN + s * L::CS + 4 * (lane % PPR);
           float4 v = ldg_f32x4(w.in + off, ok);
@@ -382,9 +430,9 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       }
     };
     // registers of load_slab -> the fp16 planes of W_0[slab s] (scaled by the tile scale, D^-1/2 for sym-norm)
-    auto store_slab = [&](int s, const float (&xin)[L::CPT], int pbuf) {
+    auto store_slab = [&](int s, const float (&xin)[L::CPT], int pbuf, unsigned char* Ws) {
       if (MODE == 0) {
-        unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
+        unsigned char* base = Ws + (qtr * (L::CPT / 8)) * L::PW + r * 16;
         const float f0 = scale_next * rowf_next;   // rowf_next = d^-1/2 of this thread's row (1 when not normalised)
 #pragma unroll
         for (int c = 0; c < L::CPT / 8; ++c) {
@@ -394,11 +442,10 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
           store_chunk_f16<NP>(base + c * L::PW, L::PLANE, v);
         }
       } else {
-        constexpr int PPR = L::CS / 4, RPI = 32 / PPR;
         const int pi = lane % PPR;
         const bool odd = pi & 1;
 #pragma unroll
-        for (int i = 0; i < L::CPT / 4; i += 2) {
+        for (int i = 0; i < NPC; i += 2) {
           // even lane keeps its piece of row(i) and receives the partner's; odd lane does the same for row(i+1)
           float snd[4], rcv[4], own[4];
 #pragma unroll
@@ -408,13 +455,13 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
-          const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+          const int row = 8 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
           float f0 = scale_next;
-          if (norm) f0 *= dtab[sdeg[(pbuf * 2 + 0) * L::ROWS + row] + sdeg[(pbuf * 2 + 1) * L::ROWS + row]];
+          if (norm) f0 *= dtab[row_degree(sdeg, pbuf, row)];
           float v[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { v[e] = (odd ? rcv[e] : own[e]) * f0; v[4 + e] = (odd ? own[e] : rcv[e]) * f0; }
-          store_chunk_f16<NP>(Wb + s * L::SLAB + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
+          store_chunk_f16<NP>(Ws + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
         }
       }
     };
@@ -424,9 +471,16 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) tc5::mbar_arrive(bar);
     };
+    // buffer of slab s that the next state of the slab goes into; toggles with every state written
+    auto next_wbuf = [&](int s) -> unsigned char* {
+      unsigned char* p = Wb + (2 * s + ((wbuf >> s) & 1)) * L::SLAB;
+      wbuf ^= 1u << s;
+      return p;
+    };
 
-    // P[r][c] = 1 iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
-    // TMEM lane r; the two warps of a quadrant interleave 4-chunk groups of source rows.  Chunks t0..t1-1 of 8.
+    // P[r][c] = 2^-c iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
+    // TMEM lane r; the four warps of a quadrant take every fourth chunk of 8 source rows (balanced for any N).
+    // Slots t0..t1-1 of the 4 this thread owns.
     int degcnt = 0;
     auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
       const float2* sp = sp_all + pbuf * L::ROWS;
@@ -437,17 +491,17 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       const bool row_ok = r < w.gpc * N;
 #pragma unroll 1
       for (int t = t0; t < t1; ++t) {
-        const int qc = (t >> 2) * 8 + half * 4 + (t & 3);   // chunk of 8 source rows = 4 TMEM columns
+        const int qc = 4 * t + qtr;   // chunk of 8 source rows = 4 TMEM columns
         uint32_t bits = 0;
         if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
           bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
         degcnt += __popc(bits);
-        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0), p_word(bits, 2), p_word(bits, 4),
-                      p_word(bits, 6));
+        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0, pval), p_word(bits, 2, pval),
+                      p_word(bits, 4, pval), p_word(bits, 6, pval));
       }
     };
     auto publish_p = [&](int pbuf) {
-      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;   // read after the tile-maximum barrier below
+      sdeg[(pbuf * 4 + qtr) * L::ROWS + r] = degcnt;   // read after the tile-maximum barrier below
       degcnt = 0;
       tc5::tmem_st_wait();
       tc5::fence_before_sync();
@@ -455,66 +509,124 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       if (lane == 0) tc5::mbar_arrive(p_ready);
     };
 
-    // The loop runs once per tile plus one leading iteration (it == -1) that only prepares the first tile's
-    // operands, so that the per-tile code exists exactly once.  P of the next tile is double-buffered in TMEM and
-    // built in two halves right after the first two write-backs of the live tile (where the workers have slack).
-    int tile = t_begin;               // tile whose MMAs run during this iteration (none when it == -1)
+    // Epilogue of a finished tile, one piece per call so that it can be interleaved with the write-backs of the tile
+    // that follows (OUT is double buffered).  MODE 0/2: piece = 32 output columns through the swizzled staging buffer
+    // and the TMA store engine (full 128-byte lines); MODE 1: piece = 16 columns of dX per thread, coalesced over n.
+    constexpr int kEpiPieces = (MODE != 1) ? COUT / 32 : COUT / 64;
+    int epi_tile = -1, epi_piece = 0, epi_ob = 0;   // pending epilogue (epi_tile < 0: none)
+    auto epilogue_piece = [&]() {
+      const int b0 = epi_tile * w.gpc;
+      if (epi_piece == 0) {
+        tc5::mbar_wait_suspend(&out_full[epi_ob], (par_ofl >> epi_ob) & 1); par_ofl ^= 1u << epi_ob;
+        tc5::fence_after_sync();
+        GFC_KSTAMP(500);
+      }
+      const int pc = epi_piece;
+      if constexpr (MODE != 1) {
+        const int col = pc * 32 + qtr * 8;
+        uint32_t v[8];
+        tc5::tmem_ld8u(tm_lane + L::TM_OUT + epi_ob * COUT + col, v);
+        tc5::tmem_ld_wait();
+        unsigned char* srow = stage_out + r * 128;
+        // the TMA store of the previous piece has finished reading the staging buffer
+        if (wt == 0) tc5::tma_store_wait_read();
+        worker_bar();
+#pragma unroll
+        for (int i4 = 0; i4 < 2; ++i4) {
+          const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i4 * 4);
+          float4 o;
+          o.x = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 0]), inv_prev, bb.x), act_neg, act_min);
+          o.y = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 1]), inv_prev, bb.y), act_neg, act_min);
+          o.z = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 2]), inv_prev, bb.z), act_neg, act_min);
+          o.w = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 3]), inv_prev, bb.w), act_neg, act_min);
+          const int cc = qtr * 2 + i4;
+          *reinterpret_cast<float4*>(srow + ((cc ^ (r & 7)) << 4)) = o;
+        }
+        tc5::fence_proxy_async();
+        worker_bar();
+        if (wt == 0) {
+          tc5::tma_store_2d(&tmap_out, stage_out, pc * 32, b0 * N);
+          tc5::tma_store_commit();
+        }
+      } else {
+        // dX[(b0 + j), g, n]: lanes = consecutive nodes n, one coalesced store per channel
+        const int rows_used = min(w.gpc, w.B - b0) * N;
+        const int col = qtr * (COUT / 4) + pc * 16;
+        uint32_t v[16];
+        tc5::tmem_ld16(tm_lane + L::TM_OUT + epi_ob * COUT + col, v);
+        tc5::tmem_ld_wait();
+        if (r < rows_used) {
+          float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]) * inv_prev;
+        }
+      }
+      if (++epi_piece == kEpiPieces) {
+        tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(&out_free[epi_ob]);
+        epi_tile = -1;
+        GFC_KSTAMP(501);
+      }
+    };
+
+    // The loop runs once per tile, plus one leading iteration (no live tile: it only prepares the first tile's
+    // operands) and one trailing iteration (no live tile, no next tile: it drains the last epilogue), so that every
+    // piece of per-tile code exists at exactly ONE place in the binary — the kernel has to stay inside the
+    // instruction cache, each role runs its code once per tile.  An iteration is a sequence of slots; slot i does the
+    // write-back of phase i, one half of the next tile's P, and one piece of the previous tile's epilogue.
+    int tile = t_begin;               // tile whose MMAs run during this iteration (if live)
     int it = -1;
+    bool live = false;
     int next = t_begin;
     if (next < t_end) load_pos(next);
     while (true) {
-      const bool live = it >= 0;
       const bool has_next = next < t_end;
-      if (!live && !has_next) break;
+      if (!live && !has_next && epi_tile < 0) break;
       const int pbuf = (it + 1) & 1;
       if (has_next) {
         if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;   // positions of `next` (loaded one tile ahead)
         worker_bar();
         if (next + 1 < t_end) load_pos(next + 1);
-        if (wt == 0 && !w.no_prefetch) {   // L2 prefetch runs two tiles ahead
-          if (!live) prefetch_tile(next);
-          if (next + 1 < t_end) prefetch_tile(next + 1);
-        }
-        if (!live || K == 1) {
-          if (K > 1) build_p_part(next, pbuf, 0, 8);
-          publish_p(pbuf);
-        }
       }
-      // ---- write-backs of the K-1 hops ------------------------------------------------------------------
       const int nwb = live ? 2 * (K - 1) : 0;
-      bool slab0_loaded = false;
+      const int p_slots = (has_next && K > 1) ? 2 : 0;
+      const int nslots = max(max(nwb, p_slots), has_next ? 1 : 0);
+      const int load_slot = max(nwb - 2, 0);        // inputs of the next tile: requested two write-backs before their use
+      const int pub_slot = max(p_slots, 1) - 1;
 #pragma unroll 1
-      for (int ph = 0; ph < nwb; ++ph) {
-        // next tile's inputs: requested two write-backs ahead of their use (memory latency behind the last taps)
-        if (has_next && !slab0_loaded && ph + 2 >= nwb) { load_slab(next, 0, xin0); load_slab(next, 1, xin1); slab0_loaded = true; }
-        {
-          const int s = ph & 1;
-          tc5::mbar_wait(&mma_done[s], (par_md >> s) & 1); par_md ^= 1u << s;
+      for (int slot = 0; slot < nslots || epi_tile >= 0; ++slot) {
+        if (has_next && slot == load_slot) { load_slab(next, 0, xin0); load_slab(next, 1, xin1); }
+        if (slot < nwb) {
+          const int s = slot & 1;
+          GFC_KSTAMP(100 + slot);
+          tc5::mbar_wait_suspend(&hop_done[s], (par_hd >> s) & 1); par_hd ^= 1u << s;
           tc5::fence_after_sync();
-          // hop result (exact fp32, scaled units) -> fp16 planes of W_{k+1}[slab s], 8 columns at a time;
-          // wbf = 2^-c (x 1/d of this row for sym-norm)
-          const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + half * L::CPT;
-          unsigned char* base = Wb + s * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
-#pragma unroll 1
+          GFC_KSTAMP(200 + slot);
+          // hop result (exact fp32, already in the units of W_{k+1}) -> fp16 planes of W_{k+1}[slab s]; all of this
+          // thread's columns are read with ONE tcgen05.ld so that the chunks' split chains overlap
+          const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + qtr * L::CPT;
+          unsigned char* base = next_wbuf(s) + (qtr * (L::CPT / 8)) * L::PW + r * 16;
+          uint32_t v[L::CPT];
+          if constexpr (L::CPT == 16) tc5::tmem_ld16(taddr, v); else tc5::tmem_ld8u(taddr, v);
+          tc5::tmem_ld_wait();
+#pragma unroll
           for (int c = 0; c < L::CPT / 8; ++c) {
-            uint32_t v[8];
-            tc5::tmem_ld8u(taddr + c * 8, v);
-            tc5::tmem_ld_wait();
             float f[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * wbf_live;
+            for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf_live : __uint_as_float(v[c * 8 + i]);
             store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
           }
           publish(&w_ready[s]);
+          GFC_KSTAMP(300 + slot);
         }
-        if (has_next && ph < 2) {   // K > 1 here
-          build_p_part(next, pbuf, 4 * ph, 4 * ph + 4);
-          if (ph == 1) publish_p(pbuf);
-        }
+        if (slot < p_slots) build_p_part(next, pbuf, 2 * slot, 2 * slot + 2);
+        if (has_next && slot == pub_slot) publish_p(pbuf);
+        if (epi_tile >= 0) epilogue_piece();
       }
-      // ---- next tile: inputs -> registers, tile maximum -> power-of-two scale ------------------------------
+      GFC_KSTAMP(400);
+      // ---- next tile: tile maximum -> power-of-two scale, then its state W_0 ------------------------------------
       if (has_next) {
-        if (!slab0_loaded) { load_slab(next, 0, xin0); load_slab(next, 1, xin1); }
         float m = 0.f;
 #pragma unroll
         for (int i = 0; i < L::CPT; ++i) m = fmaxf(m, fmaxf(fabsf(xin0[i]), fabsf(xin1[i])));
@@ -526,88 +638,38 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         for (int i = 1; i < kWorkerWarps; ++i) mt = max(mt, smax[i]);
         if (w.amax && wt == 0) atomicMax(reinterpret_cast<unsigned int*>(w.amax) + (MODE == 1 ? 1 : 0), mt);
         scale_next = tc5::pow2_scale(mt, kWideTop, &inv_next);
-        wbf_next = hop_down; rowf_next = 1.f;
-        float sq = 1.f;
+        wbf_next = 1.f; rowf_next = 1.f;
         if (norm) {   // K > 1: the degrees of `next` were stored by publish_p before the barrier above
-          const int d = sdeg[(pbuf * 2 + 0) * L::ROWS + r] + sdeg[(pbuf * 2 + 1) * L::ROWS + r];
-          rowf_next = dtab[d]; wbf_next = hop_down * dtab[128 + d]; sq = dtab[256 + d];
+          const int d = row_degree(sdeg, pbuf, r);
+          rowf_next = dtab[d]; wbf_next = dtab[128 + d];
+          inv_next *= dtab[256 + d];   // epilogue factor of this thread's row: 1/s x d^1/2
         }
-        inv_next *= sq;   // epilogue factor of this thread's row: 1/s (x d^1/2)
+        inv_next *= inv_th;
       }
-      // ---- the live tile's slabs become free one by one: next tile's state W_0 ---------------------------
+      GFC_KSTAMP(401);
+      // slab s of W_0 goes into the buffer that held W_{K-2}[s] of the live tile (free once taps(K-2,s) completed;
+      // K = 1: the buffer was read by the taps of the tile before the live one, whose epilogue — drained in the slot
+      // loop above — waited for that tile's out_full)
 #pragma unroll 1
       for (int s = 0; s < 2; ++s) {
-        if (live) { tc5::mbar_wait(&mma_done[s], (par_md >> s) & 1); par_md ^= 1u << s; }
+        if (live && K >= 2) { tc5::mbar_wait_suspend(&w0_free[s], (par_w0 >> s) & 1); par_w0 ^= 1u << s; }
+        GFC_KSTAMP(410 + s);
         if (has_next) {
-          if (s == 0) store_slab(0, xin0, pbuf); else store_slab(1, xin1, pbuf);
+          unsigned char* Ws = next_wbuf(s);
+          if (s == 0) store_slab(0, xin0, pbuf, Ws); else store_slab(1, xin1, pbuf, Ws);
           publish(&w_ready[s]);
         }
+        GFC_KSTAMP(420 + s);
       }
-      // ---- epilogue of the live tile (the issuer is already working on the next one) -------------------
-      if (live) {
-        const int b0 = tile * w.gpc;
-        const int rows_used = min(w.gpc, w.B - b0) * N;
-        const int ob = it & 1;
-        tc5::mbar_wait(&out_full[ob], (par_ofl >> ob) & 1); par_ofl ^= 1u << ob;
-        tc5::fence_after_sync();
-        if constexpr (MODE != 1) {
-          // y tile through swizzled staging buffers and the TMA store engine: full 128-byte lines
-#pragma unroll 1
-          for (int pc = 0; pc < COUT / 32; ++pc) {
-            const int col = pc * 32 + half * 16;
-            uint32_t v[16];
-            tc5::tmem_ld16(tm_lane + L::TM_OUT + ob * COUT + col, v);
-            tc5::tmem_ld_wait();
-            unsigned char* sbuf = stage_out + (pc & 1) * (L::ROWS * 128);
-            unsigned char* srow = sbuf + r * 128;
-            // the TMA store that last used this buffer (two pieces ago) has finished reading it
-            if (wt == 0) tc5::tma_store_wait_read1();
-            worker_bar();
-#pragma unroll
-            for (int i4 = 0; i4 < 4; ++i4) {
-              const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i4 * 4);
-              float4 o;
-              o.x = apply_act(__uint_as_float(v[i4 * 4 + 0]) * inv_live * inv_th + bb.x, w.act, w.slope);
-              o.y = apply_act(__uint_as_float(v[i4 * 4 + 1]) * inv_live * inv_th + bb.y, w.act, w.slope);
-              o.z = apply_act(__uint_as_float(v[i4 * 4 + 2]) * inv_live * inv_th + bb.z, w.act, w.slope);
-              o.w = apply_act(__uint_as_float(v[i4 * 4 + 3]) * inv_live * inv_th + bb.w, w.act, w.slope);
-              const int cc = half * 4 + i4;
-              *reinterpret_cast<float4*>(srow + ((cc ^ (r & 7)) << 4)) = o;
-            }
-            tc5::fence_proxy_async();
-            worker_bar();
-            if (wt == 0) {
-              tc5::tma_store_2d(&tmap_out, sbuf, pc * 32, b0 * N);
-              tc5::tma_store_commit();
-            }
-          }
-        } else {
-          // dX[(b0 + j), g, n]: lanes = consecutive nodes n, one coalesced store per channel
-          const bool valid = r < rows_used;
-#pragma unroll 1
-          for (int cb = 0; cb < COUT / 2; cb += 16) {
-            const int col = half * (COUT / 2) + cb;
-            uint32_t v[16];
-            tc5::tmem_ld16(tm_lane + L::TM_OUT + ob * COUT + col, v);
-            tc5::tmem_ld_wait();
-            if (valid) {
-              float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
-#pragma unroll
-              for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]) * inv_live * inv_th;
-            }
-          }
-        }
-        tc5::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc5::mbar_arrive(&out_free[ob]);
+      if (live) { epi_tile = tile; epi_piece = 0; epi_ob = it & 1; inv_prev = inv_live; }   // queue the live tile's epilogue
+      live = has_next;
+      if (has_next) {
+        tile = next;
+        next += 1;
+        ++it;
+        inv_live = inv_next; wbf_live = wbf_next;
       }
-      if (!has_next) break;
-      tile = next;
-      next += 1;
-      ++it;
-      inv_live = inv_next; wbf_live = wbf_next; rowf_live = rowf_next;
     }
-    (void)rowf_live;
   }
   if (tid == 64) tc5::tma_store_wait_all();
   tc5::fence_before_sync();
@@ -636,7 +698,7 @@ template <int G, int F, int FH, int NP>
 struct DhLayout {
   static constexpr int ROWS = 128;
   static constexpr int NFH = F / FH;
-  static constexpr int CPT = FH / 2;                 // V columns per worker thread in a write-back
+  static constexpr int CPT = FH / 4;                 // V columns per worker thread in a write-back (4 column quarters)
   static constexpr int NCH = FH / 8;
   static constexpr int PW = ROWS * 16;
   static constexpr int PLANE = NCH * PW;
@@ -646,7 +708,7 @@ struct DhLayout {
   static constexpr int OFF_P = OFF_V + 3 * VBUF;
   static constexpr int OFF_SP = OFF_P + 2 * P_BYTES;
   static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;
-  static constexpr int OFF_TAB = OFF_DEG + 2 * 2 * ROWS * 4;
+  static constexpr int OFF_TAB = OFF_DEG + 2 * 4 * ROWS * 4;
   static constexpr int OFF_DB = OFF_TAB + 3 * 128 * 4;
   static constexpr int OFF_BAR = OFF_DB + FH * 4;
   static constexpr int NBAR = 6;
@@ -765,17 +827,18 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     __syncwarp();
   } else if (warp >= 2) {
     // =========================== workers ======================================================
-    const int wt = tid - 64;
-    const int ww = warp - 2;
+    const int wt = tid - 64;                   // 0..511
+    const int ww = warp - 2;                   // 0..15
     const int q = warp & 3;
-    const int hf = ww >> 2;
+    const int qtr = ww >> 2;                   // column quarter (write-back, drain) / row quarter (X^T)
     const int r = q * 32 + lane;               // tile row (write-back) and feature lane g (X^T, drain)
     const int jr = r / N;
     const bool g_ok = r < G;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
-    constexpr int PPR = FH / 4, RPI = 32 / PPR;   // V_0 loads: 16-byte pieces per row, rows per warp instruction
-    float xt[64];                              // x[g = r][rows 64 hf .. 64 hf + 63] of the next tile
-    float xin[FH / 2];                         // V_0 pieces of the next tile (short-lived)
+    constexpr int PPR = FH / 4, RPI = 32 / PPR, NPC = FH / 16;   // V_0 loads: 16-byte pieces per row, rows per warp instruction, pieces per thread
+    static_assert(RPI * NPC == 8 && NPC % 2 == 0, "piece mapping");
+    float xt[32];                              // x[g][rows 32 qtr .. 32 qtr + 31] of the next tile (two 16-lane halves)
+    float xin[4 * NPC];                        // V_0 pieces of the next tile (short-lived)
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};     // column sums of V_0 (columns 4*(lane % PPR) .. +3)
     float2 mypos = make_float2(0.f, 0.f);
     uint32_t par_hd = 0, par_id = 0;
@@ -784,8 +847,8 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     const int xtop = norm ? kWideTop - 4 : kWideTop;   // Xhat = D^1/2 X grows by < 2^3.5 (N <= 128)
     const float s_x = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax)), xtop, &inv_sx);
     const float s_v = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax + 1)), kWideTop, &inv_sv);
-    const float hop_down = __uint_as_float((uint32_t)(127 - w.cshift) << 23);   // 2^-c
-    float wbf_live = hop_down, wbf_next = hop_down;
+    const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;   // an edge of P = 2^-c: the hop result is V_{k+1} 2^(-c (k+1)) directly
+    float wbf_live = 1.f, wbf_next = 1.f;
 
     auto publish = [&](uint64_t* bar) {
       tc5::fence_proxy_async();
@@ -812,20 +875,19 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     };
     // X^T operand: x[(b0 + j), g, n] -> TMEM lane g, column (tile row / 2).  The 16x256b store shape lets a
     // thread own 4 consecutive tile rows (one float4 of x) of the feature lanes  16 h + t/4  and  16 h + t/4 + 8:
-    // a warp load instruction then touches 8 lines instead of 32.  xt[16 P + 8 u + 4 gs + i]: part P = 2 h + e
-    // (e selects rho in {2e, 2e+1}), u = rho & 1 ... see store_xt for the register order of the store.
-    auto load_xt_part = [&](int tile, auto part_c) {
-      constexpr int PART = decltype(part_c)::value;
-      constexpr int h16 = PART >> 1, e = PART & 1;
+    // a warp load instruction then touches 8 lines instead of 32.  This warp covers tile rows 32 qtr .. 32 qtr + 31
+    // (16 TMEM columns): xt[16 h + 8 rho + 4 gs + i] = x[g = 32 q + 16 h + 8 gs + t/4][row 32 qtr + 16 rho + 4 (t%4) + i].
+    auto load_xt_part = [&](int tile, auto h16_c) {
+      constexpr int h16 = decltype(h16_c)::value;   // compile-time register indices (no local-memory array)
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {          // rho = 2 e + u
+      for (int rho = 0; rho < 2; ++rho) {
 #pragma unroll
         for (int gs = 0; gs < 2; ++gs) {     // feature lane t/4 (+ 8)
           const int g = q * 32 + 16 * h16 + 8 * gs + (lane >> 2);
-          const int rr = hf * 64 + 16 * (2 * e + u) + 4 * (lane & 3);
-          float* dst = &xt[16 * PART + 8 * u + 4 * gs];
+          const int rr = qtr * 32 + 16 * rho + 4 * (lane & 3);
+          float* dst = &xt[16 * h16 + 8 * rho + 4 * gs];
           if ((N & 3) == 0) {
             const int j = rr / N, n = rr - j * N;
             const float4 v = ldg_f32x4(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr < rows_used);
@@ -840,36 +902,31 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         }
       }
     };
-    auto load_xt_slot = [&](int tile, int slot) {
-      if (slot == 0) load_xt_part(tile, std::integral_constant<int, 0>{});
-      else if (slot == 1) load_xt_part(tile, std::integral_constant<int, 1>{});
-      else if (slot == 2) load_xt_part(tile, std::integral_constant<int, 2>{});
-      else load_xt_part(tile, std::integral_constant<int, 3>{});
+    auto load_xt_half = [&](int tile, int h16) {
+      if (h16 == 0) load_xt_part(tile, std::integral_constant<int, 0>{});
+      else load_xt_part(tile, std::integral_constant<int, 1>{});
     };
     auto store_xt = [&](int pbuf) {
       if (q * 32 < G) {   // warp-uniform: this quadrant holds real feature lanes
-        // row factors of the 16 tile rows this thread touches: S_x (x d^1/2 for sym-norm); row = hf*64 + 16 rho + 4 (lane&3) + i
-        float rf[4][4];
+        // row factors of the 8 tile rows this thread touches: S_x (x d^1/2 for sym-norm); row = 32 qtr + 16 rho + 4 (lane&3) + i
+        float rf[2][4];
 #pragma unroll
-        for (int rho = 0; rho < 4; ++rho) {
+        for (int rho = 0; rho < 2; ++rho) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float f0 = s_x;
-            if (norm) {
-              const int row = hf * 64 + 16 * rho + 4 * (lane & 3) + i;
-              f0 *= dtab[256 + sdeg[(pbuf * 2 + 0) * L::ROWS + row] + sdeg[(pbuf * 2 + 1) * L::ROWS + row]];
-            }
+            if (norm) f0 *= dtab[256 + row_degree(sdeg, pbuf, qtr * 32 + 16 * rho + 4 * (lane & 3) + i)];
             rf[rho][i] = f0;
           }
         }
 #pragma unroll
         for (int h16 = 0; h16 < 2; ++h16) {
-          uint32_t p0[16], p1[16];
+          uint32_t p0[8], p1[8];
 #pragma unroll
-          for (int rho = 0; rho < 4; ++rho) {
+          for (int rho = 0; rho < 2; ++rho) {
 #pragma unroll
             for (int gs = 0; gs < 2; ++gs) {
-              const float* src = &xt[16 * (2 * h16 + (rho >> 1)) + 8 * (rho & 1) + 4 * gs];
+              const float* src = &xt[16 * h16 + 8 * rho + 4 * gs];
               const float a = src[0] * rf[rho][0], b = src[1] * rf[rho][1], c = src[2] * rf[rho][2], d = src[3] * rf[rho][3];
               if (NP == 2) {
                 tc5::split_f16x2(a, b, p0[4 * rho + 2 * gs], p1[4 * rho + 2 * gs]);
@@ -880,9 +937,9 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
               }
             }
           }
-          const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * h16) << 16) + L::TM_X + hf * 32;
-          tc5::tmem_st_16x256b_x4(ta, p0);
-          if (NP == 2) tc5::tmem_st_16x256b_x4(ta + 64, p1);
+          const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * h16) << 16) + L::TM_X + qtr * 16;
+          tc5::tmem_st_16x256b_x2(ta, p0);
+          if (NP == 2) tc5::tmem_st_16x256b_x2(ta + 64, p1);
         }
         tc5::tmem_st_wait();
       }
@@ -890,13 +947,14 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       __syncwarp();
       if (lane == 0) tc5::mbar_arrive(x_ready);
     };
-    // V_0 = dY o act'(y) of this CTA's feature slice: coalesced pieces -> registers (+ db), then planes
+    // V_0 = dY o act'(y) of this CTA's feature slice: coalesced pieces -> registers (+ db), then planes.
+    // Warp ww owns tile rows 8 ww .. 8 ww + 7.
     auto load_v0 = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
 #pragma unroll
-      for (int i = 0; i < FH / 8; ++i) {
-        const int row = 16 * ww + RPI * i + lane / PPR;
+      for (int i = 0; i < NPC; ++i) {
+        const int row = 8 * ww + RPI * i + lane / PPR;
         const bool ok = row < rows_used;
         const size_t off = ((size_t)b0 * N + row) * F + fh * FH + 4 * (lane % PPR);
         float4 v;
@@ -919,11 +977,11 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       const int pi = lane % PPR;
       const bool odd = pi & 1;
 #pragma unroll
-      for (int i = 0; i < FH / 8; ++i) {
+      for (int i = 0; i < NPC; ++i) {
         dbacc[0] += xin[4 * i]; dbacc[1] += xin[4 * i + 1]; dbacc[2] += xin[4 * i + 2]; dbacc[3] += xin[4 * i + 3];
       }
 #pragma unroll
-      for (int i = 0; i < FH / 8; i += 2) {
+      for (int i = 0; i < NPC; i += 2) {
         float snd[4], rcv[4], own[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -932,16 +990,16 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
-        const int row = 16 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+        const int row = 8 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
         float f0 = s_v;
-        if (norm) f0 *= dtab[sdeg[(pbuf * 2 + 0) * L::ROWS + row] + sdeg[(pbuf * 2 + 1) * L::ROWS + row]];
+        if (norm) f0 *= dtab[row_degree(sdeg, pbuf, row)];
         float v[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { v[e] = (odd ? rcv[e] : own[e]) * f0; v[4 + e] = (odd ? own[e] : rcv[e]) * f0; }
         store_chunk_f16<NP>(vbuf + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
       }
     };
-    // P[r][c] (smem, K-major A operand): chunks t0..t1-1 of the 8 this thread owns
+    // P[r][c] (smem, K-major A operand): slots t0..t1-1 of the 4 chunks (qc = 4 t + qtr) this thread owns
     int degcnt = 0;
     auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
       const float2* sp = sp_all + pbuf * L::ROWS;
@@ -952,18 +1010,18 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       if (r < w.gpc * N) {
 #pragma unroll 1
         for (int t = t0; t < t1; ++t) {
-          const int qc = 2 * t + hf;
+          const int qc = 4 * t + qtr;
           if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
             const uint32_t bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
             degcnt += __popc(bits);
             *reinterpret_cast<uint4*>(pb + qc * L::PW + r * 16) =
-                make_uint4(p_word(bits, 0), p_word(bits, 2), p_word(bits, 4), p_word(bits, 6));
+                make_uint4(p_word(bits, 0, pval), p_word(bits, 2, pval), p_word(bits, 4, pval), p_word(bits, 6, pval));
           }
         }
       }
     };
     auto publish_p = [&](int pbuf) {
-      sdeg[(pbuf * 2 + hf) * L::ROWS + r] = degcnt;
+      sdeg[(pbuf * 4 + qtr) * L::ROWS + r] = degcnt;
       degcnt = 0;
       publish(p_ready);
     };
@@ -981,8 +1039,8 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
 #pragma unroll 1
-          for (int cb = 0; cb < FH / 2; cb += 8) {
-            const int col = hf * (FH / 2) + cb;
+          for (int cb = 0; cb < FH / 4; cb += 8) {
+            const int col = qtr * (FH / 4) + cb;
             uint32_t v[8];
             tc5::tmem_ld8u(tm_lane + L::TM_ACC + k * FH + col, v);
             tc5::tmem_ld_wait();
@@ -1000,8 +1058,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 
     // One leading iteration (it == -1) prepares the first tile; afterwards iteration `it` serves tile `tile`
     // (write-backs) and prepares `next`.
-    int tile = t_begin, next = t_begin, it = -1, vbase = 0, n_items = 0;
-    (void)tile;
+    int next = t_begin, it = -1, vbase = 0, n_items = 0;
     if (next < t_end) load_pos(next);
     while (true) {
       const bool live = it >= 0;
@@ -1027,55 +1084,53 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         // next tile's V_0 pieces: requested two write-backs ahead of their use so that the (long) memory latency
         // overlaps the remaining taps of the live tile
         if (has_next && !v0_loaded && k + 2 >= nwb) { load_v0(next); v0_loaded = true; }
-        tc5::mbar_wait(hop_done, par_hd); par_hd ^= 1;
+        tc5::mbar_wait_suspend(hop_done, par_hd); par_hd ^= 1;
         tc5::fence_after_sync();
-        unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (hf * (L::CPT / 8)) * L::PW + r * 16;
-        const uint32_t taddr = tm_lane + TM_HOP + hf * L::CPT;
-#pragma unroll 1
+        unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (qtr * (L::CPT / 8)) * L::PW + r * 16;
+        const uint32_t taddr = tm_lane + TM_HOP + qtr * L::CPT;
+        uint32_t v[L::CPT];
+        if constexpr (L::CPT == 16) tc5::tmem_ld16(taddr, v); else tc5::tmem_ld8u(taddr, v);
+        tc5::tmem_ld_wait();
+#pragma unroll
         for (int c = 0; c < L::CPT / 8; ++c) {
-          uint32_t v[8];
-          tc5::tmem_ld8u(taddr + c * 8, v);
-          tc5::tmem_ld_wait();
           float f[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(v[i]) * wbf_live;
+          for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf_live : __uint_as_float(v[c * 8 + i]);
           store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
         }
         publish(v_ready);
         if (has_next) {
           if (K > 1 && k < 2) {
-            build_p_part(next, pbuf, 4 * k, 4 * k + 4);
+            build_p_part(next, pbuf, 2 * k, 2 * k + 2);
             if (k == 1 || nwb == 1) {
-              if (nwb == 1) build_p_part(next, pbuf, 4, 8);
+              if (nwb == 1) build_p_part(next, pbuf, 2, 4);
               publish_p(pbuf); p_done = true;
             }
           }
-          if (xt_slot < 2) load_xt_slot(next, xt_slot++);   // half of X^T early; the rest once V_0's registers are free
+          if (xt_slot < 1) load_xt_half(next, xt_slot++);   // half of X^T early; the rest once V_0's registers are free
         }
       }
       if (has_next) {
-        if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 8); publish_p(pbuf); }
+        if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 4); publish_p(pbuf); }
         if (norm) {   // every thread's partial degrees of `next` are visible after this barrier
           worker_bar();
-          const int d = sdeg[(pbuf * 2 + 0) * L::ROWS + r] + sdeg[(pbuf * 2 + 1) * L::ROWS + r];
-          wbf_next = hop_down * dtab[128 + d];
+          wbf_next = dtab[128 + row_degree(sdeg, pbuf, r)];
         }
         // V_0 of the next tile goes into the ring buffer after the live tile's last one (free: its last reader
         // was tap K-3 of the live tile, which completed before the hop result of tap K-2 was signalled)
         if (!v0_loaded) load_v0(next);
         store_v0(Vb + ((vbase + (live ? K : 0)) % 3) * L::VBUF, pbuf);
         publish(v0_ready);
-        while (xt_slot < 4) load_xt_slot(next, xt_slot++);   // latency hides behind the last tap's MMAs / the drain
+        while (xt_slot < 2) load_xt_half(next, xt_slot++);   // latency hides behind the last tap's MMAs / the drain
       }
       if (live) {
-        tc5::mbar_wait(item_done, par_id); par_id ^= 1;   // every dH product of the live tile has completed
+        tc5::mbar_wait_suspend(item_done, par_id); par_id ^= 1;   // every dH product of the live tile has completed
         ++n_items;
         if (!has_next || (n_items % w.flush_every) == 0) flush();
         vbase = (vbase + K) % 3;
       }
       if (has_next) store_xt(pbuf);
       if (!has_next) break;
-      tile = next;
       next += 1;
       ++it;
       wbf_live = wbf_next;

@@ -32,6 +32,7 @@ struct WideArgs {
   int act;
   float slope;
   int no_prefetch;         // experiment: skip the L2 bulk prefetch
+  long long* dbg;          // optional clock stamps of CTA 0 (issuer at [0..), worker warp 2 at [4096..)), else null
 };
 
 struct WideDhArgs {
