@@ -50,7 +50,7 @@ template <int CIN, int COUT, int NP>
 struct WideLayout {
   static constexpr int ROWS = 128;
   static constexpr int CS = CIN / 2;                 // channels per slab
-  static constexpr int CPT = CS / 4;                 // state columns per worker thread (4 column quarters)
+  static constexpr int CPT = CS / 2;                 // state columns per worker thread (2 column halves per TMEM lane quadrant)
   static constexpr int NCH = CS / 8;                 // 16-byte chunks (8 fp16) per row and slab
   static constexpr int PW = ROWS * 16;               // bytes between chunks (one chunk column of all rows)
   static constexpr int PLANE = NCH * PW;             // one fp16 plane of a slab
@@ -61,11 +61,11 @@ struct WideLayout {
   static constexpr int NSTAGE = 2;
   static constexpr int OFF_W = 0;                    // state planes: [slab][buffer] — double buffered, so the write-back of
   static constexpr int OFF_RING = OFF_W + 4 * SLAB;  //   W_{k+1} only waits for hop k, not for the taps that still read W_k
-  static constexpr int OFF_STAGE = (OFF_RING + NSTAGE * PHASE + 1023) / 1024 * 1024;   // TMA store staging buffer [128 rows x 32 cols] fp32, 128B swizzle
+  static constexpr int OFF_STAGE = (OFF_RING + NSTAGE * PHASE + 1023) / 1024 * 1024;   // TMA store staging: 8 warp-private slots [32 rows x 16 cols] fp32, 64B swizzle
   static constexpr int OFF_BIAS = OFF_STAGE + ROWS * 128;
   static constexpr int OFF_SP = OFF_BIAS + COUT * 4;         // float2 positions of the tile rows (two buffers, alternating per tile)
-  static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;      // int [2 buffers][4 quarters][128]: partial row degrees (sym-norm)
-  static constexpr int OFF_TAB = OFF_DEG + 2 * 4 * ROWS * 4; // float [3][128]: d^-1/2, 1/d, d^1/2 by degree
+  static constexpr int OFF_DEG = OFF_SP + 2 * ROWS * 8;      // int [2 buffers][2 halves][128]: partial row degrees (sym-norm)
+  static constexpr int OFF_TAB = OFF_DEG + 2 * 2 * ROWS * 4; // float [3][128]: d^-1/2, 1/d, d^1/2 by degree
   static constexpr int OFF_MAX = OFF_TAB + 3 * 128 * 4;      // uint [16]: per-warp tile maxima
   static constexpr int OFF_BAR = OFF_MAX + 64;
   static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 2 + 1 + 2 + 2;
@@ -80,18 +80,26 @@ struct WideLayout {
   static_assert(CPT % 8 == 0, "whole chunks per worker thread");
   static_assert(BYTES <= 227 * 1024, "shared memory");
 };
-// row degree of tile row `row` from the four partial counts
+// row degree of tile row `row` from the two partial counts (forward / dX kernel)
 __device__ __forceinline__ int row_degree(const int* sdeg, int pbuf, int row) {
+  const int* p = sdeg + pbuf * 2 * 128 + row;
+  return p[0] + p[128];
+}
+// dH kernel: four partial counts
+__device__ __forceinline__ int row_degree4(const int* sdeg, int pbuf, int row) {
   const int* p = sdeg + pbuf * 4 * 128 + row;
   return p[0] + p[128] + p[256] + p[384];
 }
 
-// warp 0: MMA issuer, warp 1: TMA producer + TMEM owner, warps 2..17: workers.  The workers' code (TMEM read-back,
-// plane split, pair tests) is a chain of dependent instructions; with 8 worker warps (2 per scheduler) the round-2
-// profile showed 36 % issue slots used at 7 cycles per issued instruction and the tensor pipe 32 % busy, so the
-// worker set is 16 warps (4 per scheduler, 4 column quarters per TMEM lane quadrant).
+// warp 0: MMA issuer, warp 1: TMA producer + TMEM owner, warps 2..17: workers.  Forward / dX kernel: the workers
+// are TWO groups of 8 warps (2 per TMEM lane quadrant each).  Group A only turns hop results into the next state
+// planes — the one piece of CUDA-core work that sits between two MMAs of a chain; group B prepares the next tile
+// (positions, P, tile scale, W_0) and stores the previous tile's output.  With one worker set doing everything in
+// turn (round-2 timeline, tools/wide_clocks.py) a write-back queued behind ~2000-cycle epilogue pieces and the issuer
+// waited ~11k of every 20k cycles per tile.  The dH kernel still uses all 16 warps as one set.
 constexpr int kWideThreads = 576;
 constexpr int kWorkerWarps = 16;
+constexpr int kGroupWarps = 8;
 int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
 int g_wide_no_prefetch = 0;    // experiment switch
 
@@ -168,6 +176,9 @@ __device__ __forceinline__ float ldg_cg(const float* p) {
   return v;
 }
 __device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+__device__ __forceinline__ void group_b_bar() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+struct WideMaps { CUtensorMap m[3]; };   // y store boxes: 32 rows / the partial third / the partial fourth row quadrant of a tile
 
 // act(v) = v > 0 ? v : v * neg   (neg: 1 none, 0 relu, slope leaky) == max(v, v neg) for neg <= 1, min(v, v neg) otherwise
 __device__ __forceinline__ float act_fast(float v, float neg, bool use_min) {
@@ -196,7 +207,7 @@ __device__ __forceinline__ void fill_degree_tables(float* tab, int tid, int nthr
 //            p_ready, out_full[2], out_free[2] as before (P and OUT double buffered across tiles)
 template <int CIN, int COUT, int MODE, int NP>
 __global__ void __launch_bounds__(kWideThreads, 1)
-tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUtensorMap tmap_out) {
+tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ WideMaps maps) {
   using L = WideLayout<CIN, COUT, NP>;
   extern __shared__ __align__(128) unsigned char wsmem[];
   unsigned char* Wb = wsmem + L::OFF_W;
@@ -233,13 +244,13 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
   if (tid == 0) {
     for (int i = 0; i < L::NSTAGE; ++i) { tc5::mbar_init(&h_full[i], 1); tc5::mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      tc5::mbar_init(&w_ready[i], kWorkerWarps);
+      tc5::mbar_init(&w_ready[i], kGroupWarps);    // W_0 by group B, W_k (k >= 1) by group A
       tc5::mbar_init(&hop_done[i], 1);
       tc5::mbar_init(&w0_free[i], 1);
       tc5::mbar_init(&out_full[i], 1);
-      tc5::mbar_init(&out_free[i], kWorkerWarps);
+      tc5::mbar_init(&out_free[i], kGroupWarps);
     }
-    tc5::mbar_init(p_ready, kWorkerWarps);
+    tc5::mbar_init(p_ready, kGroupWarps);
     tc5::fence_mbar_init();
   }
   if (warp == 1) tc5::tmem_alloc(tmem_ptr, L::TM_COLS);
@@ -258,7 +269,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       constexpr uint32_t kIdescTap = tc5::idesc_f16(128, COUT, 0, 0);
       constexpr uint32_t kIdescHop = tc5::idesc_f16(128, L::CS, 0, 1);
       const uint32_t w_addr = tc5::smem_u32(Wb), r_addr = tc5::smem_u32(Rb);
-      uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0, wbuf = 0;
+      uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0;
       int st = 0;
       const int hop_ksteps = (w.gpc * N + 15) >> 4;
       int it = 0;
@@ -282,8 +293,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
           tc5::mbar_wait(&w_ready[s], (par_wr >> s) & 1); par_wr ^= 1u << s;
           tc5::fence_after_sync();
           GFC_WSTAMP(200 + ph);
-          const uint32_t ws = w_addr + (2 * s + ((wbuf >> s) & 1)) * L::SLAB;
-          wbuf ^= 1u << s;
+          const uint32_t ws = w_addr + (2 * s + ((it * K + k) & 1)) * L::SLAB;   // state k of a slab alternates between two buffers
           if (k + 1 < K) {
             // hop: D_hop[s] = P * W_k[slab s]   (A = P from tensor memory, B = state planes MN-major)
             const uint32_t d_hop = tmem + L::TM_HOP + s * L::CS;
@@ -358,13 +368,63 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       }
     }
     __syncwarp();
-  } else {
-    // =========================== workers ======================================================
-    const int wt = tid - 64;                 // 0..511
-    const int ww = warp - 2;                 // 0..15
+  } else if (warp < 2 + kGroupWarps) {
+    // =========================== group A: write-backs of the hop chain ==========================
+    // The only per-phase work between two MMAs of a chain: hop result (TMEM, exact fp32, already in the units of
+    // W_{k+1}) -> fp16 planes of W_{k+1}[slab s].  These warps do nothing else, so the chain never queues behind the
+    // next tile's preparation or the previous tile's epilogue (group B).
+    const int gw = warp - 2;                 // 0..7
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int qtr = ww >> 2;                 // which quarter of a slab's columns
+    const int half = gw >> 2;                // which half of a slab's columns
     const int r = q * 32 + lane;             // tile row owned by this thread (= its TMEM lane)
+    const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t par_hd = 0;
+    int nstamp = 0;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+#ifdef GFC_WIDE_TIMELINE
+#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[4096 + 2 * nstamp] = clock64(); w.dbg[4096 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#else
+#define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
+#endif
+    int it = 0;
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      float wbf = 1.f;
+#pragma unroll 1
+      for (int slot = 0; slot < 2 * (K - 1); ++slot) {
+        const int s = slot & 1, k1 = (slot >> 1) + 1;   // this write-back produces W_{k1}[s]
+        GFC_KSTAMP(100 + slot);
+        tc5::mbar_wait_suspend(&hop_done[s], (par_hd >> s) & 1); par_hd ^= 1u << s;
+        tc5::fence_after_sync();
+        GFC_KSTAMP(200 + slot);
+        // sym-norm: What_{k+1} = D^-1 (A What_k); the degrees of this tile were published by group B with its P
+        if (norm && slot == 0) wbf = dtab[128 + row_degree(sdeg, it & 1, r)];
+        const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + half * L::CPT;
+        unsigned char* base = Wb + (2 * s + ((it * K + k1) & 1)) * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
+        uint32_t v[L::CPT];
+        if constexpr (L::CPT == 32) tc5::tmem_ld32(taddr, v); else tc5::tmem_ld16(taddr, v);
+        tc5::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < L::CPT / 8; ++c) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf : __uint_as_float(v[c * 8 + i]);
+          store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
+        }
+        tc5::fence_proxy_async();
+        tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(&w_ready[s]);
+        GFC_KSTAMP(300 + slot);
+      }
+    }
+#undef GFC_KSTAMP
+  } else {
+    // =========================== group B: next tile's operands, previous tile's epilogue ==========
+    const int gw = warp - (2 + kGroupWarps); // 0..7
+    const int wt = tid - 32 * (2 + kGroupWarps);   // 0..255
+    const int q = warp & 3;
+    const int half = gw >> 2;
+    const int r = q * 32 + lane;
     const int jr = r / N, nr = r - jr * N;   // (graph, node) of the row
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     const float inv_th = __ldg(reinterpret_cast<const float*>(w.hpack));   // 1 / (tap scale)
@@ -372,17 +432,20 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
     const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;
     const float act_neg = w.act == GFC_ACT_NONE ? 1.f : (w.act == GFC_ACT_RELU ? 0.f : w.slope);
     const bool act_min = act_neg > 1.f;
-    float xin0[L::CPT], xin1[L::CPT];
+    // y store: this warp's 32 rows x 16 columns at a time through a private 2 KB staging slot (64-byte rows, 64B
+    // swizzle) and its own TMA store — no barrier with any other warp.  A quadrant holding fewer than 32 real rows
+    // (gpc N < 128) uses a tensor map with a shorter box.
+    unsigned char* slot_out = stage_out + gw * 2048;
+    const int hq = min(32, max(0, w.gpc * N - 32 * q));
+    const CUtensorMap* my_map = hq == 32 ? &maps.m[0] : (q == 2 ? &maps.m[1] : &maps.m[2]);
+    float xin[L::CPT];
     float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_hd = 0, par_ofl = 0, par_w0 = 0, wbuf = 0;
-    // per-tile scalars: of the tile whose epilogue is pending (prev), of the LIVE tile (its MMAs run) and of the
-    // NEXT one (being prepared)
-    float inv_prev = 1.f, inv_live = 1.f, wbf_live = 1.f;
-    float scale_next = 1.f, inv_next = 1.f, wbf_next = 1.f, rowf_next = 1.f;
+    uint32_t par_ofl = 0, par_w0 = 0;
+    float inv_prev = 1.f, inv_next = 1.f, scale_next = 1.f, rowf_next = 1.f;
     int nstamp = 0;
-    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && wt == 0;
 #ifdef GFC_WIDE_TIMELINE
-#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[4096 + 2 * nstamp] = clock64(); w.dbg[4096 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[8192 + 2 * nstamp] = clock64(); w.dbg[8192 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
 #else
 #define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
 #endif
@@ -395,16 +458,16 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
                                   : make_float2(0.f, 0.f);
     };
     // MODE 1 / 2: dY / y are row-major [rows x CIN]: a warp instruction reads whole 16-byte pieces of RPI consecutive
-    // rows (4 full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle at
-    // store time.  Warp ww owns rows 8 ww .. 8 ww + 7, lane = (row offset, piece).
+    // rows (full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle at
+    // store time.  Warp gw owns rows 16 gw .. 16 gw + 15, lane = (row offset, piece).
     constexpr int PPR = L::CS / 4, RPI = 32 / PPR, NPC = L::CPT / 4;   // pieces per row, rows per instruction, pieces per thread
-    static_assert(NPC % 2 == 0 && RPI * NPC == 8, "piece mapping");
-    auto load_slab = [&](int tile, int s, float (&xin)[L::CPT]) {
+    static_assert(NPC % 2 == 0 && RPI * NPC == 16, "piece mapping");
+    auto load_slab = [&](int tile, int s) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
       if (MODE == 0) {
         const bool valid = r < gcount * N;
-        const int c0 = s * L::CS + qtr * L::CPT;
+        const int c0 = s * L::CS + half * L::CPT;
         const float* src = w.in + ((size_t)(b0 + jr) * CIN + c0) * N + nr;
 #pragma unroll
         for (int i = 0; i < L::CPT; ++i) { xin[i] = ldg_f32(src, valid); src += N; }
@@ -412,7 +475,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         const int rows_used = gcount * N;
 #pragma unroll
         for (int i = 0; i < NPC; ++i) {
-          const int row = 8 * ww + RPI * i + lane / PPR;
+          const int row = 16 * gw + RPI * i + lane / PPR;
           const bool ok = row < rows_used;
           const size_t off = ((size_t)b0 * N + row) * CIN + s * L::CS + 4 * (lane % PPR);
           float4 v = ldg_f32x4(w.in + off, ok);
@@ -430,9 +493,9 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
       }
     };
     // registers of load_slab -> the fp16 planes of W_0[slab s] (scaled by the tile scale, D^-1/2 for sym-norm)
-    auto store_slab = [&](int s, const float (&xin)[L::CPT], int pbuf, unsigned char* Ws) {
+    auto store_slab = [&](int pbuf, unsigned char* Ws) {
       if (MODE == 0) {
-        unsigned char* base = Ws + (qtr * (L::CPT / 8)) * L::PW + r * 16;
+        unsigned char* base = Ws + (half * (L::CPT / 8)) * L::PW + r * 16;
         const float f0 = scale_next * rowf_next;   // rowf_next = d^-1/2 of this thread's row (1 when not normalised)
 #pragma unroll
         for (int c = 0; c < L::CPT / 8; ++c) {
@@ -455,7 +518,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
           }
 #pragma unroll
           for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
-          const int row = 8 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+          const int row = 16 * gw + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
           float f0 = scale_next;
           if (norm) f0 *= dtab[row_degree(sdeg, pbuf, row)];
           float v[8];
@@ -465,213 +528,157 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ CUte
         }
       }
     };
-    auto publish = [&](uint64_t* bar) {   // this warp's shared-memory writes -> tensor core, then arrive
-      tc5::fence_proxy_async();
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(bar);
-    };
-    // buffer of slab s that the next state of the slab goes into; toggles with every state written
-    auto next_wbuf = [&](int s) -> unsigned char* {
-      unsigned char* p = Wb + (2 * s + ((wbuf >> s) & 1)) * L::SLAB;
-      wbuf ^= 1u << s;
-      return p;
-    };
-
     // P[r][c] = 2^-c iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
-    // TMEM lane r; the four warps of a quadrant take every fourth chunk of 8 source rows (balanced for any N).
-    // Slots t0..t1-1 of the 4 this thread owns.
-    int degcnt = 0;
-    auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
+    // TMEM lane r; the two warps of a quadrant take every second chunk of 8 source rows (balanced for any N).
+    auto build_p = [&](int tile, int pbuf) {
       const float2* sp = sp_all + pbuf * L::ROWS;
       const int gcount = min(w.gpc, w.B - tile * w.gpc);
       const int rows_used = gcount * N;
       const int c_lo = jr * N, c_hi = c_lo + N;
       const float2 me = sp[r];
       const bool row_ok = r < w.gpc * N;
+      int degcnt = 0;
+      if (K > 1) {
 #pragma unroll 1
-      for (int t = t0; t < t1; ++t) {
-        const int qc = 4 * t + qtr;   // chunk of 8 source rows = 4 TMEM columns
-        uint32_t bits = 0;
-        if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
-          bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
-        degcnt += __popc(bits);
-        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0, pval), p_word(bits, 2, pval),
-                      p_word(bits, 4, pval), p_word(bits, 6, pval));
+        for (int t = 0; t < 8; ++t) {
+          const int qc = 2 * t + half;   // chunk of 8 source rows = 4 TMEM columns
+          uint32_t bits = 0;
+          if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
+            bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+          degcnt += __popc(bits);
+          tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0, pval), p_word(bits, 2, pval),
+                        p_word(bits, 4, pval), p_word(bits, 6, pval));
+        }
       }
-    };
-    auto publish_p = [&](int pbuf) {
-      sdeg[(pbuf * 4 + qtr) * L::ROWS + r] = degcnt;   // read after the tile-maximum barrier below
-      degcnt = 0;
+      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;   // read after the tile-maximum barrier (B) / the first hop (A)
       tc5::tmem_st_wait();
       tc5::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc5::mbar_arrive(p_ready);
     };
-
-    // Epilogue of a finished tile, one piece per call so that it can be interleaved with the write-backs of the tile
-    // that follows (OUT is double buffered).  MODE 0/2: piece = 32 output columns through the swizzled staging buffer
-    // and the TMA store engine (full 128-byte lines); MODE 1: piece = 16 columns of dX per thread, coalesced over n.
-    constexpr int kEpiPieces = (MODE != 1) ? COUT / 32 : COUT / 64;
-    int epi_tile = -1, epi_piece = 0, epi_ob = 0;   // pending epilogue (epi_tile < 0: none)
-    auto epilogue_piece = [&]() {
-      const int b0 = epi_tile * w.gpc;
-      if (epi_piece == 0) {
-        tc5::mbar_wait_suspend(&out_full[epi_ob], (par_ofl >> epi_ob) & 1); par_ofl ^= 1u << epi_ob;
-        tc5::fence_after_sync();
-        GFC_KSTAMP(500);
+    // upper bound of the tile's |operand| -> power-of-two scale.  One flat pass over the (L2-prefetched) tile; the
+    // values are read again, slab by slab, when W_0 is formed — holding the whole tile in registers across the
+    // epilogue would cost 64 registers per thread.
+    auto tile_max = [&](int tile) -> float {
+      const int b0 = tile * w.gpc;
+      const int gcount = min(w.gpc, w.B - b0);
+      const float4* p = reinterpret_cast<const float4*>(w.in + (size_t)b0 * N * CIN);
+      const int n4 = gcount * N * (CIN / 4);
+      float m = 0.f;
+#pragma unroll 4
+      for (int i = wt; i < n4; i += 32 * kGroupWarps) {
+        const float4 v = __ldg(p + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
       }
-      const int pc = epi_piece;
-      if constexpr (MODE != 1) {
-        const int col = pc * 32 + qtr * 8;
-        uint32_t v[8];
-        tc5::tmem_ld8u(tm_lane + L::TM_OUT + epi_ob * COUT + col, v);
-        tc5::tmem_ld_wait();
-        unsigned char* srow = stage_out + r * 128;
-        // the TMA store of the previous piece has finished reading the staging buffer
-        if (wt == 0) tc5::tma_store_wait_read();
-        worker_bar();
-#pragma unroll
-        for (int i4 = 0; i4 < 2; ++i4) {
-          const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i4 * 4);
-          float4 o;
-          o.x = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 0]), inv_prev, bb.x), act_neg, act_min);
-          o.y = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 1]), inv_prev, bb.y), act_neg, act_min);
-          o.z = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 2]), inv_prev, bb.z), act_neg, act_min);
-          o.w = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 3]), inv_prev, bb.w), act_neg, act_min);
-          const int cc = qtr * 2 + i4;
-          *reinterpret_cast<float4*>(srow + ((cc ^ (r & 7)) << 4)) = o;
-        }
-        tc5::fence_proxy_async();
-        worker_bar();
-        if (wt == 0) {
-          tc5::tma_store_2d(&tmap_out, stage_out, pc * 32, b0 * N);
-          tc5::tma_store_commit();
-        }
-      } else {
-        // dX[(b0 + j), g, n]: lanes = consecutive nodes n, one coalesced store per channel
-        const int rows_used = min(w.gpc, w.B - b0) * N;
-        const int col = qtr * (COUT / 4) + pc * 16;
+      if (MODE == 1 && w.act == GFC_ACT_LEAKY_RELU && w.slope > 1.f) m *= w.slope;   // |dY o act'(y)| <= |dY| max(1, slope)
+      return m;
+    };
+    // Epilogue of a finished tile: this warp's 32 rows x COUT/2 columns.
+    auto epilogue = [&](int tile, int ob, float inv) {
+      const int b0 = tile * w.gpc;
+      tc5::mbar_wait_suspend(&out_full[ob], (par_ofl >> ob) & 1); par_ofl ^= 1u << ob;
+      tc5::fence_after_sync();
+      GFC_KSTAMP(500);
+#pragma unroll 1
+      for (int pc = 0; pc < COUT / 32; ++pc) {
+        const int col = half * (COUT / 2) + pc * 16;
         uint32_t v[16];
-        tc5::tmem_ld16(tm_lane + L::TM_OUT + epi_ob * COUT + col, v);
+        tc5::tmem_ld16(tm_lane + L::TM_OUT + ob * COUT + col, v);
         tc5::tmem_ld_wait();
-        if (r < rows_used) {
-          float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
+        if constexpr (MODE != 1) {
+          float4 o[4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]) * inv_prev;
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 bb = *reinterpret_cast<const float4*>(sbias + col + i4 * 4);
+            o[i4].x = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 0]), inv, bb.x), act_neg, act_min);
+            o[i4].y = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 1]), inv, bb.y), act_neg, act_min);
+            o[i4].z = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 2]), inv, bb.z), act_neg, act_min);
+            o[i4].w = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 3]), inv, bb.w), act_neg, act_min);
+          }
+          // the TMA store of the previous piece has finished reading the staging slot
+          if (lane == 0) tc5::tma_store_wait_read();
+          __syncwarp();
+          unsigned char* srow = slot_out + lane * 64;
+          const int sw = (lane >> 1) & 3;
+#pragma unroll
+          for (int i4 = 0; i4 < 4; ++i4) *reinterpret_cast<float4*>(srow + ((i4 ^ sw) << 4)) = o[i4];
+          tc5::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && hq > 0) {
+            tc5::tma_store_2d(my_map, slot_out, col, b0 * N + q * 32);
+            tc5::tma_store_commit();
+          }
+        } else {
+          // dX[(b0 + j), g, n]: lanes = consecutive nodes n, one coalesced store per channel
+          const int rows_used = min(w.gpc, w.B - b0) * N;
+          if (r < rows_used) {
+            float* dst = w.out + ((size_t)(b0 + jr) * COUT + col) * N + nr;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dst[(size_t)i * N] = __uint_as_float(v[i]) * inv;
+          }
         }
       }
-      if (++epi_piece == kEpiPieces) {
-        tc5::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc5::mbar_arrive(&out_free[epi_ob]);
-        epi_tile = -1;
-        GFC_KSTAMP(501);
-      }
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(&out_free[ob]);
+      GFC_KSTAMP(501);
     };
 
-    // The loop runs once per tile, plus one leading iteration (no live tile: it only prepares the first tile's
-    // operands) and one trailing iteration (no live tile, no next tile: it drains the last epilogue), so that every
-    // piece of per-tile code exists at exactly ONE place in the binary — the kernel has to stay inside the
-    // instruction cache, each role runs its code once per tile.  An iteration is a sequence of slots; slot i does the
-    // write-back of phase i, one half of the next tile's P, and one piece of the previous tile's epilogue.
-    int tile = t_begin;               // tile whose MMAs run during this iteration (if live)
-    int it = -1;
-    bool live = false;
-    int next = t_begin;
+    // Iteration j: prepare tile j (positions, P, scale), store its W_0 as soon as the running tile j-1 has released
+    // the buffers, then run the epilogue of tile j-1.  Every piece of per-tile code exists at exactly one place.
+    int next = t_begin, itn = 0;
+    int epi_tile = -1, epi_ob = 0;
     if (next < t_end) load_pos(next);
     while (true) {
       const bool has_next = next < t_end;
-      if (!live && !has_next && epi_tile < 0) break;
-      const int pbuf = (it + 1) & 1;
+      if (!has_next && epi_tile < 0) break;
       if (has_next) {
+        const int pbuf = itn & 1;
         if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;   // positions of `next` (loaded one tile ahead)
-        worker_bar();
+        group_b_bar();
         if (next + 1 < t_end) load_pos(next + 1);
-      }
-      const int nwb = live ? 2 * (K - 1) : 0;
-      const int p_slots = (has_next && K > 1) ? 2 : 0;
-      const int nslots = max(max(nwb, p_slots), has_next ? 1 : 0);
-      const int load_slot = max(nwb - 2, 0);        // inputs of the next tile: requested two write-backs before their use
-      const int pub_slot = max(p_slots, 1) - 1;
-#pragma unroll 1
-      for (int slot = 0; slot < nslots || epi_tile >= 0; ++slot) {
-        if (has_next && slot == load_slot) { load_slab(next, 0, xin0); load_slab(next, 1, xin1); }
-        if (slot < nwb) {
-          const int s = slot & 1;
-          GFC_KSTAMP(100 + slot);
-          tc5::mbar_wait_suspend(&hop_done[s], (par_hd >> s) & 1); par_hd ^= 1u << s;
-          tc5::fence_after_sync();
-          GFC_KSTAMP(200 + slot);
-          // hop result (exact fp32, already in the units of W_{k+1}) -> fp16 planes of W_{k+1}[slab s]; all of this
-          // thread's columns are read with ONE tcgen05.ld so that the chunks' split chains overlap
-          const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + qtr * L::CPT;
-          unsigned char* base = next_wbuf(s) + (qtr * (L::CPT / 8)) * L::PW + r * 16;
-          uint32_t v[L::CPT];
-          if constexpr (L::CPT == 16) tc5::tmem_ld16(taddr, v); else tc5::tmem_ld8u(taddr, v);
-          tc5::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < L::CPT / 8; ++c) {
-            float f[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf_live : __uint_as_float(v[c * 8 + i]);
-            store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
-          }
-          publish(&w_ready[s]);
-          GFC_KSTAMP(300 + slot);
-        }
-        if (slot < p_slots) build_p_part(next, pbuf, 2 * slot, 2 * slot + 2);
-        if (has_next && slot == pub_slot) publish_p(pbuf);
-        if (epi_tile >= 0) epilogue_piece();
-      }
-      GFC_KSTAMP(400);
-      // ---- next tile: tile maximum -> power-of-two scale, then its state W_0 ------------------------------------
-      if (has_next) {
-        float m = 0.f;
-#pragma unroll
-        for (int i = 0; i < L::CPT; ++i) m = fmaxf(m, fmaxf(fabsf(xin0[i]), fabsf(xin1[i])));
+        build_p(next, pbuf);
+        GFC_KSTAMP(430);
+        // ---- tile maximum -> power-of-two scale ------------------------------------------------------------------
+        const float m = tile_max(next);
         const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like uints
-        if (lane == 0) smax[ww] = mw;
-        worker_bar();
+        if (lane == 0) smax[gw] = mw;
+        group_b_bar();
         uint32_t mt = smax[0];
 #pragma unroll
-        for (int i = 1; i < kWorkerWarps; ++i) mt = max(mt, smax[i]);
+        for (int i = 1; i < kGroupWarps; ++i) mt = max(mt, smax[i]);
         if (w.amax && wt == 0) atomicMax(reinterpret_cast<unsigned int*>(w.amax) + (MODE == 1 ? 1 : 0), mt);
         scale_next = tc5::pow2_scale(mt, kWideTop, &inv_next);
-        wbf_next = 1.f; rowf_next = 1.f;
-        if (norm) {   // K > 1: the degrees of `next` were stored by publish_p before the barrier above
+        rowf_next = 1.f;
+        if (norm) {   // the degrees of `next` were stored by build_p before the barrier above
           const int d = row_degree(sdeg, pbuf, r);
-          rowf_next = dtab[d]; wbf_next = dtab[128 + d];
+          rowf_next = dtab[d];
           inv_next *= dtab[256 + d];   // epilogue factor of this thread's row: 1/s x d^1/2
         }
         inv_next *= inv_th;
-      }
-      GFC_KSTAMP(401);
-      // slab s of W_0 goes into the buffer that held W_{K-2}[s] of the live tile (free once taps(K-2,s) completed;
-      // K = 1: the buffer was read by the taps of the tile before the live one, whose epilogue — drained in the slot
-      // loop above — waited for that tile's out_full)
+        GFC_KSTAMP(401);
+        // slab s of W_0 goes into the buffer that held W_{K-2}[s] of the running tile (free once taps(K-2,s) completed;
+        // K = 1: the buffer was read by the taps of the tile before the running one, whose epilogue — run in the
+        // previous iteration — waited for that tile's out_full)
 #pragma unroll 1
-      for (int s = 0; s < 2; ++s) {
-        if (live && K >= 2) { tc5::mbar_wait_suspend(&w0_free[s], (par_w0 >> s) & 1); par_w0 ^= 1u << s; }
-        GFC_KSTAMP(410 + s);
-        if (has_next) {
-          unsigned char* Ws = next_wbuf(s);
-          if (s == 0) store_slab(0, xin0, pbuf, Ws); else store_slab(1, xin1, pbuf, Ws);
-          publish(&w_ready[s]);
+        for (int s = 0; s < 2; ++s) {
+          load_slab(next, s);
+          if (itn >= 1 && K >= 2) { tc5::mbar_wait_suspend(&w0_free[s], (par_w0 >> s) & 1); par_w0 ^= 1u << s; }
+          GFC_KSTAMP(410 + s);
+          store_slab(pbuf, Wb + (2 * s + ((itn * K) & 1)) * L::SLAB);
+          tc5::fence_proxy_async();
+          tc5::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc5::mbar_arrive(&w_ready[s]);
+          GFC_KSTAMP(420 + s);
         }
-        GFC_KSTAMP(420 + s);
       }
-      if (live) { epi_tile = tile; epi_piece = 0; epi_ob = it & 1; inv_prev = inv_live; }   // queue the live tile's epilogue
-      live = has_next;
-      if (has_next) {
-        tile = next;
-        next += 1;
-        ++it;
-        inv_live = inv_next; wbf_live = wbf_next;
-      }
+      if (epi_tile >= 0) { epilogue(epi_tile, epi_ob, inv_prev); epi_tile = -1; }
+      if (has_next) { epi_tile = next; epi_ob = itn & 1; inv_prev = inv_next; ++next; ++itn; }
     }
+    if (MODE != 1 && lane == 0) tc5::tma_store_wait_all();
+#undef GFC_KSTAMP
   }
-  if (tid == 64) tc5::tma_store_wait_all();
   tc5::fence_before_sync();
   __syncthreads();
   if (warp == 1) tc5::tmem_dealloc(tmem, L::TM_COLS);
@@ -915,7 +922,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float f0 = s_x;
-            if (norm) f0 *= dtab[256 + row_degree(sdeg, pbuf, qtr * 32 + 16 * rho + 4 * (lane & 3) + i)];
+            if (norm) f0 *= dtab[256 + row_degree4(sdeg, pbuf, qtr * 32 + 16 * rho + 4 * (lane & 3) + i)];
             rf[rho][i] = f0;
           }
         }
@@ -992,7 +999,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
         const int row = 8 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
         float f0 = s_v;
-        if (norm) f0 *= dtab[row_degree(sdeg, pbuf, row)];
+        if (norm) f0 *= dtab[row_degree4(sdeg, pbuf, row)];
         float v[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { v[e] = (odd ? rcv[e] : own[e]) * f0; v[4 + e] = (odd ? own[e] : rcv[e]) * f0; }
@@ -1114,7 +1121,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 4); publish_p(pbuf); }
         if (norm) {   // every thread's partial degrees of `next` are visible after this barrier
           worker_bar();
-          wbf_next = dtab[128 + row_degree(sdeg, pbuf, r)];
+          wbf_next = dtab[128 + row_degree4(sdeg, pbuf, r)];
         }
         // V_0 of the next tile goes into the ring buffer after the live tile's last one (free: its last reader
         // was tap K-3 of the live tile, which completed before the hop result of tap K-2 was signalled)
@@ -1253,7 +1260,7 @@ size_t wide_pack_bytes(int G, int F, int K) { return align_up((size_t)kPackHeade
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
 static int encode_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint32_t box_inner,
-                          uint32_t box_outer) {
+                          uint32_t box_outer, CUtensorMapSwizzle swz) {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
   if (!fn) {
     void* p = nullptr;
@@ -1267,7 +1274,7 @@ static int encode_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uin
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   GFC_REQUIRE(r == CUDA_SUCCESS, GFC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return GFC_OK;
@@ -1277,11 +1284,17 @@ template <int CIN, int COUT, int MODE, int NP>
 static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   using L = WideLayout<CIN, COUT, NP>;
   WideArgs a = a0;
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
-  if (MODE != 1) {   // y viewed as [B*N rows, COUT cols]; one box = [gpc*N rows x 32 cols]
-    int rc = encode_tmap_2d(&tmap, a.out, COUT, (uint64_t)a.B * a.N, 32, (uint32_t)(a.gpc * a.N));
-    if (rc) return rc;
+  WideMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if (MODE != 1) {   // y viewed as [B*N rows, COUT cols]; a box = one warp's [32 rows x 16 cols] (shorter in a partial row quadrant)
+    const int rows_full = a.gpc * a.N;
+    for (int i = 0; i < 3; ++i) {
+      int h = i == 0 ? 32 : rows_full - 32 * (i + 1);
+      h = h > 32 ? 32 : h;
+      if (h <= 0) continue;
+      int rc = encode_tmap_2d(&maps.m[i], a.out, COUT, (uint64_t)a.B * a.N, 16, (uint32_t)h, CU_TENSOR_MAP_SWIZZLE_64B);
+      if (rc) return rc;
+    }
   }
   auto kern = tc5_wide_kernel<CIN, COUT, MODE, NP>;
   GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
@@ -1289,7 +1302,7 @@ static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   int rc = get_device_info(&di);
   if (rc) return rc;
   const int grid = a.ntiles < di.sm_count ? a.ntiles : di.sm_count;
-  kern<<<grid, kWideThreads, L::BYTES, st>>>(a, tmap);
+  kern<<<grid, kWideThreads, L::BYTES, st>>>(a, maps);
   GFC_LAUNCH_CHECK(MODE == 0 ? "tc5_wide_kernel<fwd>" : MODE == 1 ? "tc5_wide_kernel<dX>" : "tc5_wide_kernel<fwd,node-major in>");
   return GFC_OK;
 }

@@ -292,6 +292,56 @@ def filter_goldens():
                         **run_ref_filter(gml, h, b, S, x, dOut, True))
 
 
+def model_goldens():
+    """The reference policy ``DecentralPlannerNet`` (graphs/models/suhaas_model.py) executed end to end on CPU, as
+    ``suhaas_agent.py:115-128`` drives it (``model.addGSO(S)``; ``model(inputs, refs, alphas)``; summed MSE loss;
+    ``backward``).  Stored: what goes into and comes out of its graph-filter stage ``self.GFL``
+    (suhaas_model.py:112-123,182-185) — the only part the drop-in replaces — plus the gradients autograd hands to and
+    takes from that stage.  The CNN / MLP weights (2.5 M parameters) are not stored: the stage's input is."""
+    Net = ri.decentral_planner_net()
+    for tag, nA, B, seed in (("n3", 3, 16, 11), ("n8", 8, 4, 12)):
+        torch.manual_seed(seed)
+        rng = np.random.default_rng(seed)
+        model = Net(nA=nA).double()      # the agent runs the model in double (suhaas_agent.py / forward :169)
+        model.device = "cpu"
+        model.train()
+        frames = load_frames("positionList_expert_%d.npy" % nA, nA)
+        idx = rng.choice(len(frames), B, replace=False)
+        S = torch.from_numpy(ref_binary(frames[idx], 2).astype(np.float64))          # [B,N,N] as custom_dataset hands it over
+        inputs = torch.rand(B, nA, 100, 100, dtype=torch.float64)
+        refs = torch.rand(B, nA, 1, dtype=torch.float64)
+        alphas = torch.rand(B, nA, 1, dtype=torch.float64)
+        actions = torch.randn(B, nA, 2, dtype=torch.float64)
+        cap = {}
+
+        def pre_hook(mod, args):
+            x = args[0]
+            x.retain_grad()
+            cap["x"] = x
+
+        def post_hook(mod, args, out):
+            out.retain_grad()
+            cap["y"] = out
+
+        h1 = model.GFL.register_forward_pre_hook(pre_hook)
+        h2 = model.GFL.register_forward_hook(post_hook)
+        model.addGSO(S)
+        outs = model(inputs, refs, alphas)
+        crit = torch.nn.MSELoss()
+        loss = crit(outs[0], actions[:, 0])
+        for i in range(1, nA):
+            loss = loss + crit(outs[i], actions[:, i])
+        loss.backward()
+        h1.remove(); h2.remove()
+        gf = model.GFL[0]
+        np.savez_compressed(os.path.join(OUT, "model_gfl_%s.npz" % tag),
+                            S=S.numpy().astype(np.float32), x=cap["x"].detach().numpy(),
+                            h=gf.weight.detach().numpy(), b=gf.bias.detach().numpy(),
+                            y=cap["y"].detach().numpy(), dOut=cap["y"].grad.numpy(),
+                            dX=cap["x"].grad.numpy(), dH=gf.weight.grad.numpy(), db=gf.bias.grad.numpy(),
+                            loss=float(loss), slope=0.01)
+
+
 if __name__ == "__main__":
     assert ri.available(), "run in the build container (needs /root/reference)"
     os.makedirs(OUT, exist_ok=True)
@@ -300,5 +350,6 @@ if __name__ == "__main__":
     same_gso_goldens()
     batch_gso_goldens()
     relu_golden()
+    model_goldens()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

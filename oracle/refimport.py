@@ -83,3 +83,34 @@ def fixed_radius_gso(agent_pos, radius, zero_tol=1e-9):
     W, _r, conn = mod.multiRobotSim.computeAdjacencyMatrix_fixedCommRadius(
         fake_self, 0, agent_pos, radius)
     return W, conn
+
+
+def decentral_planner_net(gml_module=None):
+    """The reference policy class ``DecentralPlannerNet`` (graphs/models/suhaas_model.py:12-259).
+
+    With ``gml_module`` the reference file is executed with ITS OWN ``import utils.graphUtils.graphML as gml``
+    resolving to that module instead — the one-line swap of INTEGRATION.md §1 — so the returned class is the
+    unmodified reference model wired to the drop-in layer (``suhaas_model.py:114``)."""
+    ref_gml = graphml()
+    _stub_pkg("graphs", os.path.join(REF_ROOT, "graphs"))
+    _stub_pkg("graphs.models", os.path.join(REF_ROOT, "graphs", "models"))
+    if "torchsummaryX" not in sys.modules:
+        ts = types.ModuleType("torchsummaryX")
+        ts.summary = lambda *a, **k: None
+        sys.modules["torchsummaryX"] = ts
+    importlib.import_module("graphs.weights_initializer")
+    path = os.path.join(REF_ROOT, "graphs", "models", "suhaas_model.py")
+    name = "graphs.models.suhaas_model" + ("" if gml_module is None else "__gfc_swapped")
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    pkg = sys.modules["utils.graphUtils"]
+    saved_mod, saved_attr = sys.modules["utils.graphUtils.graphML"], getattr(pkg, "graphML", None)
+    try:
+        if gml_module is not None:   # `import a.b.c as x` binds sys.modules / the parent package attribute
+            sys.modules["utils.graphUtils.graphML"] = gml_module
+            pkg.graphML = gml_module
+        spec.loader.exec_module(mod)
+    finally:
+        sys.modules["utils.graphUtils.graphML"] = saved_mod
+        pkg.graphML = saved_attr if saved_attr is not None else ref_gml
+    return mod.DecentralPlannerNet

@@ -190,3 +190,33 @@ def test_new_layers_match_the_live_reference_surface():
     ref = gml.GraphFilterBatchGSO(4, 4, 4, 2); ours = gnnfc.GraphFilterBatchGSO(4, 4, 4, 2)
     ref.addGSO(S); ours.addGSO(S)
     assert torch.allclose(ref.SK, ours.SK, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.skipif(not refimport.available(), reason="reference tree only exists in the build container")
+def test_reference_policy_constructs_with_the_dropin_layer():
+    """a10: the UNMODIFIED reference model file (graphs/models/suhaas_model.py) executed with its
+    ``import utils.graphUtils.graphML as gml`` resolving to gnnfc: the GFL stage is built from the drop-in layer
+    (:114), the reference model's own state_dict loads into it, and ``addGSO`` + the per-forward wiring
+    ``self.GFL[2*l].addGSO(self.S)`` (:149-159,182) hand the layer the ``[B,1,N,N]`` GSO it expects."""
+    RefNet = refimport.decentral_planner_net()
+    SwapNet = refimport.decentral_planner_net(gnnfc)
+    torch.manual_seed(0)
+    ref = RefNet(nA=3)
+    swp = SwapNet(nA=3)
+    assert type(swp.GFL[0]) is gnnfc.GraphFilterBatch and type(ref.GFL[0]) is not gnnfc.GraphFilterBatch
+    assert repr(swp.GFL) == repr(ref.GFL)
+    assert [(k, tuple(v.shape)) for k, v in swp.state_dict().items()] == \
+           [(k, tuple(v.shape)) for k, v in ref.state_dict().items()]
+    assert sum(p.numel() for p in swp.parameters()) == 2584034          # SURVEY 8c(4)
+    missing, unexpected = swp.load_state_dict(ref.state_dict())
+    assert not missing and not unexpected
+    assert torch.equal(swp.GFL[0].weight, ref.GFL[0].weight) and torch.equal(swp.GFL[0].bias, ref.GFL[0].bias)
+    S = torch.zeros(5, 3, 3, dtype=torch.float64)
+    swp.addGSO(S)
+    assert swp.S.shape == (5, 1, 3, 3)
+    for l in range(swp.L):
+        swp.GFL[2 * l].addGSO(swp.S)                                     # suhaas_model.py:182
+    assert swp.GFL[0].N == 3 and swp.GFL[0].S is swp.S
+    with pytest.raises(AssertionError):
+        swp.addGSO(torch.zeros(5, 1, 3, 3))                              # :153  E == 1 wants [B,N,N]
+    assert swp.double().GFL[0].weight.dtype == torch.float64            # the agent runs the model in double

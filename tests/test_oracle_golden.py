@@ -19,11 +19,12 @@ FILTER_FILES = ["filter_cfg1.npz", "filter_general_e2.npz", "filter_k1_nobias.np
 SAME_GSO_FILES = ["samegso_e2_nin.npz", "samegso_cfg2_f32.npz"]
 BATCH_GSO_FILES = ["batchgso_cfg2_3d.npz", "batchgso_e2_4d.npz"]
 RELU_FILES = ["filter_relu.npz"]
+MODEL_FILES = ["model_gfl_n3.npz", "model_gfl_n8.npz"]
 
 
 def test_golden_inventory(golden_dir):
     have = sorted(os.path.basename(p) for p in glob.glob(os.path.join(golden_dir, "*.npz")))
-    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES + RELU_FILES)
+    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES + RELU_FILES + MODEL_FILES)
 
 
 @pytest.mark.parametrize("name", GSO_FILES)
@@ -142,6 +143,18 @@ def test_relu_pairing_oracle_matches_reference_golden(golden_dir):
     y, dX, dH, db = lsigf.filter_fwd_bwd(g["h"], g["S"], g["x"], g["b"], g["dOut"], lsigf.ACT_RELU)
     assert rel_err(y, g["y"]) < 1e-13
     assert rel_err(dX, g["dX"]) < 2e-7 and rel_err(dH, g["dH"]) < 2e-7 and rel_err(db, g["db"]) < 2e-7
+
+
+@pytest.mark.parametrize("name", MODEL_FILES)
+def test_model_gfl_stage_oracle_matches_reference_golden(golden_dir, name):
+    """the graph-filter stage of the reference policy executed end to end (DecentralPlannerNet.addGSO / GFL,
+    suhaas_model.py:149-159,182-185; loss of suhaas_agent.py:123-126): S [B,N,N] -> unsqueeze(1), LeakyReLU(0.01)"""
+    g = np.load(os.path.join(golden_dir, name))
+    S = g["S"][:, None]                                   # addGSO: [B,N,N] -> [B,1,N,N]  (suhaas_model.py:155)
+    y, dX, dH, db = lsigf.filter_fwd_bwd(g["h"], S, g["x"], g["b"], g["dOut"], lsigf.ACT_LEAKY_RELU)
+    assert rel_err(y, g["y"]) < 1e-13
+    assert rel_err(dX, g["dX"]) < 2e-7                    # the stage's input is fp32 (torch.zeros default, :165): its grad is too
+    assert rel_err(dH, g["dH"]) < 1e-12 and rel_err(db, g["db"]) < 1e-12
 
 
 def test_closed_form_gradients_match_autograd():

@@ -7,7 +7,8 @@ from bench import WORKLOADS, HotPath, RADIUS, SLOPE
 C = gnnfc._cabi
 name = sys.argv[1] if len(sys.argv) > 1 else "cfg3"
 flushes = [int(a) for a in sys.argv[2:]] or [0]
-w = WORKLOADS[name]; dev = torch.device("cuda", 0)
+w = dict(WORKLOADS[name]); dev = torch.device("cuda", 0)
+if os.environ.get("GFC_B"): w["B"] = int(os.environ["GFC_B"])
 hp = HotPath(w, dev, 1)
 if os.environ.get("NOPF"): C.check(C.lib.gfc_set_option(C.OPT_WIDE_NO_PREFETCH, 1), "opt")
 B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]

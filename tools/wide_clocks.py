@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timeline of CTA 0 of the tcgen05 wide forward kernel (issuer thread + worker warp 2): SM-clock stamps
+"""Timeline of CTA 0 of the tcgen05 wide forward kernel (issuer thread, first warp of worker group A (W) and of group B): SM-clock stamps
 (gfc_set_debug_clock_buffer).  usage: wide_clocks.py [cfg] [B] [first_event] [n_events]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -30,13 +30,15 @@ def wname(tag):
     if 100 <= tag < 200: return "        W wait mma_done ph%d" % (tag - 100)
     if 200 <= tag < 300: return "        W got  mma_done ph%d" % (tag - 200)
     if 300 <= tag < 400: return "        W wrote back + published ph%d" % (tag - 300)
-    return {400: "        W write-backs done", 401: "        W inputs loaded, tile max done", 410: "        W slab0 free", 411: "        W slab1 free",
+    return {400: "        W write-backs done", 401: "        W inputs loaded, tile max done", 430: "        W P published", 410: "        W slab0 free", 411: "        W slab1 free",
             420: "        W W0 slab0 stored", 421: "        W W0 slab1 stored", 500: "        W got out_full", 501: "        W epilogue done"}.get(tag, "        W %d" % tag)
 ev = []
 a = t[0:4000].reshape(-1, 2)
 ev += [(int(c), name(int(tag))) for c, tag in a if c]
 a = t[4096:4096 + 4000].reshape(-1, 2)
 ev += [(int(c), wname(int(tag))) for c, tag in a if c]
+a = t[8192:8192 + 4000].reshape(-1, 2)     # group B (next tile's operands, previous tile's epilogue)
+ev += [(int(c), "                        B" + wname(int(tag)).strip().lstrip("W")) for c, tag in a if c]
 ev.sort()
 t0 = ev[0][0]
 lo = int(sys.argv[3]) if len(sys.argv) > 3 else 150
