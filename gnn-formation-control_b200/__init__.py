@@ -12,10 +12,14 @@ from . import _cabi
 from ._cabi import GfcError, version, last_launch_count
 from .gso import build_gso, build_csr, SparseGSO
 from .graph_filter import GraphFilterBatch, GraphFilter, GraphFilterBatchGSO, graph_filter
-from .data import robot_major_to_batch, graphs_from_recording, gso_batch_from_recording, positions_from_recording
-from .dp import GradBucket, PeerExchange, shard_range, broadcast_parameters
+from .recurrent import GraphFilterRNNBatch, GraphFilterMoRNNBatch, GraphFilterL2ShareBatch, torchpermul
+from .rollout import Rollout
+from .data import (robot_major_to_batch, graphs_from_recording, gso_batch_from_recording, positions_from_recording,
+                   RecordingLoader)
+from .dp import GradBucket, BucketedReducer, PeerExchange, shard_range, broadcast_parameters
 
 __all__ = ["GraphFilterBatch", "GraphFilter", "GraphFilterBatchGSO", "graph_filter", "build_gso", "build_csr", "SparseGSO",
+           "GraphFilterRNNBatch", "GraphFilterMoRNNBatch", "GraphFilterL2ShareBatch", "torchpermul", "Rollout",
            "robot_major_to_batch", "graphs_from_recording", "gso_batch_from_recording", "positions_from_recording",
-           "GradBucket", "PeerExchange", "shard_range", "broadcast_parameters", "GfcError", "version",
+           "RecordingLoader", "GradBucket", "BucketedReducer", "PeerExchange", "shard_range", "broadcast_parameters", "GfcError", "version",
            "last_launch_count"]

@@ -40,3 +40,70 @@ def positions_from_recording(position_list, nA):
     E, M, two = p.shape
     assert two == 2 and M % nA == 0
     return p.reshape(E * (M // nA), nA, 2).to(torch.float32).contiguous()
+
+
+class RecordingLoader:
+    """Device-side replacement for ``RobotDataset`` + ``DataLoader(trainset, batch_size=16, shuffle=True,
+    drop_last=True)`` as the agent uses them (custom_dataset.py:15-82, suhaas_agent.py:110-121).
+
+    The reference re-lays every recording out with per-element Python loops into fresh float64 arrays on the host and
+    then ships each batch to the GPU piece by piece.  Here the robot-major recordings are uploaded ONCE (float32, as
+    recorded — data.py:43 declares them float32), the ``[T, nA, ...]`` layout is a strided view, and a batch is one
+    ``index_select`` per key on the device; nothing touches the host inside the epoch.  Batches carry the reference's
+    keys and shapes: ``data [b,nA,inW,inH]``, ``graphs [b,nA,nA,nA]``, ``actions [b,nA,2]``, ``refs [b,nA,1]``,
+    ``alphas [b,nA,1]`` in ``dtype`` (float64 like ``transform=ToTensor`` + ``.double()``), plus ``S`` =
+    ``graphs[:, view]`` — the ``[b,nA,nA]`` batch ``model.addGSO`` takes (suhaas_agent.py:117,121)."""
+
+    KEYS = ("data", "actions", "graphs", "refs", "alphas")
+
+    def __init__(self, observations, actions, graphs, refs, alphas, nA, inW=100, inH=100, batch_size=16,
+                 shuffle=True, drop_last=True, device="cuda", dtype=torch.float64, view=0, generator=None):
+        self.nA, self.batch_size, self.shuffle, self.drop_last = int(nA), int(batch_size), shuffle, drop_last
+        self.device, self.dtype, self.view = torch.device(device), dtype, int(view)
+        self.generator = generator
+
+        def up(a):
+            t = torch.as_tensor(np.asarray(a))
+            return t.to(device=self.device, dtype=torch.float32 if t.is_floating_point() else t.dtype)
+
+        self.cols = dict(
+            data=robot_major_to_batch(up(observations), nA, (inW, inH)),
+            actions=robot_major_to_batch(up(actions), nA, (2,)),
+            graphs=robot_major_to_batch(up(graphs), nA, (nA, nA)),
+            refs=robot_major_to_batch(up(refs), nA, (1,)),
+            alphas=robot_major_to_batch(up(alphas), nA, (1,)))
+        self.T = self.cols["data"].shape[0]
+        for k in self.KEYS:
+            assert self.cols[k].shape[0] == self.T, "recordings of different lengths"
+
+    @classmethod
+    def from_recordings(cls, per_robot, nA=None, **kw):
+        """``per_robot``: one mapping per robot with the keys ``data.py`` records (``observations``, ``actions``,
+        ``graph``, ``obs2`` — columns 1 and 2 of ``obs2`` are the reference angle and alpha, suhaas_agent.py:103-104),
+        e.g. ``np.load('data/data001_0.npz')``; robots are concatenated robot-major like ``Data.append`` does."""
+        nA = len(per_robot) if nA is None else nA
+        cat = lambda key: np.concatenate([np.asarray(d[key]) for d in per_robot], axis=0)   # noqa: E731
+        obs2 = cat("obs2")
+        return cls(cat("observations"), cat("actions"), cat("graph"), obs2[:, 1], obs2[:, 2], nA, **kw)
+
+    @classmethod
+    def from_npz(cls, paths, **kw):
+        return cls.from_recordings([np.load(p) for p in paths], **kw)
+
+    def __len__(self):
+        n = self.T // self.batch_size
+        return n if self.drop_last or self.T % self.batch_size == 0 else n + 1
+
+    def batch(self, idx):
+        idx = torch.as_tensor(idx, device=self.device, dtype=torch.long)
+        out = {k: self.cols[k].index_select(0, idx).to(self.dtype) for k in self.KEYS}
+        out["S"] = out["graphs"][:, self.view]
+        return out
+
+    def __iter__(self):
+        if self.shuffle:
+            order = torch.randperm(self.T, generator=self.generator).to(self.device)
+        else:
+            order = torch.arange(self.T, device=self.device)
+        for i in range(len(self)):
+            yield self.batch(order[i * self.batch_size:(i + 1) * self.batch_size])

@@ -103,6 +103,110 @@ class GradBucket:
         self.unpack()
 
 
+class BucketedReducer:
+    """Data-parallel gradient exchange for the WHOLE policy — filter taps and encoder / MLP weights — overlapped with
+    the backward pass (the reference trains on one device, suhaas_agent.py:115-128).
+
+    Parameters are grouped into buckets in reverse registration order (the order autograd finishes them, as the
+    reference model is wired: action MLP -> graph filter -> compress MLP -> CNN, suhaas_model.py:53-143,161-212).
+    ``filter_params`` (the ``GraphFilterBatch`` taps / biases) get a bucket of their own, small enough for the one-shot
+    peer-memory kernel; everything else is cut into ``bucket_bytes`` (default 10 MB) buckets for NCCL.  Every
+    parameter carries a post-accumulate-grad hook: the gradient is copied into its bucket slice as soon as autograd
+    has produced it, and when a bucket is complete its all-reduce is launched on a SIDE stream (ordered after the
+    copies through an event) while the main stream continues with the rest of the backward — e.g. the action-MLP
+    bucket travels while the filter backward kernels run, the filter bucket while the CNN backward runs.
+    ``finish()`` makes the main stream wait for every bucket and writes the reduced values back into ``p.grad``.
+
+    ``overlap=False`` launches the same collectives on the main stream inside ``finish()`` (the A/B baseline).
+    CPU tensors / gloo: same bucketing and hooks, collectives run inline (tests/test_dp_gloo.py)."""
+
+    def __init__(self, params, filter_params=(), bucket_bytes=10 << 20, average=True, process_group=None,
+                 overlap=True):
+        params = [p for p in params if p.requires_grad]
+        fset = {id(p) for p in filter_params}
+        self.average, self.group, self.overlap = average, process_group, overlap
+        groups, cur, cur_bytes = [], [], 0
+        for p in reversed([p for p in params if id(p) not in fset]):
+            nb = p.numel() * 4
+            if cur and cur_bytes + nb > bucket_bytes:
+                groups.append(cur); cur, cur_bytes = [], 0
+            cur.append(p); cur_bytes += nb
+        if cur:
+            groups.append(cur)
+        fl = [p for p in params if id(p) in fset]
+        if fl:
+            groups.append(fl)
+        self.buckets = [GradBucket(g, average=average, process_group=process_group) for g in groups]
+        self.filter_bucket = len(self.buckets) - 1 if fl else None
+        self._slot = {}
+        for bi, b in enumerate(self.buckets):
+            off = 0
+            for p in b.params:
+                self._slot[id(p)] = (bi, off, p.numel())
+                off += p.numel()
+        self._pending = [len(b.params) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._done = [None] * len(self.buckets)
+        dev = params[0].device if params else torch.device("cpu")
+        self.cuda = dev.type == "cuda"
+        self.side = torch.cuda.Stream(device=dev) if (self.cuda and overlap) else None
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in params]
+        self.launch_order = []      # bucket indices in the order their collectives were launched (last step)
+
+    def remove_hooks(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+    @property
+    def total_numel(self):
+        return sum(b.numel for b in self.buckets)
+
+    def _on_grad(self, p):
+        bi, off, n = self._slot[id(p)]
+        b = self.buckets[bi]
+        b.flat[off:off + n].copy_(p.grad.reshape(-1))
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and self.overlap:
+            self._launch(bi)
+
+    def _launch(self, bi):
+        b = self.buckets[bi]
+        self._launched[bi] = True
+        self.launch_order.append(bi)
+        if self.side is not None:
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(b.flat.device))
+            self.side.wait_event(ready)
+            with torch.cuda.stream(self.side):
+                b.allreduce()
+                done = torch.cuda.Event()
+                done.record(self.side)
+            self._done[bi] = done
+        else:
+            b.allreduce()
+
+    def finish(self):
+        """wait for / run the outstanding collectives, then unpack into ``p.grad``; call after ``loss.backward()``"""
+        for bi, b in enumerate(self.buckets):
+            if not self._launched[bi]:
+                if self._pending[bi]:              # parameters that received no gradient this step contribute zeros
+                    for p in b.params:
+                        if p.grad is None:
+                            _, off, n = self._slot[id(p)]
+                            b.flat[off:off + n].zero_()
+                self._launch(bi)
+        for bi, b in enumerate(self.buckets):
+            if self._done[bi] is not None:
+                torch.cuda.current_stream(b.flat.device).wait_event(self._done[bi])
+                self._done[bi] = None
+            b.unpack()
+        self._pending = [len(b.params) for b in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        order, self.launch_order = self.launch_order, []
+        return order
+
+
 def broadcast_parameters(params, src=0, group=None):
     """identical taps on every rank before the first step"""
     if not (dist.is_available() and dist.is_initialized()):

@@ -342,6 +342,102 @@ def model_goldens():
                             loss=float(loss), slope=0.01)
 
 
+def recurrent_goldens():
+    """The reference's recurrent graph-filter layers (graphML.py:2491-2987) executed on CPU over two time steps with
+    the hidden state carried (``updateHiddenState``), loss = sum of both outputs against seeded cotangents, backward
+    through time.  Stored: inputs, parameters, outputs, the final hidden state and every gradient."""
+    gml = ri.graphml()
+    g8 = np.load(os.path.join(OUT, "gso_expert8.npz"))
+    for tag, cls, (G, H, F, K, N, B), seed in (
+            ("rnn_n8", "GraphFilterRNNBatch", (32, 32, 16, 3, 8, 6), 21),
+            ("rnn_nin", "GraphFilterRNNBatch", (8, 16, 16, 2, 8, 3), 22),
+            ("mornn_n16", "GraphFilterMoRNNBatch", (8, 16, 16, 2, 16, 4), 23),
+            ("l2share_n16", "GraphFilterL2ShareBatch", (8, 16, 16, 2, 16, 4), 24)):
+        torch.manual_seed(seed)
+        rng = np.random.default_rng(seed)
+        m = getattr(gml, cls)(G, H, F, K)
+        if N == 8:
+            S = g8["adj_le"][5:5 + B].astype(np.float32)[:, None]
+        else:
+            A = (rng.random((B, N, N)) < 0.25).astype(np.float32)
+            A = np.triu(A, 1); S = (A + A.transpose(0, 2, 1))[:, None]
+        Nin = N - 2 if tag == "rnn_nin" else N
+        xs = [rng.standard_normal((B, G, Nin)).astype(np.float32) for _ in range(2)]
+        dOuts = [rng.standard_normal((B, F, Nin)) for _ in range(2)]
+        h0 = rng.standard_normal((B, H, N)).astype(np.float32)
+        m.addGSO(torch.from_numpy(S))
+        h0t = torch.from_numpy(h0).double().requires_grad_(True)
+        xts = [torch.from_numpy(x).clone().requires_grad_(True) for x in xs]
+        m.updateHiddenState(h0t)
+        loss = 0
+        ys = []
+        for xt, dO in zip(xts, dOuts):
+            y = m(xt)
+            ys.append(y)
+            loss = loss + (y * torch.from_numpy(dO).to(y.dtype)).sum()
+        loss.backward()
+        out = dict(S=S, h0=h0, x0=xs[0], x1=xs[1], dOut0=dOuts[0], dOut1=dOuts[1],
+                   y0=ys[0].detach().numpy(), y1=ys[1].detach().numpy(), hT=m.hiddenState.detach().numpy(),
+                   dx0=xts[0].grad.numpy(), dx1=xts[1].grad.numpy(), dh0=h0t.grad.numpy(),
+                   dims=np.array([G, H, F, K, N, B, Nin]))
+        for n, p in m.named_parameters():
+            out["p_" + n] = p.detach().numpy()
+            out["g_" + n] = p.grad.numpy()
+        np.savez_compressed(os.path.join(OUT, "recurrent_%s.npz" % tag), **out)
+
+
+def rollout_golden():
+    """The reference's per-step inference pattern (scene.py:385-394 -> robot.py:654 -> suhaas_agent.py:30-57): at every
+    simulation step EVERY robot rebuilds the adjacency with ``Scene.readADjMatrix`` and runs the policy at batch 1,
+    keeping only its own column of the output.  Executed here for the graph-filter stack (two reference
+    ``GraphFilterBatch`` + ``LeakyReLU`` layers, the GFL of suhaas_model.py:112-123 with L = 2) on recorded 12- and
+    8-robot frames; expected[t, :, i] is robot i's own result at step t."""
+    gml = ri.graphml()
+    for tag, nA, fname, T, dims, seed in (("n12", 12, "positionList_expert_12_longer.npy", 6, (128, 128, 128), 31),
+                                          ("n8", 8, "positionList_expert_8.npy", 10, (32, 64, 32), 32)):
+        path = os.path.join(ri.REF_ROOT, fname)
+        if not os.path.exists(path):
+            cands = [f for f in sorted(os.listdir(ri.REF_ROOT)) if f.startswith("positionList") and ("_%d" % nA) in f]
+            fname = cands[0]
+        frames = load_frames(fname, nA)
+        rng = np.random.default_rng(seed)
+        idx = np.sort(rng.choice(len(frames), T, replace=False))
+        pos = frames[idx]
+        assert np.array_equal(pos.astype(np.float32).astype(np.float64), pos)
+        torch.manual_seed(seed)
+        layers = []
+        for l in range(len(dims) - 1):
+            layers += [gml.GraphFilterBatch(dims[l], dims[l + 1], 3, 1, True), torch.nn.LeakyReLU(inplace=True)]
+        gfl = torch.nn.Sequential(*layers)
+        x = rng.standard_normal((T, dims[0], nA)).astype(np.float32)
+        exp = np.zeros((T, dims[-1], nA))
+        with torch.no_grad():
+            for t_ in range(T):
+                for i in range(nA):                       # every robot: its own GSO build + its own batch-1 forward
+                    S = ri.scene_read_adj(pos[t_].tolist(), 2).reshape(1, 1, nA, nA)
+                    St = torch.from_numpy(np.array(S))
+                    for l in range(len(dims) - 1):
+                        gfl[2 * l].addGSO(St)
+                    out = gfl(torch.from_numpy(x[t_:t_ + 1]).double())
+                    exp[t_, :, i] = out[0, :, i].numpy()
+        out = dict(pos=pos.astype(np.float32), x=x, expected=exp, radius=2.0, dims=np.array(dims), source=fname)
+        for l in range(len(dims) - 1):
+            out["h%d" % l] = gfl[2 * l].weight.detach().numpy()
+            out["b%d" % l] = gfl[2 * l].bias.detach().numpy()
+        np.savez_compressed(os.path.join(OUT, "rollout_%s.npz" % tag), **out)
+
+
+def model_param_layout():
+    """(name, shape) of every parameter of the reference policy (2 584 034 parameters, suhaas_model.py:53-143), in
+    registration order: the layout the data-parallel gradient buckets are tested with."""
+    import json
+    Net = ri.decentral_planner_net()
+    model = Net(nA=3)
+    lay = [[n, list(p.shape)] for n, p in model.named_parameters()]
+    assert sum(int(np.prod(s)) for _, s in lay) == 2584034
+    json.dump(lay, open(os.path.join(OUT, "model_param_layout.json"), "w"))
+
+
 if __name__ == "__main__":
     assert ri.available(), "run in the build container (needs /root/reference)"
     os.makedirs(OUT, exist_ok=True)
@@ -351,5 +447,8 @@ if __name__ == "__main__":
     batch_gso_goldens()
     relu_golden()
     model_goldens()
+    recurrent_goldens()
+    rollout_golden()
+    model_param_layout()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

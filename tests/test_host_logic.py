@@ -220,3 +220,117 @@ def test_reference_policy_constructs_with_the_dropin_layer():
     with pytest.raises(AssertionError):
         swp.addGSO(torch.zeros(5, 1, 3, 3))                              # :153  E == 1 wants [B,N,N]
     assert swp.double().GFL[0].weight.dtype == torch.float64            # the agent runs the model in double
+
+
+# --------------------------------------------------------------------------- #
+# §8 f-4: recurrent layers (graphML.py:2491-2987) — surface; the arithmetic is checked on the GPU against goldens
+# --------------------------------------------------------------------------- #
+def test_recurrent_layers_surface():
+    m = gnnfc.GraphFilterRNNBatch(4, 8, 6, 3)
+    assert [(k, tuple(v.shape)) for k, v in m.state_dict().items()] == [
+        ("weight_A", (8, 1, 3, 4)), ("weight_B", (8, 1, 3, 8)), ("weight_D", (6, 1, 3, 8)),
+        ("bias_A", (8, 1)), ("bias_B", (8, 1)), ("bias_D", (6, 1))]
+    assert float(m.weight_A.abs().max()) <= 1 / math.sqrt(4 * 3) and float(m.weight_B.abs().max()) <= 1 / math.sqrt(8 * 3)
+    assert repr(m) == ("GraphFilterRNNBatch(in_features=4, out_features=6, hidden_features=8, filter_taps=3, "
+                       "edge_features=1, bias=True, no GSO stored)")
+    with pytest.raises(AssertionError):
+        m.addGSO(torch.zeros(2, 5, 5))                       # graphML.py:2587
+    m.addGSO(torch.zeros(2, 1, 5, 5))
+    assert m.N == 5 and repr(m).endswith("GSO stored)")
+    h = torch.zeros(2, 8, 5)
+    m.updateHiddenState(h)
+    assert m.hiddenState is h
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(2, 4, 5))
+    mo = gnnfc.GraphFilterMoRNNBatch(4, 8, 6, 3)
+    assert tuple(mo.weight_B.shape) == (8, 8) and tuple(mo.weight_D.shape) == (6, 8)
+    assert float(mo.weight_B.abs().max()) <= 1 / math.sqrt(8)
+    nb = gnnfc.GraphFilterRNNBatch(4, 8, 6, 3, bias=False)   # the reference raises here (documented deviation)
+    assert nb.bias_A is None and nb.bias_D is None and "bias=False" in repr(nb)
+    # torchpermul is the reference's elementwise broadcast product, not a matmul (graphML.py:2656-2679)
+    x, w, b = torch.rand(2, 3, 3), torch.rand(3, 3), torch.rand(3, 1)
+    assert torch.equal(gnnfc.torchpermul(w, x, b), (x.permute(0, 2, 1) * w.permute(1, 0)).permute(0, 2, 1) + b)
+
+
+@pytest.mark.skipif(not refimport.available(), reason="reference tree only exists in the build container")
+def test_recurrent_layers_match_the_live_reference_surface():
+    gml = refimport.graphml()
+    for name in ("GraphFilterRNNBatch", "GraphFilterMoRNNBatch", "GraphFilterL2ShareBatch"):
+        torch.manual_seed(3); ref = getattr(gml, name)(6, 5, 5, 2)
+        torch.manual_seed(3); ours = getattr(gnnfc, name)(6, 5, 5, 2)
+        assert [(k, tuple(v.shape)) for k, v in ref.state_dict().items()] == \
+               [(k, tuple(v.shape)) for k, v in ours.state_dict().items()]
+        for k in ref.state_dict():
+            assert torch.equal(ref.state_dict()[k], ours.state_dict()[k]), k       # same init law and draw order
+        assert ref.extra_repr() == ours.extra_repr()
+        S = torch.rand(3, 1, 5, 5)
+        ref.addGSO(S); ours.addGSO(S)
+        assert ref.extra_repr() == ours.extra_repr() and ref.N == ours.N
+        ours.load_state_dict(ref.state_dict())
+    x, w, b = torch.rand(2, 4, 4), torch.rand(4, 4), torch.rand(4, 1)
+    assert torch.equal(gml.torchpermul(w, x, b), gnnfc.torchpermul(w, x, b))
+
+
+# --------------------------------------------------------------------------- #
+# §8 f-4: device-side recording loader vs RobotDataset + DataLoader (custom_dataset.py, suhaas_agent.py:110-121)
+# --------------------------------------------------------------------------- #
+def _recording(rng, nA, T, inW, inH):
+    per_robot = []
+    for r in range(nA):
+        per_robot.append(dict(observations=rng.random((T, inW * inH)).astype(np.float32),
+                              actions=rng.standard_normal((T, 2)).astype(np.float32),
+                              graph=(rng.random((T, nA * nA)) < 0.5).astype(np.float32),
+                              obs2=rng.standard_normal((T, 6 + nA)).astype(np.float32)))
+    return per_robot
+
+
+def test_recording_loader_matches_the_reference_dataset_loops():
+    rng = np.random.default_rng(8)
+    nA, T, inW, inH = 3, 11, 4, 5
+    rec = _recording(rng, nA, T, inW, inH)
+    ld = gnnfc.RecordingLoader.from_recordings(rec, batch_size=4, shuffle=False, device="cpu", inW=inW, inH=inH)
+    assert len(ld) == 2                                                   # drop_last=True like suhaas_agent.py:111
+    batches = list(ld)
+    assert [tuple(batches[0][k].shape) for k in ("data", "graphs", "actions", "refs", "alphas", "S")] == \
+           [(4, nA, inW, inH), (4, nA, nA, nA), (4, nA, 2), (4, nA, 1), (4, nA, 1), (4, nA, nA)]
+    assert all(v.dtype == torch.float64 for v in batches[0].values())
+    # the reference's loops restated (custom_dataset.py:15-63): c[i, j] = rows[j*T + i]
+    for bi, bt in enumerate(batches):
+        for q in range(4):
+            i = bi * 4 + q
+            for j in range(nA):
+                assert np.array_equal(bt["data"][q, j].numpy(), rec[j]["observations"][i].reshape(inW, inH).astype(np.float64))
+                assert np.array_equal(bt["graphs"][q, j].numpy(), rec[j]["graph"][i].reshape(nA, nA).astype(np.float64))
+                assert np.array_equal(bt["actions"][q, j].numpy(), rec[j]["actions"][i].astype(np.float64))
+                assert bt["refs"][q, j, 0] == float(rec[j]["obs2"][i, 1]) and bt["alphas"][q, j, 0] == float(rec[j]["obs2"][i, 2])
+            assert torch.equal(bt["S"][q], bt["graphs"][q, 0])            # suhaas_agent.py:117
+    # shuffling: a permutation of the time steps, every step at most once, remainder dropped
+    g = torch.Generator().manual_seed(0)
+    ld2 = gnnfc.RecordingLoader.from_recordings(rec, batch_size=4, shuffle=True, device="cpu", inW=inW, inH=inH, generator=g)
+    seen = torch.cat([b["actions"][:, 0, 0] for b in ld2])
+    ref_col = torch.from_numpy(rec[0]["actions"][:, 0].astype(np.float64))
+    assert len(seen) == 8 and len(set(seen.tolist())) == 8 and all(v in ref_col.tolist() for v in seen.tolist())
+    ld3 = gnnfc.RecordingLoader.from_recordings(rec, batch_size=4, shuffle=False, drop_last=False, device="cpu", inW=inW, inH=inH)
+    assert len(ld3) == 3 and list(ld3)[-1]["data"].shape[0] == 3
+
+
+@pytest.mark.skipif(not refimport.available(), reason="reference tree only exists in the build container")
+def test_recording_loader_matches_the_live_robot_dataset():
+    import sys
+    sys.path.insert(0, refimport.REF_ROOT)
+    try:
+        from custom_dataset import RobotDataset
+    finally:
+        sys.path.pop(0)
+    rng = np.random.default_rng(9)
+    nA, T, inW, inH = 4, 6, 3, 3
+    rec = _recording(rng, nA, T, inW, inH)
+    cat = lambda k: np.concatenate([r[k] for r in rec], axis=0)           # noqa: E731  (Data.append, data.py:153-156)
+    ds = RobotDataset(cat("observations"), cat("actions"), cat("graph"), cat("obs2")[:, 1], cat("obs2")[:, 2], nA,
+                      inW=inW, inH=inH, transform=True)
+    ld = gnnfc.RecordingLoader.from_recordings(rec, batch_size=T, shuffle=False, device="cpu", inW=inW, inH=inH)
+    bt = next(iter(ld))
+    for i in range(T):
+        item = ds[i]
+        for k in ("data", "graphs", "actions", "refs", "alphas"):
+            assert torch.equal(bt[k][i], item[k]), k

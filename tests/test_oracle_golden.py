@@ -20,11 +20,14 @@ SAME_GSO_FILES = ["samegso_e2_nin.npz", "samegso_cfg2_f32.npz"]
 BATCH_GSO_FILES = ["batchgso_cfg2_3d.npz", "batchgso_e2_4d.npz"]
 RELU_FILES = ["filter_relu.npz"]
 MODEL_FILES = ["model_gfl_n3.npz", "model_gfl_n8.npz"]
+RECURRENT_FILES = ["recurrent_rnn_n8.npz", "recurrent_rnn_nin.npz", "recurrent_mornn_n16.npz", "recurrent_l2share_n16.npz"]
+ROLLOUT_FILES = ["rollout_n12.npz", "rollout_n8.npz"]
 
 
 def test_golden_inventory(golden_dir):
     have = sorted(os.path.basename(p) for p in glob.glob(os.path.join(golden_dir, "*.npz")))
-    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES + RELU_FILES + MODEL_FILES)
+    assert have == sorted(GSO_FILES + FILTER_FILES + SAME_GSO_FILES + BATCH_GSO_FILES + RELU_FILES + MODEL_FILES +
+                          RECURRENT_FILES + ROLLOUT_FILES)
 
 
 @pytest.mark.parametrize("name", GSO_FILES)
@@ -210,3 +213,39 @@ def test_oracle_matches_live_reference():
         assert np.array_equal(ogso.adjacency(p[None], 2, ogso.MODE_BINARY_LE)[0], ref)
         W, _ = refimport.fixed_radius_gso(p[None].astype(np.float64), 2.0)
         assert np.array_equal(ogso.gso(p[None], 2.0, ogso.MODE_SYM_NORM_LT)[0], W)
+
+
+@pytest.mark.parametrize("name", RECURRENT_FILES)
+def test_recurrent_oracle_matches_reference_golden(golden_dir, name):
+    """oracle restatement of graphML.py:2491-2987 (two steps, hidden state carried, backward through time) vs the
+    outputs and gradients of the executed reference classes"""
+    import torch
+    g = np.load(os.path.join(golden_dir, name))
+    kind = name.split("_")[1]
+    p = {k[2:]: torch.from_numpy(g[k]).requires_grad_(True) for k in g.files if k.startswith("p_")}
+    S = torch.from_numpy(g["S"])
+    h0 = torch.from_numpy(g["h0"]).double().requires_grad_(True)
+    xs = [torch.from_numpy(g["x0"]).requires_grad_(True), torch.from_numpy(g["x1"]).requires_grad_(True)]
+    hid, loss, ys = h0, 0, []
+    for x, dO in zip(xs, (g["dOut0"], g["dOut1"])):
+        y, hid = lsigf.recurrent_step_torch(kind, p, S, x, hid)
+        ys.append(y)
+        loss = loss + (y * torch.from_numpy(dO).to(y.dtype)).sum()
+    loss.backward()
+    assert rel_err(ys[0].detach().numpy(), g["y0"]) < 1e-12 and rel_err(ys[1].detach().numpy(), g["y1"]) < 1e-12
+    assert rel_err(hid.detach().numpy(), g["hT"]) < 1e-12
+    assert rel_err(xs[0].grad.numpy(), g["dx0"]) < 1e-6 and rel_err(h0.grad.numpy(), g["dh0"]) < 1e-12
+    for k, v in p.items():
+        assert rel_err(v.grad.numpy(), g["g_" + k]) < 1e-6, k          # reference grads are fp32-rounded
+
+
+@pytest.mark.parametrize("name", ROLLOUT_FILES)
+def test_rollout_oracle_matches_reference_golden(golden_dir, name):
+    """the reference's per-robot batch-1 pattern gives, for every robot, the same column as ONE batched pass: oracle GSO
+    (scene.py:140-154 restatement) + oracle filter stack vs the golden produced by the per-robot loop"""
+    g = np.load(os.path.join(golden_dir, name))
+    S = ogso.gso(g["pos"], float(g["radius"]), ogso.MODE_BINARY_LE)[0][:, None]
+    y = g["x"]
+    for l in range(len(g["dims"]) - 1):
+        y = lsigf.activation(lsigf.lsigf_forward(g["h%d" % l], S, y, g["b%d" % l]), lsigf.ACT_LEAKY_RELU)
+    assert rel_err(y, g["expected"]) < 1e-12
