@@ -56,6 +56,7 @@ SIGNATURES = {
     "gfc_csr_count": (_i, [_p, _i, _i, _d, _i, _p, _p]),
     "gfc_csr_scan": (_i, [_p, _i, _i, _p, _p]),
     "gfc_csr_fill": (_i, [_p, _i, _i, _d, _i, _p, _i64, _p, _p, _p]),
+    "gfc_csr_build": (_i, [_p, _i, _i, _d, _i, _p, _i64, _p, _p, _p, _p]),
     "gfc_filter_csr_workspace_bytes": (_sz, [_i] * 6),
     "gfc_filter_csr_fwd": (_i, [_p, _p, _p, _p, _i64, _p, _p, _p] + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),
     "gfc_filter_csr_bwd": (_i, [_p] * 7 + [_i64] + [_p] * 6 + [_i] * 5 + [_i, _f, _i, _p, _sz, _p]),

@@ -158,6 +158,229 @@ csr_scan_kernel(const int32_t* __restrict__ deg, int N, int32_t* __restrict__ ro
   for (int i = lo; i < hi; ++i) { rp[i] = run; run += d[i]; }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// CSR build in ONE launch: one CTA per graph, cell list instead of the O(N^2) pair walk.
+//   1. positions -> shared memory, bounding box (block reduction);
+//   2. uniform grid with cell edge >= 1.001 R (so every neighbour lies in the 3x3 cells around a node; the margin
+//      absorbs the fp32 rounding of the cell index, the index map is monotone), at most 64 x 64 cells;
+//   3. counting sort of the nodes by cell: shared-memory atomics give an arbitrary slot, the final position is the
+//      node's RANK among the indices of its cell, so every cell list is ascending — deterministic;
+//   4. thread = row: count the neighbours among the <= 9 cell lists (fp32 screen, exact fp64 rule inside the rounding
+//      band — the bit-exact decision of kernel (a)), block scan -> rowptr;
+//   5. thread = row: 9-way merge of the (ascending) cell lists emits the row's columns in ascending order.
+// nnz_stride is a CAPACITY: if a graph needs more, *overflow = max(*overflow, needed) and the surplus edges are
+// dropped (the caller checks the flag; gnnfc.SparseGSO.check()).  colidx == NULL: rowptr only (sizing pass).
+constexpr int kCellDim = 64;
+constexpr int kCellMax = kCellDim * kCellDim;
+
+struct CellRanges { int lo[3], hi[3]; };
+
+template <bool NORM>
+__global__ void __launch_bounds__(1024)
+csr_build_fused_kernel(const float* __restrict__ pos, int N, double thr, float thr_lo, float thr_hi, float cell0,
+                       int32_t* __restrict__ rowptr, long long nnz_stride, int32_t* __restrict__ colidx,
+                       float* __restrict__ vals, int* __restrict__ overflow) {
+  extern __shared__ unsigned char csr_smem[];
+  float2* sp = reinterpret_cast<float2*>(csr_smem);          // [N] positions
+  int* cellstart = reinterpret_cast<int*>(sp + N);             // [kCellMax + 1]
+  int* cid = cellstart + kCellMax + 1;                         // [N] cell of node
+  int* lst = cid + N;                                          // [N] nodes ordered by (cell, index)
+  int* aux = lst + N;                                          // [N] slot -> degree
+  int* un = aux + N;                                           // [N] unsorted cell lists -> local rowptr
+  __shared__ float redf[4][32];
+  __shared__ int wsum[32];
+  __shared__ int carry_s;
+  const int b = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const float2* gp = reinterpret_cast<const float2*>(pos) + (size_t)b * N;
+  int32_t* rp = rowptr + (size_t)b * (N + 1);
+
+  // 1. load + bounding box
+  float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+  for (int i = tid; i < N; i += nt) {
+    const float2 p = __ldg(gp + i);
+    sp[i] = p;
+    mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x); mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (lane == 0) { redf[0][wid] = mnx; redf[1][wid] = mxx; redf[2][wid] = mny; redf[3][wid] = mxy; }
+  __syncthreads();
+  mnx = INFINITY; mny = INFINITY; mxx = -INFINITY; mxy = -INFINITY;
+  for (int w = 0; w < nw; ++w) {
+    mnx = fminf(mnx, redf[0][w]); mxx = fmaxf(mxx, redf[1][w]); mny = fminf(mny, redf[2][w]); mxy = fmaxf(mxy, redf[3][w]);
+  }
+  // 2. grid (all threads compute the same values).  Non-finite extents (inf / nan positions) collapse to one cell
+  //    per axis: still correct, every pair is then tested.
+  float ex = mxx - mnx, ey = mxy - mny;
+  if (!(ex >= 0.f) || !(ex < 3.0e38f)) ex = 0.f;
+  if (!(ey >= 0.f) || !(ey < 3.0e38f)) ey = 0.f;
+  const bool one_cell = !(cell0 > 0.f) || !(cell0 < 3.0e38f) || !(mnx > -3.0e38f) || !(mny > -3.0e38f) ||
+                        (mxx - mnx != ex) || (mxy - mny != ey);
+  const float cx = fmaxf(cell0, ex * (1.f / (kCellDim - 0.5f)));
+  const float cy = fmaxf(cell0, ey * (1.f / (kCellDim - 0.5f)));
+  const int gx = one_cell ? 1 : min(kCellDim, (int)__fdiv_rn(ex, cx) + 1);
+  const int gy = one_cell ? 1 : min(kCellDim, (int)__fdiv_rn(ey, cy) + 1);
+  const int ncell = gx * gy;
+  for (int c = tid; c <= ncell; c += nt) cellstart[c] = 0;
+  __syncthreads();
+  // 3. counting sort by cell
+  for (int i = tid; i < N; i += nt) {
+    int c = 0;
+    if (!one_cell) {
+      const float2 p = sp[i];
+      int ix = (int)__fdiv_rn(p.x - mnx, cx), iy = (int)__fdiv_rn(p.y - mny, cy);   // NaN -> 0
+      ix = max(0, min(gx - 1, ix)); iy = max(0, min(gy - 1, iy));
+      c = iy * gx + ix;
+    }
+    cid[i] = c;
+    aux[i] = atomicAdd(&cellstart[c + 1], 1);      // counts live one slot up: the scan below turns them into starts
+  }
+  __syncthreads();
+  {  // inclusive scan of cellstart[1..ncell] (counts) in place -> cellstart[c] = start of cell c
+    int carry = 0;
+    for (int base = 1; base <= ncell; base += nt) {
+      const int c = base + tid;
+      const int v = c <= ncell ? cellstart[c] : 0;
+      int sc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+      if (lane == 31) wsum[wid] = sc;
+      __syncthreads();
+      if (wid == 0) {
+        int ws = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+        wsum[lane] = ws;
+      }
+      __syncthreads();
+      const int pre = (wid ? wsum[wid - 1] : 0) + carry;
+      if (c <= ncell) cellstart[c] = pre + sc;
+      carry += wsum[nw - 1];
+      __syncthreads();
+    }
+  }
+  // now cellstart[c] = number of nodes in cells < c ... shifted: cellstart[c+1] = inclusive end of cell c, [0] = 0
+  for (int i = tid; i < N; i += nt) un[cellstart[cid[i]] + aux[i]] = i;
+  __syncthreads();
+  for (int i = tid; i < N; i += nt) {
+    const int c = cid[i], s0 = cellstart[c], s1 = cellstart[c + 1];
+    int r = 0;
+    for (int q = s0; q < s1; ++q) r += un[q] < i;
+    lst[s0 + r] = i;
+  }
+  __syncthreads();
+
+  // 4. degrees
+  auto ranges = [&](int c, CellRanges& R) {
+    const int iy = c / gx, ix = c - iy * gx;
+    const int x0 = max(ix - 1, 0), x1 = min(ix + 1, gx - 1);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int y2 = iy + d - 1;
+      const bool ok = y2 >= 0 && y2 < gy;
+      R.lo[d] = ok ? cellstart[y2 * gx + x0] : 0;
+      R.hi[d] = ok ? cellstart[y2 * gx + x1 + 1] : 0;
+    }
+  };
+  auto edge = [&](float2 pi, int i, int j) -> bool {
+    const float2 pj = sp[j];
+    const float dx = pi.x - pj.x, dy = pi.y - pj.y;
+    const float sq = fmaf(dx, dx, dy * dy);
+    bool e = sq < thr_lo;
+    if (!e && !(sq > thr_hi)) e = csr_pair_exact(pi.x, pi.y, pj.x, pj.y, thr);
+    return e && j != i;
+  };
+  for (int i = tid; i < N; i += nt) {
+    CellRanges R;
+    ranges(cid[i], R);
+    const float2 pi = sp[i];
+    int d = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      for (int q = R.lo[k]; q < R.hi[k]; ++q) d += edge(pi, i, lst[q]) ? 1 : 0;
+    aux[i] = d;
+  }
+  __syncthreads();
+  // rowptr = exclusive scan of aux (kept in un[] for the fill pass)
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < N; base += nt) {
+    const int i = base + tid;
+    const int v = i < N ? aux[i] : 0;
+    int sc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (lane >= o) sc += t; }
+    if (lane == 31) wsum[wid] = sc;
+    __syncthreads();
+    if (wid == 0) {
+      int ws = lane < nw ? wsum[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += t; }
+      wsum[lane] = ws;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int excl = (wid ? wsum[wid - 1] : 0) + carry + sc - v;
+    if (i < N) { un[i] = excl; rp[i] = excl; }
+    __syncthreads();
+    if (tid == 0) carry_s = carry + wsum[nw - 1];
+    __syncthreads();
+  }
+  const int total = carry_s;
+  if (tid == 0) {
+    rp[N] = total;
+    if (colidx && (long long)total > nnz_stride && overflow) atomicMax(overflow, total);
+  }
+  if (!colidx) return;
+
+  // 5. fill: 9-way merge of ascending lists
+  int32_t* ci = colidx + (size_t)b * nnz_stride;
+  float* vv = vals ? vals + (size_t)b * nnz_stride : nullptr;
+  for (int i = tid; i < N; i += nt) {
+    const int c = cid[i];
+    const int iy = c / gx, ix = c - iy * gx;
+    int hd[9], en[9], hv[9];
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+#pragma unroll
+      for (int e = 0; e < 3; ++e) {
+        const int y2 = iy + d - 1, x2 = ix + e - 1;
+        const bool ok = y2 >= 0 && y2 < gy && x2 >= 0 && x2 < gx;
+        const int cc = ok ? y2 * gx + x2 : 0;
+        hd[d * 3 + e] = ok ? cellstart[cc] : 0;
+        en[d * 3 + e] = ok ? cellstart[cc + 1] : 0;
+        hv[d * 3 + e] = hd[d * 3 + e] < en[d * 3 + e] ? lst[hd[d * 3 + e]] : 0x7fffffff;
+      }
+    const float2 pi = sp[i];
+    long long w = un[i];
+    double isd_i = 0.0;
+    if (NORM) isd_i = inv_sqrt_deg(aux[i]);
+    for (;;) {
+      int best = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) best = min(best, hv[k]);
+      if (best == 0x7fffffff) break;
+#pragma unroll
+      for (int k = 0; k < 9; ++k)
+        if (hv[k] == best) {   // node indices are unique across the lists: exactly one k matches
+          ++hd[k];
+          hv[k] = hd[k] < en[k] ? lst[hd[k]] : 0x7fffffff;
+        }
+      if (edge(pi, i, best)) {
+        if (w < nnz_stride) {
+          ci[w] = best;
+          if (vv) vv[w] = NORM ? (float)__dmul_rn(inv_sqrt_deg(aux[best]), isd_i) : 1.f;
+        }
+        ++w;
+      }
+    }
+  }
+}
+
 }  // namespace gfc
 
 using namespace gfc;
@@ -281,5 +504,39 @@ extern "C" int gfc_csr_fill(const float* pos, int B, int N, double radius, int m
                                                                             ci0, v0);
     GFC_LAUNCH_CHECK("csr_rows_kernel<fill>");
   }
+  return GFC_OK;
+}
+
+extern "C" int gfc_csr_build(const float* pos, int B, int N, double radius, int mode, int32_t* rowptr,
+                             int64_t nnz_stride, int32_t* colidx, float* vals, int32_t* overflow, void* stream) {
+  launch_counter() = 0;
+  GFC_REQUIRE(B >= 0 && N >= 0 && nnz_stride >= 0, GFC_ERR_BAD_ARG, "gfc_csr_build: negative size");
+  if (B == 0) return GFC_OK;
+  GFC_REQUIRE(pos && rowptr, GFC_ERR_BAD_ARG, "gfc_csr_build: NULL pointer");
+  double thr; bool norm;
+  int rc = mode_threshold(mode, radius, &thr, &norm);
+  if (rc) return rc;
+  float lo, hi;
+  screen_band(thr, &lo, &hi);
+  DeviceInfo di;
+  rc = get_device_info(&di);
+  if (rc) return rc;
+  const size_t smem = (size_t)N * (sizeof(float2) + 4 * sizeof(int)) + (size_t)(kCellMax + 1) * sizeof(int);
+  GFC_REQUIRE(smem <= (size_t)di.smem_optin, GFC_ERR_UNSUPPORTED,
+              "gfc_csr_build: N=%d needs %zu B shared memory (> %d); use gfc_csr_count/scan/fill", N, smem, di.smem_optin);
+  // cell edge: 1.001 R (>= the largest distance the rule can accept, with room for the fp32 index rounding)
+  const double r_acc = thr > 0 ? sqrt(thr) : 0.0;
+  float cell0 = (float)(r_acc * 1.001);
+  if (!(cell0 > 0.f)) cell0 = 0.f;   // no edges possible (or everything): one cell
+  const int threads = N >= 1024 ? 1024 : (N > 512 ? 1024 : (N > 256 ? 512 : 256));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (norm) {
+    GFC_CUDA_TRY(cudaFuncSetAttribute(csr_build_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    csr_build_fused_kernel<true><<<B, threads, smem, st>>>(pos, N, thr, lo, hi, cell0, rowptr, nnz_stride, colidx, vals, overflow);
+  } else {
+    GFC_CUDA_TRY(cudaFuncSetAttribute(csr_build_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    csr_build_fused_kernel<false><<<B, threads, smem, st>>>(pos, N, thr, lo, hi, cell0, rowptr, nnz_stride, colidx, vals, overflow);
+  }
+  GFC_LAUNCH_CHECK("csr_build_fused_kernel");
   return GFC_OK;
 }

@@ -145,6 +145,17 @@ int gfc_csr_fill(const float* pos, int B, int N, double radius, int mode,
                  const int32_t* rowptr, int64_t nnz_stride,
                  int32_t* colidx, float* vals, void* stream);
 
+/* gfc_csr_build : the three steps above in ONE launch (one CTA per graph, cell list over a uniform grid of edge
+ *                 >= R instead of the O(N^2) pair walk; same bit-exact rule, same ascending columns).  nnz_stride is a
+ *                 per-graph CAPACITY chosen by the caller — no host round trip to size colidx, so the call can be
+ *                 captured in a CUDA graph: a graph that needs more sets *overflow = max(*overflow, needed nnz)
+ *                 (int32 device word, zeroed by the caller; may be NULL) and drops the surplus edges.  colidx NULL:
+ *                 sizing pass, only rowptr is written.  GFC_ERR_UNSUPPORTED when one graph's positions + lists do not
+ *                 fit shared memory (N above ~8000): use count/scan/fill.                                             */
+int gfc_csr_build(const float* pos, int B, int N, double radius, int mode,
+                  int32_t* rowptr, int64_t nnz_stride, int32_t* colidx, float* vals,
+                  int32_t* overflow, void* stream);
+
 /* CSR of S^T ("gather lists": row n holds the m with S[m,n] != 0, value S[m,n]).
  * vals may be NULL (all ones).  csr_t_* is the CSR of S itself, needed by the
  * backward; pass the same arrays when S is symmetric.                         */
