@@ -10,7 +10,7 @@ import ctypes as ct
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgfc.so")
+LIB_PATH = os.environ.get("GFC_LIB") or os.path.join(_HERE, "libgfc.so")   # GFC_LIB: an instrumented build (tools/)
 
 GFC_OK, GFC_ERR_BAD_ARG, GFC_ERR_UNSUPPORTED, GFC_ERR_WORKSPACE, GFC_ERR_CUDA, GFC_ERR_TIMEOUT = range(6)
 GSO_BINARY_LE, GSO_SYM_NORM_LT, GSO_BINARY_LT = 0, 1, 2

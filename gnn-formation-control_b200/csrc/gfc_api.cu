@@ -368,7 +368,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         WideArgs wa{};
         fill_wide_graph(wa.g, gs, a, norm);
         wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
-        wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs; wa.act = act; wa.slope = slope;
+        wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
         if (want_grads) {
           wa.amax = amax;   // max |dY o act'(y)| of the batch: by-product of the tile scales
           if (act != GFC_ACT_NONE) { wide_dpre = reinterpret_cast<float*>(wb + wws.dpre); wa.d_out = wide_dpre; }
@@ -390,7 +390,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         fill_wide_graph(da.g, gs, a, norm);
         da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre; da.amax = amax;
         da.dHp = dhp; da.dbp = db ? dbp : nullptr;
-        da.B = B; da.N = N; da.K = K; da.cshift = cs; da.act = act; da.slope = slope;
+        da.B = B; da.N = N; da.K = K; da.cshift = cs; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
         GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)npart * nH * sizeof(float), st));   // partials are accumulated with red.add
         rc = launch_wide_dh(da, G, F, np, st);
         if (rc) return rc;

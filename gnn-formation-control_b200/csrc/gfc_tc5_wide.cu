@@ -68,7 +68,7 @@ struct WideLayout {
   static constexpr int OFF_TAB = OFF_DEG + 2 * 2 * ROWS * 4; // float [3][128]: d^-1/2, 1/d, d^1/2 by degree
   static constexpr int OFF_MAX = OFF_TAB + 3 * 128 * 4;      // uint [16]: per-warp tile maxima
   static constexpr int OFF_BAR = OFF_MAX + 64;
-  static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 2 + 1 + 2 + 2;
+  static constexpr int NBAR = 2 * NSTAGE + 2 + 2 + 2 + 1 + 2 + 2 + 2;
   static constexpr int BYTES = OFF_BAR + NBAR * 8 + 16;
   static constexpr int TM_OUT = 0;                   // two output accumulators [128 x COUT]
   static constexpr int TM_HOP = 2 * COUT;            // two hop accumulators   [128 x CS]
@@ -98,7 +98,6 @@ __device__ __forceinline__ int row_degree4(const int* sdeg, int pbuf, int row) {
 // turn (round-2 timeline, tools/wide_clocks.py) a write-back queued behind ~2000-cycle epilogue pieces and the issuer
 // waited ~11k of every 20k cycles per tile.  The dH kernel still uses all 16 warps as one set.
 constexpr int kWideThreads = 576;
-constexpr int kWorkerWarps = 16;
 constexpr int kGroupWarps = 8;
 int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
 int g_wide_no_prefetch = 0;    // experiment switch
@@ -175,10 +174,9 @@ __device__ __forceinline__ float ldg_cg(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 __device__ __forceinline__ void group_b_bar() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
-struct WideMaps { CUtensorMap m[3]; };   // y store boxes: 32 rows / the partial third / the partial fourth row quadrant of a tile
+struct WideMaps { CUtensorMap m[2]; };   // y store boxes: 32 rows / the one partial row quadrant of a tile (rows_full % 32 rows)
 
 // act(v) = v > 0 ? v : v * neg   (neg: 1 none, 0 relu, slope leaky) == max(v, v neg) for neg <= 1, min(v, v neg) otherwise
 __device__ __forceinline__ float act_fast(float v, float neg, bool use_min) {
@@ -200,7 +198,12 @@ __device__ __forceinline__ void fill_degree_tables(float* tab, int tid, int nthr
 //   hop(k,0) taps(k,0) hop(k,1) taps(k,1) hop(k+1,0) ...
 // hop(k,s) reads W_k[s] (buffer b) and commits hop_done[s]; the workers then write W_{k+1}[s] into buffer 1-b while
 // taps(k,s), hop(k,1-s) and taps(k,1-s) execute — about 2000 tensor-pipe cycles of slack for one write-back.
-// Barriers:  w_ready[s]  workers -> issuer   W_k[s] written (K per tile: the W_0 store and K-1 write-backs)
+// Barriers:  w_ready[s]  group A -> issuer   W_k[s] written, k >= 1 (K-1 write-backs per tile)
+//            w0_ready[s] group B -> issuer   W_0[s] of a tile written.  NOT the same barrier as w_ready[s]: group B may
+//                        publish the next tile's W_0[s] (it only waits for w0_free[s]) before the issuer has polled for
+//                        W_{K-1}[s] of the running tile; on a shared barrier two phases then complete between two polls,
+//                        the parity the issuer waits for comes round again and the kernel hangs (seen as soon as the
+//                        tile-maximum pass got faster; profiles/r2/wide_timeline_notes.md)
 //            hop_done[s] issuer  -> workers  hop(k,s) complete (K-1 per tile)
 //            w0_free[s]  issuer  -> workers  taps(K-2,s) complete: W_{K-2}[s]'s buffer may take the next tile's W_0
 //            h_full/h_empty[2]   TMA producer <-> issuer, one stage = all tap planes of a phase
@@ -227,7 +230,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
   uint64_t* p_ready = w0_free + 2;              // [1]
   uint64_t* out_full = p_ready + 1;             // [2]
   uint64_t* out_free = out_full + 2;            // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(out_free + 2);
+  uint64_t* w0_ready = out_free + 2;            // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w0_ready + 2);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
@@ -244,7 +248,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
   if (tid == 0) {
     for (int i = 0; i < L::NSTAGE; ++i) { tc5::mbar_init(&h_full[i], 1); tc5::mbar_init(&h_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      tc5::mbar_init(&w_ready[i], kGroupWarps);    // W_0 by group B, W_k (k >= 1) by group A
+      tc5::mbar_init(&w_ready[i], kGroupWarps);    // W_k (k >= 1) by group A
+      tc5::mbar_init(&w0_ready[i], kGroupWarps);   // W_0 by group B
       tc5::mbar_init(&hop_done[i], 1);
       tc5::mbar_init(&w0_free[i], 1);
       tc5::mbar_init(&out_full[i], 1);
@@ -269,7 +274,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       constexpr uint32_t kIdescTap = tc5::idesc_f16(128, COUT, 0, 0);
       constexpr uint32_t kIdescHop = tc5::idesc_f16(128, L::CS, 0, 1);
       const uint32_t w_addr = tc5::smem_u32(Wb), r_addr = tc5::smem_u32(Rb);
-      uint32_t par_wr = 0, par_of = 0, par_pr = 0, par_hf = 0;
+      uint32_t par_wr = 0, par_w0 = 0, par_of = 0, par_pr = 0, par_hf = 0;
       int st = 0;
       const int hop_ksteps = (w.gpc * N + 15) >> 4;
       int it = 0;
@@ -290,7 +295,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         for (int ph = 0; ph < 2 * K; ++ph) {
           const int k = ph >> 1, s = ph & 1;
           GFC_WSTAMP(100 + ph);
-          tc5::mbar_wait(&w_ready[s], (par_wr >> s) & 1); par_wr ^= 1u << s;
+          if (k == 0) { tc5::mbar_wait(&w0_ready[s], (par_w0 >> s) & 1); par_w0 ^= 1u << s; }
+          else { tc5::mbar_wait(&w_ready[s], (par_wr >> s) & 1); par_wr ^= 1u << s; }
           tc5::fence_after_sync();
           GFC_WSTAMP(200 + ph);
           const uint32_t ws = w_addr + (2 * s + ((it * K + k) & 1)) * L::SLAB;   // state k of a slab alternates between two buffers
@@ -333,6 +339,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         }
         tc5::mma_commit(&out_full[ob]);
       }
+#undef GFC_WSTAMP
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -437,7 +444,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     // (gpc N < 128) uses a tensor map with a shorter box.
     unsigned char* slot_out = stage_out + gw * 2048;
     const int hq = min(32, max(0, w.gpc * N - 32 * q));
-    const CUtensorMap* my_map = hq == 32 ? &maps.m[0] : (q == 2 ? &maps.m[1] : &maps.m[2]);
+    const CUtensorMap* my_map = hq == 32 ? &maps.m[0] : &maps.m[1];
     float xin[L::CPT];
     float2 mypos = make_float2(0.f, 0.f);
     uint32_t par_ofl = 0, par_w0 = 0;
@@ -461,7 +468,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     // rows (full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle at
     // store time.  Warp gw owns rows 16 gw .. 16 gw + 15, lane = (row offset, piece).
     constexpr int PPR = L::CS / 4, RPI = 32 / PPR, NPC = L::CPT / 4;   // pieces per row, rows per instruction, pieces per thread
-    static_assert(NPC % 2 == 0 && RPI * NPC == 16, "piece mapping");
+    static_assert(NPC % 4 == 0 && RPI * NPC == 16, "piece mapping");
     auto load_slab = [&](int tile, int s) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
@@ -472,23 +479,40 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
 #pragma unroll
         for (int i = 0; i < L::CPT; ++i) { xin[i] = ldg_f32(src, valid); src += N; }
       } else {
+        // Loads are issued in batches of four pieces (dY and, for the mask, y) BEFORE the first value is used: with
+        // load / use / load / use every piece cost a full L2 round trip (8 per slab, ~7k cycles: the issuer idled
+        // 19k of every 33k cycles per tile in the dX kernel, profiles/r2/wide_timeline_notes.md).
         const int rows_used = gcount * N;
+        const bool masked = MODE == 1 && w.act != GFC_ACT_NONE;
 #pragma unroll
-        for (int i = 0; i < NPC; ++i) {
-          const int row = 16 * gw + RPI * i + lane / PPR;
-          const bool ok = row < rows_used;
-          const size_t off = ((size_t)b0 * N + row) * CIN + s * L::CS + 4 * (lane % PPR);
-          float4 v = ldg_f32x4(w.in + off, ok);
-          if (MODE == 1 && w.act != GFC_ACT_NONE) {
-            const float4 yo = ldg_f32x4(w.yout + off, ok);
-            v.x = act_grad(v.x, yo.x, w.act, w.slope);
-            v.y = act_grad(v.y, yo.y, w.act, w.slope);
-            v.z = act_grad(v.z, yo.z, w.act, w.slope);
-            v.w = act_grad(v.w, yo.w, w.act, w.slope);
-            // hand dY o act'(y) to the dH kernel: it then streams ONE tensor and never waits on the mask
-            if (w.d_out && ok) *reinterpret_cast<float4*>(w.d_out + off) = v;
+        for (int hb = 0; hb < NPC; hb += 4) {
+          float4 vv[4], yy[4];
+          size_t off[4];
+          bool ok[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int row = 16 * gw + RPI * (hb + i) + lane / PPR;
+            ok[i] = row < rows_used;
+            off[i] = ((size_t)b0 * N + row) * CIN + s * L::CS + 4 * (lane % PPR);
+            vv[i] = ldg_f32x4(w.in + off[i], ok[i]);
           }
-          xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+          if (masked) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) yy[i] = ldg_f32x4(w.yout + off[i], ok[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              vv[i].x = act_grad(vv[i].x, yy[i].x, w.act, w.slope);
+              vv[i].y = act_grad(vv[i].y, yy[i].y, w.act, w.slope);
+              vv[i].z = act_grad(vv[i].z, yy[i].z, w.act, w.slope);
+              vv[i].w = act_grad(vv[i].w, yy[i].w, w.act, w.slope);
+              // hand dY o act'(y) to the dH kernel: it then streams ONE tensor and never waits on the mask
+              if (w.d_out && ok[i]) *reinterpret_cast<float4*>(w.d_out + off[i]) = vv[i];
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            xin[4 * (hb + i)] = vv[i].x; xin[4 * (hb + i) + 1] = vv[i].y; xin[4 * (hb + i) + 2] = vv[i].z; xin[4 * (hb + i) + 3] = vv[i].w;
+          }
         }
       }
     };
@@ -565,10 +589,18 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       const float4* p = reinterpret_cast<const float4*>(w.in + (size_t)b0 * N * CIN);
       const int n4 = gcount * N * (CIN / 4);
       float m = 0.f;
-#pragma unroll 4
-      for (int i = wt; i < n4; i += 32 * kGroupWarps) {
-        const float4 v = __ldg(p + i);
-        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+      // eight independent 16-byte loads in flight per thread and round trip (a full 128 x 128 tile = 2 round trips)
+#pragma unroll 1
+      for (int i0 = wt; i0 < n4; i0 += 8 * 32 * kGroupWarps) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int i = i0 + u * 32 * kGroupWarps;
+          v[u] = ldg_f32x4(reinterpret_cast<const float*>(p + (i < n4 ? i : 0)), i < n4);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          m = fmaxf(fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
       }
       if (MODE == 1 && w.act == GFC_ACT_LEAKY_RELU && w.slope > 1.f) m *= w.slope;   // |dY o act'(y)| <= |dY| max(1, slope)
       return m;
@@ -669,7 +701,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
           tc5::fence_proxy_async();
           tc5::fence_before_sync();
           __syncwarp();
-          if (lane == 0) tc5::mbar_arrive(&w_ready[s]);
+          if (lane == 0) tc5::mbar_arrive(&w0_ready[s]);
           GFC_KSTAMP(420 + s);
         }
       }
@@ -718,7 +750,7 @@ struct DhLayout {
   static constexpr int OFF_TAB = OFF_DEG + 2 * 4 * ROWS * 4;
   static constexpr int OFF_DB = OFF_TAB + 3 * 128 * 4;
   static constexpr int OFF_BAR = OFF_DB + FH * 4;
-  static constexpr int NBAR = 6;
+  static constexpr int NBAR = 7;
   static constexpr int BYTES_MIN = OFF_BAR + NBAR * 8 + 16;
   static constexpr int BYTES = BYTES_MIN < 120 * 1024 ? 120 * 1024 : BYTES_MIN;   // one CTA per SM (TMEM is taken whole)
   static constexpr int TM_X = 0;                     // NP planes x 64 columns (128 rows, two per column)
@@ -728,7 +760,17 @@ struct DhLayout {
   static_assert(BYTES <= 227 * 1024, "shared memory");
 };
 
-template <int G, int F, int FH, int NP>
+// Roles (v4): warp 0 = MMA issuer, warp 1 = TMEM owner, warps 2..9 = group A, warps 10..17 = group B.
+//   Group A does ONLY the write-backs hop result -> fp16 planes of V_{k+1}: the one piece of CUDA-core work between
+//   two MMAs of the chain.  Group B prepares the NEXT tile (positions, P, V_0, X^T) one tile ahead of the issuer and
+//   drains the accumulators.  With one worker set doing everything in turn (round-2 timeline,
+//   profiles/r2/wide_timeline_notes.md) the chain waited on the next tile's loads: ~11k of every 18-23k cycles.
+//   The issuer runs the chain hop-first:  hop(0) | hop(1) dH(0) | hop(2) dH(1) | ... | dH(K-1)  so that the X^T
+//   store of the tile (which must wait for the previous tile's last product) is not needed before hop(1).
+// Barriers: v0_ready (B -> issuer: V_0 planes), v_ready (A -> issuer: V_k, k >= 1), hop_done (issuer -> A),
+//   p_ready / x_ready (B -> issuer), item_done (issuer -> B: every product of the tile complete),
+//   v0_free (issuer -> B: the ring buffer that takes the next tile's V_0 has been read for the last time).
+template <int G, int F, int FH, int NP, bool NV4>
 __global__ void __launch_bounds__(kWideThreads, 1)
 tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   using L = DhLayout<G, F, FH, NP>;
@@ -740,15 +782,14 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   float* dtab = reinterpret_cast<float*>(wsmem + L::OFF_TAB);
   float* dbs = reinterpret_cast<float*>(wsmem + L::OFF_DB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(wsmem + L::OFF_BAR);
-  uint64_t* v_ready = bars;          // workers -> issuer: the next V buffer is written
-  uint64_t* hop_done = bars + 1;     // issuer (commit) -> workers: hop result in TMEM, older MMAs complete
-  uint64_t* item_done = bars + 2;    // issuer (commit) -> workers: every MMA of the tile complete
+  uint64_t* v_ready = bars;
+  uint64_t* hop_done = bars + 1;
+  uint64_t* item_done = bars + 2;
   uint64_t* p_ready = bars + 3;
   uint64_t* x_ready = bars + 4;
-  // V_0 of the next tile has its own barrier: a fast warp may publish it right after its last write-back, and
-  // on a shared barrier that second arrival could complete the write-back phase before a slow warp arrived
   uint64_t* v0_ready = bars + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* v0_free = bars + 6;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = w.N, K = w.K;
@@ -764,12 +805,13 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   for (int i = tid; i < FH; i += kWideThreads) dbs[i] = 0.f;
   fill_degree_tables(dtab, tid, kWideThreads);
   if (tid == 0) {
-    tc5::mbar_init(v_ready, kWorkerWarps);
+    tc5::mbar_init(v_ready, kGroupWarps);
     tc5::mbar_init(hop_done, 1);
     tc5::mbar_init(item_done, 1);
-    tc5::mbar_init(p_ready, kWorkerWarps);
-    tc5::mbar_init(x_ready, kWorkerWarps);
-    tc5::mbar_init(v0_ready, kWorkerWarps);
+    tc5::mbar_init(p_ready, kGroupWarps);
+    tc5::mbar_init(x_ready, kGroupWarps);
+    tc5::mbar_init(v0_ready, kGroupWarps);
+    tc5::mbar_init(v0_free, 1);
     tc5::fence_mbar_init();
   }
   if (warp == 1) tc5::tmem_alloc(tmem_ptr, 512);
@@ -779,6 +821,13 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   tc5::fence_after_sync();
   const uint32_t tmem = *tmem_ptr;
 
+  auto publish = [&](uint64_t* bar) {
+    tc5::fence_proxy_async();
+    tc5::fence_before_sync();
+    __syncwarp();
+    if (lane == 0) tc5::mbar_arrive(bar);
+  };
+
   if (warp == 0) {
     // =========================== MMA issuer (one elected thread) ===============================
     if (tc5::elect_one()) {
@@ -787,33 +836,24 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       uint32_t par_vr = 0, par_v0 = 0, par_pr = 0, par_xr = 0;
       const int ksteps = (w.gpc * N + 15) >> 4;
       int it = 0, vbase = 0;
+      int nstamp = 0;
+      const bool dbg = w.dbg != nullptr && blockIdx.x == 0;
+#ifdef GFC_WIDE_TIMELINE
+#define GFC_WSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[2 * nstamp] = clock64(); w.dbg[2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#else
+#define GFC_WSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
+#endif
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        GFC_WSTAMP(1);
         tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
-        const bool fresh = (it % w.flush_every) == 0;   // the workers drained the accumulators before x_ready
+        GFC_WSTAMP(3);
+        const bool fresh = (it % w.flush_every) == 0;   // group B drained the accumulators before x_ready
         const uint32_t pa = p_addr + (it & 1) * L::P_BYTES;
-#pragma unroll 1
-        for (int k = 0; k < K; ++k) {
-          if (k == 0) { tc5::mbar_wait(v0_ready, par_v0); par_v0 ^= 1; }
-          else { tc5::mbar_wait(v_ready, par_vr); par_vr ^= 1; }
-          tc5::fence_after_sync();
-          const uint32_t vs = v_addr + ((vbase + k) % 3) * L::VBUF;
-          if (k + 1 < K) {
-            // hop: D_hop = P * V_k
-            uint32_t acc = 0;
-#pragma unroll 1
-            for (int j = 0; j < ksteps; ++j) {
-              const uint64_t da = make_desc(pa + j * 2 * L::PW, L::PW, 128);
-#pragma unroll
-              for (int pl = 0; pl < NP; ++pl) {
-                tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdesc, acc);
-                acc = 1;
-              }
-            }
-            tc5::mma_commit(hop_done);
-          }
-          if (k == 0) { tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1; tc5::fence_after_sync(); }
-          // dH: acc(k)[g][f] += X^T[g][rows] * V_k[rows][f]   (hi hi + hi lo + lo hi, A from tensor memory)
-          const uint32_t d_acc = tmem + L::TM_ACC + k * FH;
+        // dH product of tap kk:  acc(kk)[g][f] += X^T[g][rows] * V_kk[rows][f]   (hi hi + hi lo + lo hi, A from tensor memory)
+        auto issue_dh = [&](int kk) {
+          if (kk == 0) { tc5::mbar_wait(x_ready, par_xr); par_xr ^= 1; tc5::fence_after_sync(); GFC_WSTAMP(260); }
+          const uint32_t vs = v_addr + ((vbase + kk) % 3) * L::VBUF;
+          const uint32_t d_acc = tmem + L::TM_ACC + kk * FH;
 #pragma unroll 1
           for (int j = 0; j < ksteps; ++j) {
             const uint32_t xa = tmem + L::TM_X + j * 8;
@@ -826,43 +866,119 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
               tc5::mma_bf16_ts(d_acc, xa + 64, b0, kIdesc, 1u);
             }
           }
+          // the ring buffer of V_{K-3} takes the next tile's V_0
+          if (K >= 3 && kk == K - 3) tc5::mma_commit(v0_free);
+          GFC_WSTAMP(300 + kk);
+        };
+#pragma unroll 1
+        for (int k = 0; k < K; ++k) {
+          GFC_WSTAMP(100 + k);
+          if (k == 0) { tc5::mbar_wait(v0_ready, par_v0); par_v0 ^= 1; }
+          else { tc5::mbar_wait(v_ready, par_vr); par_vr ^= 1; }
+          tc5::fence_after_sync();
+          GFC_WSTAMP(200 + k);
+          if (k + 1 < K) {
+            // hop: D_hop = P * V_k
+            const uint32_t vs = v_addr + ((vbase + k) % 3) * L::VBUF;
+            uint32_t acc = 0;
+#pragma unroll 1
+            for (int j = 0; j < ksteps; ++j) {
+              const uint64_t da = make_desc(pa + j * 2 * L::PW, L::PW, 128);
+#pragma unroll
+              for (int pl = 0; pl < NP; ++pl) {
+                tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdesc, acc);
+                acc = 1;
+              }
+            }
+            tc5::mma_commit(hop_done);
+            GFC_WSTAMP(250 + k);
+          }
+          if (k >= 1) issue_dh(k - 1);
         }
+        issue_dh(K - 1);
         tc5::mma_commit(item_done);
         vbase = (vbase + K) % 3;
       }
+#undef GFC_WSTAMP
     }
     __syncwarp();
-  } else if (warp >= 2) {
-    // =========================== workers ======================================================
-    const int wt = tid - 64;                   // 0..511
-    const int ww = warp - 2;                   // 0..15
+  } else if (warp >= 2 && warp < 2 + kGroupWarps) {
+    // =========================== group A: write-backs of the hop chain ==========================
+    const int gw = warp - 2;                   // 0..7
+    const int q = warp & 3;                    // TMEM lane quadrant
+    const int half = gw >> 2;                  // column half of the feature slice
+    const int r = q * 32 + lane;               // tile row = TMEM lane
+    const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
+    constexpr int CPA = FH / 2;                // columns per thread
+    uint32_t par_hd = 0;
+    int vbase = 0, it = 0;
+    int nstamp = 0;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
+#ifdef GFC_WIDE_TIMELINE
+#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[4096 + 2 * nstamp] = clock64(); w.dbg[4096 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#else
+#define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
+#endif
+    for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+      float wbf = 1.f;
+#pragma unroll 1
+      for (int k = 0; k + 1 < K; ++k) {
+        GFC_KSTAMP(100 + k);
+        tc5::mbar_wait_suspend(hop_done, par_hd); par_hd ^= 1;
+        tc5::fence_after_sync();
+        GFC_KSTAMP(200 + k);
+        // sym-norm: Vhat_{k+1} = D^-1 (A Vhat_k); this tile's degrees were published by group B with its P
+        if (norm && k == 0) wbf = dtab[128 + row_degree(sdeg, it & 1, r)];
+        unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (half * (CPA / 8)) * L::PW + r * 16;
+        const uint32_t taddr = tm_lane + TM_HOP + half * CPA;
+        uint32_t v[CPA];
+        if constexpr (CPA == 32) tc5::tmem_ld32(taddr, v); else tc5::tmem_ld16(taddr, v);
+        tc5::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < CPA / 8; ++c) {
+          float f[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf : __uint_as_float(v[c * 8 + i]);
+          store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
+        }
+        publish(v_ready);
+        GFC_KSTAMP(300 + k);
+      }
+      vbase = (vbase + K) % 3;
+    }
+#undef GFC_KSTAMP
+  } else if (warp >= 2 + kGroupWarps) {
+    // =========================== group B: next tile's operands, accumulator drains ===============
+    const int gw = warp - (2 + kGroupWarps);   // 0..7
+    const int wt = tid - 32 * (2 + kGroupWarps);   // 0..255
     const int q = warp & 3;
-    const int qtr = ww >> 2;                   // column quarter (write-back, drain) / row quarter (X^T)
-    const int r = q * 32 + lane;               // tile row (write-back) and feature lane g (X^T, drain)
+    const int half = gw >> 2;                  // column half (drain) / row half (X^T) / chunk parity (P)
+    const int r = q * 32 + lane;               // tile row (P) and feature lane g (X^T, drain)
     const int jr = r / N;
     const bool g_ok = r < G;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
-    constexpr int PPR = FH / 4, RPI = 32 / PPR, NPC = FH / 16;   // V_0 loads: 16-byte pieces per row, rows per warp instruction, pieces per thread
-    static_assert(RPI * NPC == 8 && NPC % 2 == 0, "piece mapping");
-    float xt[32];                              // x[g][rows 32 qtr .. 32 qtr + 31] of the next tile (two 16-lane halves)
-    float xin[4 * NPC];                        // V_0 pieces of the next tile (short-lived)
+    // V_0 loads: 16-byte pieces per row, rows per warp instruction, pieces per thread; warp gw owns rows 16 gw .. 16 gw + 15
+    constexpr int PPR = FH / 4, RPI = 32 / PPR, NPC = 16 / RPI;
+    static_assert(RPI * NPC == 16 && NPC % 4 == 0, "piece mapping");
+    float xt[32];                              // x[g][32 rows] of the next tile: one row quarter at a time (register budget: 96)
+    float xin[4 * NPC];                        // V_0 pieces of the next tile (dead before xt is loaded)
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};     // column sums of V_0 (columns 4*(lane % PPR) .. +3)
     float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_hd = 0, par_id = 0;
+    uint32_t par_id = 0, par_vf = 0;
     // launch-wide operand scales (powers of two) from the batch maxima
     float inv_sx, inv_sv;
     const int xtop = norm ? kWideTop - 4 : kWideTop;   // Xhat = D^1/2 X grows by < 2^3.5 (N <= 128)
     const float s_x = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax)), xtop, &inv_sx);
     const float s_v = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax + 1)), kWideTop, &inv_sv);
     const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;   // an edge of P = 2^-c: the hop result is V_{k+1} 2^(-c (k+1)) directly
-    float wbf_live = 1.f, wbf_next = 1.f;
+    int nstamp = 0;
+    const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && wt == 0;
+#ifdef GFC_WIDE_TIMELINE
+#define GFC_KSTAMP(tag) do { if (dbg && nstamp < 2000) { w.dbg[8192 + 2 * nstamp] = clock64(); w.dbg[8192 + 2 * nstamp + 1] = (tag); ++nstamp; } } while (0)
+#else
+#define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
+#endif
 
-    auto publish = [&](uint64_t* bar) {
-      tc5::fence_proxy_async();
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(bar);
-    };
     auto load_pos = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
@@ -882,102 +998,119 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     };
     // X^T operand: x[(b0 + j), g, n] -> TMEM lane g, column (tile row / 2).  The 16x256b store shape lets a
     // thread own 4 consecutive tile rows (one float4 of x) of the feature lanes  16 h + t/4  and  16 h + t/4 + 8:
-    // a warp load instruction then touches 8 lines instead of 32.  This warp covers tile rows 32 qtr .. 32 qtr + 31
-    // (16 TMEM columns): xt[16 h + 8 rho + 4 gs + i] = x[g = 32 q + 16 h + 8 gs + t/4][row 32 qtr + 16 rho + 4 (t%4) + i].
-    auto load_xt_part = [&](int tile, auto h16_c) {
-      constexpr int h16 = decltype(h16_c)::value;   // compile-time register indices (no local-memory array)
+    // a warp load instruction then touches 8 lines instead of 32.  This warp covers the two 32-row quarters
+    // qtr = 2 half + qq (16 TMEM columns each):
+    //   xt[16 h + 8 rho + 4 gs + i] = x[g = 32 q + 16 h + 8 gs + t/4][row 32 qtr + 16 rho + 4 (t%4) + i].
+    // All loads of a tile are issued before the first use (volatile asm, no consumer in between).
+    auto load_xt = [&](int tile, int qq) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
-#pragma unroll
-      for (int rho = 0; rho < 2; ++rho) {
-#pragma unroll
-        for (int gs = 0; gs < 2; ++gs) {     // feature lane t/4 (+ 8)
-          const int g = q * 32 + 16 * h16 + 8 * gs + (lane >> 2);
-          const int rr = qtr * 32 + 16 * rho + 4 * (lane & 3);
-          float* dst = &xt[16 * h16 + 8 * rho + 4 * gs];
-          if ((N & 3) == 0) {
-            const int j = rr / N, n = rr - j * N;
-            const float4 v = ldg_f32x4(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr < rows_used);
-            dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int j = (rr + i) / N, n = (rr + i) - j * N;
-              dst[i] = ldg_f32(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr + i < rows_used);
-            }
-          }
-        }
-      }
-    };
-    auto load_xt_half = [&](int tile, int h16) {
-      if (h16 == 0) load_xt_part(tile, std::integral_constant<int, 0>{});
-      else load_xt_part(tile, std::integral_constant<int, 1>{});
-    };
-    auto store_xt = [&](int pbuf) {
-      if (q * 32 < G) {   // warp-uniform: this quadrant holds real feature lanes
-        // row factors of the 8 tile rows this thread touches: S_x (x d^1/2 for sym-norm); row = 32 qtr + 16 rho + 4 (lane&3) + i
-        float rf[2][4];
-#pragma unroll
-        for (int rho = 0; rho < 2; ++rho) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float f0 = s_x;
-            if (norm) f0 *= dtab[256 + row_degree4(sdeg, pbuf, qtr * 32 + 16 * rho + 4 * (lane & 3) + i)];
-            rf[rho][i] = f0;
-          }
-        }
+      {
 #pragma unroll
         for (int h16 = 0; h16 < 2; ++h16) {
-          uint32_t p0[8], p1[8];
 #pragma unroll
           for (int rho = 0; rho < 2; ++rho) {
 #pragma unroll
             for (int gs = 0; gs < 2; ++gs) {
-              const float* src = &xt[16 * h16 + 8 * rho + 4 * gs];
-              const float a = src[0] * rf[rho][0], b = src[1] * rf[rho][1], c = src[2] * rf[rho][2], d = src[3] * rf[rho][3];
-              if (NP == 2) {
-                tc5::split_f16x2(a, b, p0[4 * rho + 2 * gs], p1[4 * rho + 2 * gs]);
-                tc5::split_f16x2(c, d, p0[4 * rho + 2 * gs + 1], p1[4 * rho + 2 * gs + 1]);
+              const int g = q * 32 + 16 * h16 + 8 * gs + (lane >> 2);
+              const int rr = (2 * half + qq) * 32 + 16 * rho + 4 * (lane & 3);
+              float* dst = &xt[16 * h16 + 8 * rho + 4 * gs];
+              if constexpr (NV4) {
+                const int j = rr / N, n = rr - j * N;
+                const float4 v = ldg_f32x4(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr < rows_used);
+                dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
               } else {
-                p0[4 * rho + 2 * gs] = tc5::pack_f16x2(a, b);
-                p0[4 * rho + 2 * gs + 1] = tc5::pack_f16x2(c, d);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int j = (rr + i) / N, n = (rr + i) - j * N;
+                  dst[i] = ldg_f32(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr + i < rows_used);
+                }
               }
             }
           }
-          const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * h16) << 16) + L::TM_X + qtr * 16;
-          tc5::tmem_st_16x256b_x2(ta, p0);
-          if (NP == 2) tc5::tmem_st_16x256b_x2(ta + 64, p1);
         }
-        tc5::tmem_st_wait();
       }
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(x_ready);
     };
-    // V_0 = dY o act'(y) of this CTA's feature slice: coalesced pieces -> registers (+ db), then planes.
-    // Warp ww owns tile rows 8 ww .. 8 ww + 7.
+    auto store_xt = [&](int pbuf, int qq) {
+      if (q * 32 < G) {   // warp-uniform: this quadrant holds real feature lanes
+        {
+          const int qtr = 2 * half + qq;
+          // row factors of the 8 tile rows this thread touches: S_x (x d^1/2 for sym-norm); row = 32 qtr + 16 rho + 4 (lane&3) + i
+          float rf[2][4];
+#pragma unroll
+          for (int rho = 0; rho < 2; ++rho) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float f0 = s_x;
+              if (norm) f0 *= dtab[256 + row_degree(sdeg, pbuf, qtr * 32 + 16 * rho + 4 * (lane & 3) + i)];
+              rf[rho][i] = f0;
+            }
+          }
+#pragma unroll
+          for (int h16 = 0; h16 < 2; ++h16) {
+            uint32_t p0[8], p1[8];
+#pragma unroll
+            for (int rho = 0; rho < 2; ++rho) {
+#pragma unroll
+              for (int gs = 0; gs < 2; ++gs) {
+                const float* src = &xt[16 * h16 + 8 * rho + 4 * gs];
+                const float a = src[0] * rf[rho][0], b = src[1] * rf[rho][1], c = src[2] * rf[rho][2], d = src[3] * rf[rho][3];
+                if (NP == 2) {
+                  tc5::split_f16x2(a, b, p0[4 * rho + 2 * gs], p1[4 * rho + 2 * gs]);
+                  tc5::split_f16x2(c, d, p0[4 * rho + 2 * gs + 1], p1[4 * rho + 2 * gs + 1]);
+                } else {
+                  p0[4 * rho + 2 * gs] = tc5::pack_f16x2(a, b);
+                  p0[4 * rho + 2 * gs + 1] = tc5::pack_f16x2(c, d);
+                }
+              }
+            }
+            const uint32_t ta = tmem + ((uint32_t)(q * 32 + 16 * h16) << 16) + L::TM_X + qtr * 16;
+            tc5::tmem_st_16x256b_x2(ta, p0);
+            if (NP == 2) tc5::tmem_st_16x256b_x2(ta + 64, p1);
+          }
+        }
+        if (qq == 1) tc5::tmem_st_wait();
+      }
+      if (qq == 1) {
+        tc5::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc5::mbar_arrive(x_ready);
+      }
+    };
+    // V_0 = dY o act'(y) of this CTA's feature slice: coalesced pieces -> registers, then planes (+ db).
+    // Every load is issued before the first value is used (the mask path used to cost one round trip per piece).
     auto load_v0 = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
+      const bool masked = w.dpre == nullptr && w.act != GFC_ACT_NONE;
+      const float* src = w.dpre ? w.dpre : w.dY;
 #pragma unroll
-      for (int i = 0; i < NPC; ++i) {
-        const int row = 8 * ww + RPI * i + lane / PPR;
-        const bool ok = row < rows_used;
-        const size_t off = ((size_t)b0 * N + row) * F + fh * FH + 4 * (lane % PPR);
-        float4 v;
-        if (w.dpre) {
-          v = ldg_f32x4(w.dpre + off, ok);      // not consumed before store_v0: the load latency is never exposed
-        } else {
-          v = ldg_f32x4(w.dY + off, ok);
-          if (w.act != GFC_ACT_NONE) {
-            const float4 yo = ldg_f32x4(w.yout + off, ok);
-            v.x = act_grad(v.x, yo.x, w.act, w.slope);
-            v.y = act_grad(v.y, yo.y, w.act, w.slope);
-            v.z = act_grad(v.z, yo.z, w.act, w.slope);
-            v.w = act_grad(v.w, yo.w, w.act, w.slope);
+      for (int hb = 0; hb < NPC; hb += 4) {
+        float4 vv[4], yy[4];
+        size_t off[4];
+        bool ok[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = 16 * gw + RPI * (hb + i) + lane / PPR;
+          ok[i] = row < rows_used;
+          off[i] = ((size_t)b0 * N + row) * F + fh * FH + 4 * (lane % PPR);
+          vv[i] = ldg_f32x4(src + off[i], ok[i]);
+        }
+        if (masked) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) yy[i] = ldg_f32x4(w.yout + off[i], ok[i]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            vv[i].x = act_grad(vv[i].x, yy[i].x, w.act, w.slope);
+            vv[i].y = act_grad(vv[i].y, yy[i].y, w.act, w.slope);
+            vv[i].z = act_grad(vv[i].z, yy[i].z, w.act, w.slope);
+            vv[i].w = act_grad(vv[i].w, yy[i].w, w.act, w.slope);
           }
         }
-        xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          xin[4 * (hb + i)] = vv[i].x; xin[4 * (hb + i) + 1] = vv[i].y; xin[4 * (hb + i) + 2] = vv[i].z; xin[4 * (hb + i) + 3] = vv[i].w;
+        }
       }
     };
     auto store_v0 = [&](unsigned char* vbuf, int pbuf) {
@@ -997,27 +1130,27 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) rcv[e] = __shfl_xor_sync(0xffffffffu, snd[e], 1);
-        const int row = 8 * ww + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
+        const int row = 16 * gw + RPI * (i + (odd ? 1 : 0)) + lane / PPR;
         float f0 = s_v;
-        if (norm) f0 *= dtab[row_degree4(sdeg, pbuf, row)];
+        if (norm) f0 *= dtab[row_degree(sdeg, pbuf, row)];
         float v[8];
 #pragma unroll
         for (int e = 0; e < 4; ++e) { v[e] = (odd ? rcv[e] : own[e]) * f0; v[4 + e] = (odd ? own[e] : rcv[e]) * f0; }
         store_chunk_f16<NP>(vbuf + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
       }
     };
-    // P[r][c] (smem, K-major A operand): slots t0..t1-1 of the 4 chunks (qc = 4 t + qtr) this thread owns
-    int degcnt = 0;
-    auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
+    // P[r][c] (smem, K-major A operand): this thread owns row r and every second chunk of 8 source rows
+    auto build_p = [&](int tile, int pbuf) {
       const float2* sp = sp_all + pbuf * L::ROWS;
       unsigned char* pb = Pb + pbuf * L::P_BYTES;
       const int rows_used = min(w.gpc, w.B - tile * w.gpc) * N;
       const int c_lo = jr * N, c_hi = c_lo + N;
       const float2 me = sp[r];
-      if (r < w.gpc * N) {
+      int degcnt = 0;
+      if (K > 1 && r < w.gpc * N) {
 #pragma unroll 1
-        for (int t = t0; t < t1; ++t) {
-          const int qc = 4 * t + qtr;
+        for (int t = 0; t < 8; ++t) {
+          const int qc = 2 * t + half;
           if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
             const uint32_t bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
             degcnt += __popc(bits);
@@ -1026,10 +1159,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
           }
         }
       }
-    };
-    auto publish_p = [&](int pbuf) {
-      sdeg[(pbuf * 4 + qtr) * L::ROWS + r] = degcnt;
-      degcnt = 0;
+      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;
       publish(p_ready);
     };
     // Drain the TMEM accumulators into this CTA group's partial buffer (zeroed by the host, L2-resident, every
@@ -1046,8 +1176,8 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #pragma unroll 1
         for (int k = 0; k < K; ++k) {
 #pragma unroll 1
-          for (int cb = 0; cb < FH / 4; cb += 8) {
-            const int col = qtr * (FH / 4) + cb;
+          for (int cb = 0; cb < FH / 2; cb += 8) {
+            const int col = half * (FH / 2) + cb;
             uint32_t v[8];
             tc5::tmem_ld8u(tm_lane + L::TM_ACC + k * FH + col, v);
             tc5::tmem_ld_wait();
@@ -1063,89 +1193,52 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       tc5::fence_before_sync();
     };
 
-    // One leading iteration (it == -1) prepares the first tile; afterwards iteration `it` serves tile `tile`
-    // (write-backs) and prepares `next`.
-    int next = t_begin, it = -1, vbase = 0, n_items = 0;
-    if (next < t_end) load_pos(next);
-    while (true) {
-      const bool live = it >= 0;
-      const bool has_next = next < t_end;
-      if (!live && !has_next) break;
-      const int pbuf = (it + 1) & 1;
-      int xt_slot = 0;
-      bool p_done = false;
-      if (has_next) {
-        if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;
-        worker_bar();
-        if (next + 1 < t_end) load_pos(next + 1);
-        if (wt == 0 && !w.no_prefetch) {   // L2 prefetch runs two tiles ahead
-          if (!live) prefetch_tile(next);
-          if (next + 1 < t_end) prefetch_tile(next + 1);
-        }
+    int vbase_next = 0, n_items = 0, itn = 0;
+    if (t_begin < t_end) load_pos(t_begin);
+    for (int next = t_begin; next < t_end; ++next, ++itn) {
+      const int pbuf = itn & 1;
+      if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;
+      group_b_bar();
+      if (next + 1 < t_end) load_pos(next + 1);
+      if (wt == 0 && !w.no_prefetch) {   // L2 prefetch runs one tile ahead of this group (two ahead of the issuer)
+        if (itn == 0) prefetch_tile(next);
+        if (next + 1 < t_end) prefetch_tile(next + 1);
       }
-      // ---- write-backs of the K-1 hops; the next tile's x columns and P are prepared in the gaps ----------
-      const int nwb = live ? K - 1 : 0;
-      bool v0_loaded = false;
-#pragma unroll 1
-      for (int k = 0; k < nwb; ++k) {
-        // next tile's V_0 pieces: requested two write-backs ahead of their use so that the (long) memory latency
-        // overlaps the remaining taps of the live tile
-        if (has_next && !v0_loaded && k + 2 >= nwb) { load_v0(next); v0_loaded = true; }
-        tc5::mbar_wait_suspend(hop_done, par_hd); par_hd ^= 1;
-        tc5::fence_after_sync();
-        unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (qtr * (L::CPT / 8)) * L::PW + r * 16;
-        const uint32_t taddr = tm_lane + TM_HOP + qtr * L::CPT;
-        uint32_t v[L::CPT];
-        if constexpr (L::CPT == 16) tc5::tmem_ld16(taddr, v); else tc5::tmem_ld8u(taddr, v);
-        tc5::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < L::CPT / 8; ++c) {
-          float f[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf_live : __uint_as_float(v[c * 8 + i]);
-          store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
-        }
-        publish(v_ready);
-        if (has_next) {
-          if (K > 1 && k < 2) {
-            build_p_part(next, pbuf, 2 * k, 2 * k + 2);
-            if (k == 1 || nwb == 1) {
-              if (nwb == 1) build_p_part(next, pbuf, 2, 4);
-              publish_p(pbuf); p_done = true;
-            }
-          }
-          if (xt_slot < 1) load_xt_half(next, xt_slot++);   // half of X^T early; the rest once V_0's registers are free
-        }
-      }
-      if (has_next) {
-        if (!p_done) { if (K > 1) build_p_part(next, pbuf, 0, 4); publish_p(pbuf); }
-        if (norm) {   // every thread's partial degrees of `next` are visible after this barrier
-          worker_bar();
-          wbf_next = dtab[128 + row_degree4(sdeg, pbuf, r)];
-        }
-        // V_0 of the next tile goes into the ring buffer after the live tile's last one (free: its last reader
-        // was tap K-3 of the live tile, which completed before the hop result of tap K-2 was signalled)
-        if (!v0_loaded) load_v0(next);
-        store_v0(Vb + ((vbase + (live ? K : 0)) % 3) * L::VBUF, pbuf);
-        publish(v0_ready);
-        while (xt_slot < 2) load_xt_half(next, xt_slot++);   // latency hides behind the last tap's MMAs / the drain
-      }
-      if (live) {
-        tc5::mbar_wait_suspend(item_done, par_id); par_id ^= 1;   // every dH product of the live tile has completed
+      load_v0(next);                     // latency overlaps the P build
+      build_p(next, pbuf);
+      GFC_KSTAMP(430);
+      if (norm) group_b_bar();           // every thread's partial degrees of `next` are visible
+      // V_0 of `next` goes into the ring buffer after the live tile's last one: free once the live tile's product
+      // K-3 has completed (K < 3: its last reader belongs to a tile whose item_done this group already saw)
+      if (itn >= 1 && K >= 3) { tc5::mbar_wait_suspend(v0_free, par_vf); par_vf ^= 1; }
+      GFC_KSTAMP(410);
+      store_v0(Vb + (vbase_next % 3) * L::VBUF, pbuf);
+      publish(v0_ready);
+      GFC_KSTAMP(420);
+      load_xt(next, 0);                  // latency overlaps the wait for the live tile
+      if (itn >= 1) {
+        GFC_KSTAMP(500);
+        tc5::mbar_wait_suspend(item_done, par_id); par_id ^= 1;   // every product of the live tile has completed
+        GFC_KSTAMP(501);
         ++n_items;
-        if (!has_next || (n_items % w.flush_every) == 0) flush();
-        vbase = (vbase + K) % 3;
+        if ((n_items % w.flush_every) == 0) flush();
+        GFC_KSTAMP(502);
       }
-      if (has_next) store_xt(pbuf);
-      if (!has_next) break;
-      next += 1;
-      ++it;
-      wbf_live = wbf_next;
+      store_xt(pbuf, 0);
+      load_xt(next, 1);
+      store_xt(pbuf, 1);
+      GFC_KSTAMP(510);
+      vbase_next = (vbase_next + K) % 3;
     }
+    if (itn >= 1) {
+      tc5::mbar_wait_suspend(item_done, par_id); par_id ^= 1;
+      flush();
+    }
+#undef GFC_KSTAMP
     if (w.dbp) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) atomicAdd(dbs + 4 * (lane % PPR) + i, dbacc[i]);
-      worker_bar();
+      group_b_bar();
       if (wt < FH) w.dbp[(size_t)part * F + fh * FH + wt] = dbs[wt];
     }
   }
@@ -1287,11 +1380,12 @@ static int launch_wide_t(const WideArgs& a0, cudaStream_t st) {
   WideMaps maps;
   memset(&maps, 0, sizeof(maps));
   if (MODE != 1) {   // y viewed as [B*N rows, COUT cols]; a box = one warp's [32 rows x 16 cols] (shorter in a partial row quadrant)
+    // at most ONE row quadrant of a tile is partial (the last non-empty one, rows_full % 32 rows): m[0] = full box,
+    // m[1] = the partial box.  (A batch smaller than a tile — B = 1 inference — has rows_full < 64: partial quadrant 0 / 1.)
     const int rows_full = a.gpc * a.N;
-    for (int i = 0; i < 3; ++i) {
-      int h = i == 0 ? 32 : rows_full - 32 * (i + 1);
-      h = h > 32 ? 32 : h;
-      if (h <= 0) continue;
+    for (int i = 0; i < 2; ++i) {
+      const int h = i == 0 ? 32 : rows_full % 32;
+      if (h <= 0 || (i == 0 && rows_full < 32)) continue;
       int rc = encode_tmap_2d(&maps.m[i], a.out, COUT, (uint64_t)a.B * a.N, 16, (uint32_t)h, CU_TENSOR_MAP_SWIZZLE_64B);
       if (rc) return rc;
     }
@@ -1334,7 +1428,7 @@ template <int G, int F, int FH, int NP>
 static int launch_wide_dh_t(const WideDhArgs& a0, cudaStream_t st) {
   using L = DhLayout<G, F, FH, NP>;
   WideDhArgs a = a0;
-  auto kern = tc5_wide_dh_kernel<G, F, FH, NP>;
+  auto kern = (a.N & 3) == 0 ? tc5_wide_dh_kernel<G, F, FH, NP, true> : tc5_wide_dh_kernel<G, F, FH, NP, false>;
   GFC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
   kern<<<a.nparts * L::NFH, kWideThreads, L::BYTES, st>>>(a);
   GFC_LAUNCH_CHECK("tc5_wide_dh_kernel");

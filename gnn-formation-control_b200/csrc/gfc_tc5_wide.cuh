@@ -51,6 +51,7 @@ struct WideDhArgs {
   int no_prefetch;
   int act;
   float slope;
+  long long* dbg;          // dH: optional clock stamps of CTA 0 (issuer at [0..), worker warp 2 at [4096..)), else null
 };
 extern int g_wide_flush_every;
 extern int g_wide_no_prefetch;

@@ -216,11 +216,11 @@ class GraphFilterBatch(nn.Module):
         self._src = _Src(_SRC_POS, pos=pos.detach().to(torch.float32).contiguous(),
                          radius=float(radius), mode=C.GSO_MODES[mode])
 
-    def addSparseGSO(self, csr_or_pos, radius=None, mode="binary_le"):
+    def addSparseGSO(self, csr_or_pos, radius=None, mode="binary_le", max_degree=None):
         """CSR path (kernel (d)) for large sparse swarms; accepts a ``SparseGSO``
-        or positions + radius."""
+        or positions + radius (``max_degree``: sync-free capacity build, see ``build_csr``)."""
         assert self.E == 1
-        csr = csr_or_pos if isinstance(csr_or_pos, SparseGSO) else build_csr(csr_or_pos, radius, mode)
+        csr = csr_or_pos if isinstance(csr_or_pos, SparseGSO) else build_csr(csr_or_pos, radius, mode, max_degree)
         self.N = csr.N
         self.S = csr
         self._src = _Src(_SRC_CSR, csr=csr)

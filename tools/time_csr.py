@@ -18,7 +18,9 @@ def t(fn, n=10):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / n
 csr = gnnfc.build_csr(pos, 2.0, "binary_le")
-print("build_csr %.3f ms" % t(lambda: gnnfc.build_csr(pos, 2.0, "binary_le")))
+print("build_csr (exact sizing, one host read) %.3f ms" % t(lambda: gnnfc.build_csr(pos, 2.0, "binary_le")))
+print("build_csr (max_degree=64, sync-free)    %.3f ms" % t(lambda: gnnfc.build_csr(pos, 2.0, "binary_le", max_degree=64)))
+print("build_csr (three-pass pair walk)        %.3f ms" % t(lambda: gnnfc.gso.build_csr_three_pass(pos, 2.0, "binary_le")))
 m.addSparseGSO(csr)
 print("forward   %.3f ms" % t(lambda: m(x)))
 y = m(x)
