@@ -152,6 +152,8 @@ class HotPath:
         self.layers = w.get("layers", 1)
         nbf = C.lib.gfc_filter_workspace_bytes(B, N, G, F, K, 1, 0)
         self.wsf = torch.empty(max(nbf, 256), dtype=torch.uint8, device=dev); self.nbf = nbf
+        # operand statistics handed from each batch's forward call to its backward call (gfc_use_stats)
+        self.stats = [torch.zeros(4, device=dev) for _ in range(ring)]
         if self.train:
             self.dY = [torch.randn(B, N, F, device=dev, generator=gen) for _ in range(ring)]
             self.dX = [torch.empty(B, G, N, device=dev) for _ in range(ring)]
@@ -164,6 +166,7 @@ class HotPath:
             self.y2 = [torch.empty(B, N, F, device=dev) for _ in range(ring)]
             self.xt = torch.empty(B, F, N, device=dev)
         self.launches_per_step = 0
+        self.use_stats = True
 
     def stream(self):
         return self.C.ct.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -171,6 +174,8 @@ class HotPath:
     def fwd(self, i, st):
         C, w = self.C, self.w
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        if self.train and self.use_stats:
+            C.lib.gfc_use_stats(C.ptr(self.stats[i]))
         C.check(C.lib.gfc_filter_fwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                          C.ptr(self.b), C.ptr(self.y[i]), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
                                          C.PREC_FP32_3XTF32, C.ptr(self.wsf), self.nbf, st), "gfc_filter_fwd_pos")
@@ -188,6 +193,8 @@ class HotPath:
     def bwd(self, i, st):
         C, w = self.C, self.w
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        if self.use_stats:
+            C.lib.gfc_use_stats(C.ptr(self.stats[i]))
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                          C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.dH),
                                          C.ptr(self.db), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
@@ -202,6 +209,8 @@ class HotPath:
     def bwd_dp(self, i, st):
         C, w, px = self.C, self.w, self.px
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
+        if self.use_stats:
+            C.lib.gfc_use_stats(C.ptr(self.stats[i]))
         C.check(C.lib.gfc_filter_bwd_pos_dp(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                             C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.grads),
                                             B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32,
@@ -648,6 +657,8 @@ def per_kernel_times(torch, hp, reps):
     out = {}
 
     def bwd_partial(i, st, want_dx, want_dh):
+        if hp.use_stats:
+            C.lib.gfc_use_stats(C.ptr(hp.stats[i]))   # filled by the forward call of this ring slot during the step
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(hp.x[i]), C.ptr(hp.pos[i]), RADIUS, hp.mode, C.ptr(hp.h),
                                          C.ptr(hp.y[i]), C.ptr(hp.dY[i]), C.ptr(hp.dX[i]) if want_dx else None,
                                          C.ptr(hp.dH) if want_dh else None, C.ptr(hp.db) if want_dh else None,

@@ -38,6 +38,7 @@ SIGNATURES = {
     "gfc_set_option": (_i, [_i, _i]),
     "gfc_set_debug_clock_buffer": (_i, [_p, _sz]),
     "gfc_device_info": (_i, [ct.POINTER(_i)] * 4),
+    "gfc_use_stats": (_i, [_p]),
     "gfc_gso_build": (_i, [_p, _i, _i, _d, _i, _p, _p, _p]),
     "gfc_filter_workspace_bytes": (_sz, [_i] * 7),
     "gfc_filter_path": (_i, [_i] * 7),

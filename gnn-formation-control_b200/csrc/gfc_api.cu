@@ -13,6 +13,7 @@ namespace gfc {
 static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static int g_skip_grad_reduce = 0;
+static thread_local float* g_next_stats = nullptr;   // gfc_use_stats: applies to the next filter call of this thread
 static long long* g_dbg_clk = nullptr;  // device buffer [>= grid][16], see gfc_set_debug_clock_buffer
 
 void set_error(const char* fmt, ...) {
@@ -235,8 +236,11 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                            float* y, int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
                            void* ws, size_t ws_bytes, cudaStream_t st) {
   launch_counter() = 0;
+  float* stats = g_next_stats;   // one-shot
+  g_next_stats = nullptr;
   int rc = check_common(fn, B, N, G, F, K, E, act, prec, slope);
   if (rc) return rc;
+  if (stats) GFC_CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(float), st));   // stats[3] stays 0: "not filled"
   if (B == 0) return GFC_OK;
   GFC_REQUIRE(x && h && y, GFC_ERR_BAD_ARG, "%s: NULL tensor pointer", fn);
   GFC_REQUIRE(gs.kind == GSRC_DENSE ? gs.S != nullptr : gs.pos != nullptr, GFC_ERR_BAD_ARG, "%s: NULL graph source", fn);
@@ -268,7 +272,10 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       fill_wide_graph(wa.g, gs, a, norm);
       wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
       wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
-      return launch_wide(wa, G, F, 0, np, st);
+      wa.amax = stats;   // stats[0] = max |x|: a by-product of the per-tile operand scales
+      rc = launch_wide(wa, G, F, 0, np, st);
+      if (rc || !stats) return rc;
+      return launch_stats_mark(stats, st);   // stats[3] = 1: filled
     }
     if (!p.h_smem) {
       float4* hp = reinterpret_cast<float4*>(static_cast<char*>(ws) + p.ws_hpack);
@@ -313,6 +320,8 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                            int B, int N, int G, int F, int K, int E, int act, float slope, int prec,
                            void* ws, size_t ws_bytes, cudaStream_t st, const DpCtx* dp = nullptr) {
   launch_counter() = 0;
+  const float* stats = g_next_stats;   // one-shot
+  g_next_stats = nullptr;
   int rc = check_common(fn, B, N, G, F, K, E, act, prec, slope);
   if (rc) return rc;
   const size_t nH = (size_t)F * E * K * G;
@@ -384,7 +393,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         float* dbp = reinterpret_cast<float*>(wb + wws.dbp);
         // launch-wide operand scales: max |x| always, max |dY| (x max(1, slope)) when the dX kernel did not run
         const float vbound = (act == GFC_ACT_LEAKY_RELU && slope > 1.f) ? slope : 1.f;
-        rc = launch_wide_absmax(x, (size_t)B * G * N, dX ? nullptr : dY, (size_t)B * N * F, vbound, amax, st);
+        rc = launch_wide_absmax(x, (size_t)B * G * N, dX ? nullptr : dY, (size_t)B * N * F, vbound, amax, stats, st);
         if (rc) return rc;
         WideDhArgs da{};
         fill_wide_graph(da.g, gs, a, norm);
@@ -591,6 +600,7 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   const char* fn = "gfc_filter_fwd_pos_nm";
   cudaStream_t st = (cudaStream_t)stream;
   launch_counter() = 0;
+  g_next_stats = nullptr;   // the node-major entry has no backward partner: a pending gfc_use_stats is dropped
   int rc = check_common(fn, B, N, G, F, K, 1, act, precision, slope);
   if (rc) return rc;
   if (B == 0) return GFC_OK;
@@ -790,5 +800,10 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
     rc = launch_hops_csr(Zw, rowptr_t, colidx_t, vals_t, nnz_stride, B, N, G, K, 1, nullptr, dX, st);
     if (rc) return rc;
   }
+  return GFC_OK;
+}
+
+extern "C" int gfc_use_stats(float* stats) {
+  g_next_stats = stats;
   return GFC_OK;
 }

@@ -175,6 +175,7 @@ __device__ __forceinline__ float ldg_cg(const float* p) {
   return v;
 }
 __device__ __forceinline__ void group_b_bar() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+__device__ __forceinline__ void group_a_bar() { asm volatile("bar.sync 3, 256;" ::: "memory"); }
 
 struct WideMaps { CUtensorMap m[2]; };   // y store boxes: 32 rows / the one partial row quadrant of a tile (rows_full % 32 rows)
 
@@ -288,7 +289,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         const int ob = it & 1;
         GFC_WSTAMP(1);
-        tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
+        if (K > 1) { tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1; }
         GFC_WSTAMP(3);
         const uint32_t d_out = tmem + L::TM_OUT + ob * COUT;
 #pragma unroll 1
@@ -350,7 +351,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       int filled = 0;
       const unsigned char* hsrc = w.hpack + kPackHeader;
       auto prefetch_tile = [&](int tile) {
-        if (tile >= t_end || w.no_prefetch) return;
+        if (tile >= t_end || w.no_prefetch || MODE == 1) return;   // dX: no gain measured, and 1.7x the DRAM reads
         const int b0 = tile * w.gpc;
         const int gcount = min(w.gpc, w.B - b0);
         const uint32_t bytes = (uint32_t)gcount * (uint32_t)N * CIN * 4u;   // multiple of 16 (CIN % 32 == 0)
@@ -376,15 +377,68 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     }
     __syncwarp();
   } else if (warp < 2 + kGroupWarps) {
-    // =========================== group A: write-backs of the hop chain ==========================
+    // =========================== group A: write-backs of the hop chain + the next tile's P =========
     // The only per-phase work between two MMAs of a chain: hop result (TMEM, exact fp32, already in the units of
-    // W_{k+1}) -> fp16 planes of W_{k+1}[slab s].  These warps do nothing else, so the chain never queues behind the
-    // next tile's preparation or the previous tile's epilogue (group B).
+    // W_{k+1}) -> fp16 planes of W_{k+1}[slab s].  A write-back takes ~600 of the ~2000 cycles between two hops of a
+    // slab; in the gaps these warps build the block-diagonal hop matrix P of the NEXT tile (positions -> shared
+    // memory -> radius rule -> TMEM), a few 8-row chunks after each write-back.  That work used to sit in group B,
+    // which was the critical path of the dX kernel (~21k cycles per tile against ~16k of MMA issue, round-2 timeline).
     const int gw = warp - 2;                 // 0..7
+    const int wa = tid - 64;                 // 0..255
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int half = gw >> 2;                // which half of a slab's columns
+    const int half = gw >> 2;                // which half of a slab's columns / every second chunk of P
     const int r = q * 32 + lane;             // tile row owned by this thread (= its TMEM lane)
+    const int jr = r / N;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
+    // an edge of P carries the per-hop headroom 2^-c (exact in fp16), so the hop result needs no rescaling
+    const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;
+    float2 mypos = make_float2(0.f, 0.f);
+    int degcnt = 0;
+    auto load_pos = [&](int tile) {
+      const int b0 = tile * w.gpc;
+      const int gcount = min(w.gpc, w.B - b0);
+      if (wa < 128)   // position of tile row wa
+        mypos = (wa < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wa)
+                                  : make_float2(0.f, 0.f);
+    };
+    // P[r][c] = 2^-c iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
+    // TMEM lane r; the two warps of a quadrant take every second chunk of 8 source rows: slots t0..t1-1 of its 8.
+    auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
+      const float2* sp = sp_all + pbuf * L::ROWS;
+      const int gcount = min(w.gpc, w.B - tile * w.gpc);
+      const int rows_used = gcount * N;
+      const int c_lo = jr * N, c_hi = c_lo + N;
+      const float2 me = sp[r];
+      const bool row_ok = r < w.gpc * N;
+#pragma unroll 1
+      for (int t = t0; t < t1; ++t) {
+        const int qc = 2 * t + half;   // chunk of 8 source rows = 4 TMEM columns
+        uint32_t bits = 0;
+        if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
+          bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+        degcnt += __popc(bits);
+        tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0, pval), p_word(bits, 2, pval),
+                      p_word(bits, 4, pval), p_word(bits, 6, pval));
+      }
+    };
+    auto publish_p = [&](int pbuf) {
+      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;   // read by group B after p_ready, by this group after its next barrier
+      degcnt = 0;
+      tc5::tmem_st_wait();
+      tc5::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc5::mbar_arrive(p_ready);
+    };
+    const int nslots = 2 * (K - 1);
+    const int cps = nslots ? (8 + nslots - 1) / nslots : 8;   // chunks per write-back slot
+    if (K > 1 && t_begin < t_end) {   // P of the first tile
+      load_pos(t_begin);
+      if (wa < 128) sp_all[wa] = mypos;
+      group_a_bar();
+      if (t_begin + 1 < t_end) load_pos(t_begin + 1);
+      build_p_part(t_begin, 0, 0, 8);
+      publish_p(0);
+    }
     uint32_t par_hd = 0;
     int nstamp = 0;
     const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && tid == 64;
@@ -396,6 +450,15 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     int it = 0;
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       float wbf = 1.f;
+      const bool has_next = K > 1 && tile + 1 < t_end;
+      const int pbn = (it + 1) & 1;
+      if (K > 1) {
+        // positions of the next tile -> shared memory (its buffer last served the tile before the running one); the
+        // barrier also orders this group's degree counts of the running tile before the reads below
+        if (has_next && wa < 128) sp_all[pbn * L::ROWS + wa] = mypos;
+        group_a_bar();
+        if (tile + 2 < t_end) load_pos(tile + 2);
+      }
 #pragma unroll 1
       for (int slot = 0; slot < 2 * (K - 1); ++slot) {
         const int s = slot & 1, k1 = (slot >> 1) + 1;   // this write-back produces W_{k1}[s]
@@ -403,7 +466,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         tc5::mbar_wait_suspend(&hop_done[s], (par_hd >> s) & 1); par_hd ^= 1u << s;
         tc5::fence_after_sync();
         GFC_KSTAMP(200 + slot);
-        // sym-norm: What_{k+1} = D^-1 (A What_k); the degrees of this tile were published by group B with its P
+        // sym-norm: What_{k+1} = D^-1 (A What_k); the degrees of this tile were counted by this group with its P
         if (norm && slot == 0) wbf = dtab[128 + row_degree(sdeg, it & 1, r)];
         const uint32_t taddr = tm_lane + L::TM_HOP + s * L::CS + half * L::CPT;
         unsigned char* base = Wb + (2 * s + ((it * K + k1) & 1)) * L::SLAB + (half * (L::CPT / 8)) * L::PW + r * 16;
@@ -422,6 +485,14 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         __syncwarp();
         if (lane == 0) tc5::mbar_arrive(&w_ready[s]);
         GFC_KSTAMP(300 + slot);
+        // gap work: chunks of the next tile's P (its TMEM buffer was last read by the hops of the previous tile,
+        // which completed before the hop this write-back followed)
+        if (has_next && slot * cps < 8) {
+          const int t1 = min(8, (slot + 1) * cps);
+          build_p_part(tile + 1, pbn, slot * cps, t1);
+          if (t1 == 8) publish_p(pbn);
+          GFC_KSTAMP(400 + slot);
+        }
       }
     }
 #undef GFC_KSTAMP
@@ -435,8 +506,6 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     const int jr = r / N, nr = r - jr * N;   // (graph, node) of the row
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     const float inv_th = __ldg(reinterpret_cast<const float*>(w.hpack));   // 1 / (tap scale)
-    // an edge of P carries the per-hop headroom 2^-c (exact in fp16), so the hop result needs no rescaling
-    const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;
     const float act_neg = w.act == GFC_ACT_NONE ? 1.f : (w.act == GFC_ACT_RELU ? 0.f : w.slope);
     const bool act_min = act_neg > 1.f;
     // y store: this warp's 32 rows x 16 columns at a time through a private 2 KB staging slot (64-byte rows, 64B
@@ -446,8 +515,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     const int hq = min(32, max(0, w.gpc * N - 32 * q));
     const CUtensorMap* my_map = hq == 32 ? &maps.m[0] : &maps.m[1];
     float xin[L::CPT];
-    float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_ofl = 0, par_w0 = 0;
+    uint32_t par_ofl = 0, par_w0 = 0, par_pb = 0;
     float inv_prev = 1.f, inv_next = 1.f, scale_next = 1.f, rowf_next = 1.f;
     int nstamp = 0;
     const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && wt == 0;
@@ -457,13 +525,6 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
 #define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
 #endif
 
-    auto load_pos = [&](int tile) {
-      const int b0 = tile * w.gpc;
-      const int gcount = min(w.gpc, w.B - b0);
-      if (wt < 128)   // rows 0..127 in thread order wt: position of row wt
-        mypos = (wt < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wt)
-                                  : make_float2(0.f, 0.f);
-    };
     // MODE 1 / 2: dY / y are row-major [rows x CIN]: a warp instruction reads whole 16-byte pieces of RPI consecutive
     // rows (full lines) instead of 32 scattered ones; the halves of an fp16 chunk meet by a lane-pair shuffle at
     // store time.  Warp gw owns rows 16 gw .. 16 gw + 15, lane = (row offset, piece).
@@ -552,34 +613,6 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         }
       }
     };
-    // P[r][c] = 2^-c iff rows r and c belong to the same graph and are adjacent (symmetric rule).  This thread owns
-    // TMEM lane r; the two warps of a quadrant take every second chunk of 8 source rows (balanced for any N).
-    auto build_p = [&](int tile, int pbuf) {
-      const float2* sp = sp_all + pbuf * L::ROWS;
-      const int gcount = min(w.gpc, w.B - tile * w.gpc);
-      const int rows_used = gcount * N;
-      const int c_lo = jr * N, c_hi = c_lo + N;
-      const float2 me = sp[r];
-      const bool row_ok = r < w.gpc * N;
-      int degcnt = 0;
-      if (K > 1) {
-#pragma unroll 1
-        for (int t = 0; t < 8; ++t) {
-          const int qc = 2 * t + half;   // chunk of 8 source rows = 4 TMEM columns
-          uint32_t bits = 0;
-          if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
-            bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
-          degcnt += __popc(bits);
-          tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0, pval), p_word(bits, 2, pval),
-                        p_word(bits, 4, pval), p_word(bits, 6, pval));
-        }
-      }
-      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;   // read after the tile-maximum barrier (B) / the first hop (A)
-      tc5::tmem_st_wait();
-      tc5::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc5::mbar_arrive(p_ready);
-    };
     // upper bound of the tile's |operand| -> power-of-two scale.  One flat pass over the (L2-prefetched) tile; the
     // values are read again, slab by slab, when W_0 is formed — holding the whole tile in registers across the
     // epilogue would cost 64 registers per thread.
@@ -660,17 +693,12 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     // the buffers, then run the epilogue of tile j-1.  Every piece of per-tile code exists at exactly one place.
     int next = t_begin, itn = 0;
     int epi_tile = -1, epi_ob = 0;
-    if (next < t_end) load_pos(next);
     while (true) {
       const bool has_next = next < t_end;
       if (!has_next && epi_tile < 0) break;
       if (has_next) {
         const int pbuf = itn & 1;
-        if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;   // positions of `next` (loaded one tile ahead)
-        group_b_bar();
-        if (next + 1 < t_end) load_pos(next + 1);
-        build_p(next, pbuf);
-        GFC_KSTAMP(430);
+        group_b_bar();   // the per-warp maxima of the previous tile have been read by every warp
         // ---- tile maximum -> power-of-two scale ------------------------------------------------------------------
         const float m = tile_max(next);
         const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like uints
@@ -682,7 +710,11 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         if (w.amax && wt == 0) atomicMax(reinterpret_cast<unsigned int*>(w.amax) + (MODE == 1 ? 1 : 0), mt);
         scale_next = tc5::pow2_scale(mt, kWideTop, &inv_next);
         rowf_next = 1.f;
-        if (norm) {   // the degrees of `next` were stored by build_p before the barrier above
+        if (norm && K > 1) {   // the degrees of `next` are published by group A together with its P
+          tc5::mbar_wait_suspend(p_ready, par_pb); par_pb ^= 1;
+          tc5::fence_after_sync();
+        }
+        if (norm) {
           const int d = row_degree(sdeg, pbuf, r);
           rowf_next = dtab[d];
           inv_next *= dtab[256 + d];   // epilogue factor of this thread's row: 1/s x d^1/2
@@ -845,9 +877,11 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #endif
       for (int tile = t_begin; tile < t_end; ++tile, ++it) {
         GFC_WSTAMP(1);
-        tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1;
+        if (K > 1) { tc5::mbar_wait(p_ready, par_pr); par_pr ^= 1; }
         GFC_WSTAMP(3);
-        const bool fresh = (it % w.flush_every) == 0;   // group B drained the accumulators before x_ready
+        // group B drained the accumulators before x_ready.  The drain schedule is shifted per CTA group: with all CTAs
+        // draining after the same tile the ~19 MB of reductions hit the L2 at once (~6k cycles per drain)
+        const bool fresh = it == 0 || ((it + part) % w.flush_every) == 0;
         const uint32_t pa = p_addr + (it & 1) * L::P_BYTES;
         // dH product of tap kk:  acc(kk)[g][f] += X^T[g][rows] * V_kk[rows][f]   (hi hi + hi lo + lo hi, A from tensor memory)
         auto issue_dh = [&](int kk) {
@@ -903,13 +937,60 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     }
     __syncwarp();
   } else if (warp >= 2 && warp < 2 + kGroupWarps) {
-    // =========================== group A: write-backs of the hop chain ==========================
+    // =========================== group A: write-backs of the hop chain + the next tile's P =========
     const int gw = warp - 2;                   // 0..7
+    const int wa = tid - 64;                   // 0..255
     const int q = warp & 3;                    // TMEM lane quadrant
-    const int half = gw >> 2;                  // column half of the feature slice
+    const int half = gw >> 2;                  // column half of the feature slice / every second chunk of P
     const int r = q * 32 + lane;               // tile row = TMEM lane
+    const int jr = r / N;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     constexpr int CPA = FH / 2;                // columns per thread
+    const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;   // an edge of P = 2^-c: the hop result is V_{k+1} 2^(-c (k+1)) directly
+    float2 mypos = make_float2(0.f, 0.f);
+    int degcnt = 0;
+    auto load_pos = [&](int tile) {
+      const int b0 = tile * w.gpc;
+      const int rows_used = min(w.gpc, w.B - b0) * N;
+      if (wa < 128)
+        mypos = (wa < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wa) : make_float2(0.f, 0.f);
+    };
+    // P[r][c] (smem, K-major A operand): this thread owns row r and every second chunk of 8 source rows; slots t0..t1-1.
+    // Built in the gaps between the write-backs (a write-back takes ~1k of the ~2k cycles between two hops).
+    auto build_p_part = [&](int tile, int pbuf, int t0, int t1) {
+      const float2* sp = sp_all + pbuf * L::ROWS;
+      unsigned char* pb = Pb + pbuf * L::P_BYTES;
+      const int rows_used = min(w.gpc, w.B - tile * w.gpc) * N;
+      const int c_lo = jr * N, c_hi = c_lo + N;
+      const float2 me = sp[r];
+      if (r < w.gpc * N) {
+#pragma unroll 1
+        for (int t = t0; t < t1; ++t) {
+          const int qc = 2 * t + half;
+          if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
+            const uint32_t bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+            degcnt += __popc(bits);
+            *reinterpret_cast<uint4*>(pb + qc * L::PW + r * 16) =
+                make_uint4(p_word(bits, 0, pval), p_word(bits, 2, pval), p_word(bits, 4, pval), p_word(bits, 6, pval));
+          }
+        }
+      }
+    };
+    auto publish_p = [&](int pbuf) {
+      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;
+      degcnt = 0;
+      publish(p_ready);
+    };
+    const int nslots = K - 1;
+    const int cps = nslots ? (8 + nslots - 1) / nslots : 8;   // chunks per write-back slot
+    if (K > 1 && t_begin < t_end) {   // P of the first tile
+      load_pos(t_begin);
+      if (wa < 128) sp_all[wa] = mypos;
+      group_a_bar();
+      if (t_begin + 1 < t_end) load_pos(t_begin + 1);
+      build_p_part(t_begin, 0, 0, 8);
+      publish_p(0);
+    }
     uint32_t par_hd = 0;
     int vbase = 0, it = 0;
     int nstamp = 0;
@@ -921,13 +1002,22 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #endif
     for (int tile = t_begin; tile < t_end; ++tile, ++it) {
       float wbf = 1.f;
+      const bool has_next = K > 1 && tile + 1 < t_end;
+      const int pbn = (it + 1) & 1;
+      if (K > 1) {
+        // positions of the next tile -> shared memory; the barrier also orders this group's degree counts of the
+        // running tile before the reads below
+        if (has_next && wa < 128) sp_all[pbn * L::ROWS + wa] = mypos;
+        group_a_bar();
+        if (tile + 2 < t_end) load_pos(tile + 2);
+      }
 #pragma unroll 1
       for (int k = 0; k + 1 < K; ++k) {
         GFC_KSTAMP(100 + k);
         tc5::mbar_wait_suspend(hop_done, par_hd); par_hd ^= 1;
         tc5::fence_after_sync();
         GFC_KSTAMP(200 + k);
-        // sym-norm: Vhat_{k+1} = D^-1 (A Vhat_k); this tile's degrees were published by group B with its P
+        // sym-norm: Vhat_{k+1} = D^-1 (A Vhat_k); this tile's degrees were counted by this group with its P
         if (norm && k == 0) wbf = dtab[128 + row_degree(sdeg, it & 1, r)];
         unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (half * (CPA / 8)) * L::PW + r * 16;
         const uint32_t taddr = tm_lane + TM_HOP + half * CPA;
@@ -943,6 +1033,13 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         }
         publish(v_ready);
         GFC_KSTAMP(300 + k);
+        // gap work: chunks of the next tile's P (its buffer was last read by the hops of the previous tile)
+        if (has_next && k * cps < 8) {
+          const int t1 = min(8, (k + 1) * cps);
+          build_p_part(tile + 1, pbn, k * cps, t1);
+          if (t1 == 8) publish_p(pbn);
+          GFC_KSTAMP(400 + k);
+        }
       }
       vbase = (vbase + K) % 3;
     }
@@ -954,7 +1051,6 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     const int q = warp & 3;
     const int half = gw >> 2;                  // column half (drain) / row half (X^T) / chunk parity (P)
     const int r = q * 32 + lane;               // tile row (P) and feature lane g (X^T, drain)
-    const int jr = r / N;
     const bool g_ok = r < G;
     const uint32_t tm_lane = tmem + ((uint32_t)(q * 32) << 16);
     // V_0 loads: 16-byte pieces per row, rows per warp instruction, pieces per thread; warp gw owns rows 16 gw .. 16 gw + 15
@@ -963,14 +1059,12 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     float xt[32];                              // x[g][32 rows] of the next tile: one row quarter at a time (register budget: 96)
     float xin[4 * NPC];                        // V_0 pieces of the next tile (dead before xt is loaded)
     float dbacc[4] = {0.f, 0.f, 0.f, 0.f};     // column sums of V_0 (columns 4*(lane % PPR) .. +3)
-    float2 mypos = make_float2(0.f, 0.f);
-    uint32_t par_id = 0, par_vf = 0;
+    uint32_t par_id = 0, par_vf = 0, par_pb = 0;
     // launch-wide operand scales (powers of two) from the batch maxima
     float inv_sx, inv_sv;
     const int xtop = norm ? kWideTop - 4 : kWideTop;   // Xhat = D^1/2 X grows by < 2^3.5 (N <= 128)
     const float s_x = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax)), xtop, &inv_sx);
     const float s_v = tc5::pow2_scale(__float_as_uint(ldg_cg(w.amax + 1)), kWideTop, &inv_sv);
-    const uint32_t pval = (uint32_t)(15 - w.cshift) << 10;   // an edge of P = 2^-c: the hop result is V_{k+1} 2^(-c (k+1)) directly
     int nstamp = 0;
     const bool dbg = w.dbg != nullptr && blockIdx.x == 0 && wt == 0;
 #ifdef GFC_WIDE_TIMELINE
@@ -979,12 +1073,6 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #define GFC_KSTAMP(tag) do { (void)dbg; (void)nstamp; } while (0)
 #endif
 
-    auto load_pos = [&](int tile) {
-      const int b0 = tile * w.gpc;
-      const int rows_used = min(w.gpc, w.B - b0) * N;
-      if (wt < 128)
-        mypos = (wt < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wt) : make_float2(0.f, 0.f);
-    };
     auto prefetch_tile = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
@@ -1139,29 +1227,6 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         store_chunk_f16<NP>(vbuf + (pi >> 1) * L::PW + row * 16, L::PLANE, v);
       }
     };
-    // P[r][c] (smem, K-major A operand): this thread owns row r and every second chunk of 8 source rows
-    auto build_p = [&](int tile, int pbuf) {
-      const float2* sp = sp_all + pbuf * L::ROWS;
-      unsigned char* pb = Pb + pbuf * L::P_BYTES;
-      const int rows_used = min(w.gpc, w.B - tile * w.gpc) * N;
-      const int c_lo = jr * N, c_hi = c_lo + N;
-      const float2 me = sp[r];
-      int degcnt = 0;
-      if (K > 1 && r < w.gpc * N) {
-#pragma unroll 1
-        for (int t = 0; t < 8; ++t) {
-          const int qc = 2 * t + half;
-          if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
-            const uint32_t bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
-            degcnt += __popc(bits);
-            *reinterpret_cast<uint4*>(pb + qc * L::PW + r * 16) =
-                make_uint4(p_word(bits, 0, pval), p_word(bits, 2, pval), p_word(bits, 4, pval), p_word(bits, 6, pval));
-          }
-        }
-      }
-      sdeg[(pbuf * 2 + half) * L::ROWS + r] = degcnt;
-      publish(p_ready);
-    };
     // Drain the TMEM accumulators into this CTA group's partial buffer (zeroed by the host, L2-resident, every
     // address owned by exactly one thread of one CTA) with fire-and-forget reductions: no read latency, and the
     // per-address order is this thread's program order, so the result is deterministic.  The tensor core's fp32
@@ -1194,20 +1259,17 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     };
 
     int vbase_next = 0, n_items = 0, itn = 0;
-    if (t_begin < t_end) load_pos(t_begin);
     for (int next = t_begin; next < t_end; ++next, ++itn) {
       const int pbuf = itn & 1;
-      if (wt < 128) sp_all[pbuf * L::ROWS + wt] = mypos;
-      group_b_bar();
-      if (next + 1 < t_end) load_pos(next + 1);
-      if (wt == 0 && !w.no_prefetch) {   // L2 prefetch runs one tile ahead of this group (two ahead of the issuer)
+      if (wt == 0 && w.no_prefetch == 2) {   // L2 prefetch one tile ahead of this group: OFF by default (0.27 ms slower at cfg3, round-2 A/B)
         if (itn == 0) prefetch_tile(next);
         if (next + 1 < t_end) prefetch_tile(next + 1);
       }
-      load_v0(next);                     // latency overlaps the P build
-      build_p(next, pbuf);
-      GFC_KSTAMP(430);
-      if (norm) group_b_bar();           // every thread's partial degrees of `next` are visible
+      load_v0(next);
+      if (norm && K > 1) {               // the degrees of `next` are published by group A together with its P
+        tc5::mbar_wait_suspend(p_ready, par_pb); par_pb ^= 1;
+        tc5::fence_after_sync();
+      }
       // V_0 of `next` goes into the ring buffer after the live tile's last one: free once the live tile's product
       // K-3 has completed (K < 3: its last reader belongs to a tile whose item_done this group already saw)
       if (itn >= 1 && K >= 3) { tc5::mbar_wait_suspend(v0_free, par_vf); par_vf ^= 1; }
@@ -1221,7 +1283,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         tc5::mbar_wait_suspend(item_done, par_id); par_id ^= 1;   // every product of the live tile has completed
         GFC_KSTAMP(501);
         ++n_items;
-        if ((n_items % w.flush_every) == 0) flush();
+        if (((n_items + part) % w.flush_every) == 0) flush();
         GFC_KSTAMP(502);
       }
       store_xt(pbuf, 0);
@@ -1299,13 +1361,18 @@ int launch_wide_pack(const float* h, int G, int F, int K, int mode, int cshift, 
 // batch maxima for the launch-wide operand scales of the dH kernel
 __global__ void __launch_bounds__(512)
 wide_absmax_kernel(const float* __restrict__ a, size_t n_a, const float* __restrict__ b, size_t n_b, float bscale,
-                   float* __restrict__ amax) {
+                   float* __restrict__ amax, const float* __restrict__ stats) {
   const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
   const size_t i0 = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  // operand statistics of the forward call (gfc_use_stats): stats[3] != 0 says stats[0] = max |a| is valid, so the pass
+  // over a (2.1 GB at cfg3) is skipped — decided on the device, no host round trip
+  const bool have_a = stats != nullptr && ldg_cg(stats + 3) != 0.f;
+  if (have_a && a && blockIdx.x == 0 && threadIdx.x == 0)
+    atomicMax(reinterpret_cast<unsigned int*>(amax), __float_as_uint(ldg_cg(stats)));
   for (int which = 0; which < 2; ++which) {
     const float* p = which ? b : a;
     const size_t n = which ? n_b : n_a;
-    if (!p) continue;
+    if (!p || (which == 0 && have_a)) continue;
     float m = 0.f;
     const bool vec = (reinterpret_cast<uintptr_t>(p) & 15) == 0;
     for (size_t i = i0; i < n; i += stride) {
@@ -1322,7 +1389,15 @@ wide_absmax_kernel(const float* __restrict__ a, size_t n_a, const float* __restr
   }
 }
 
-int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax, cudaStream_t st) {
+__global__ void wide_stats_mark_kernel(float* stats) { stats[3] = 1.f; }
+int launch_stats_mark(float* stats, cudaStream_t st) {
+  wide_stats_mark_kernel<<<1, 1, 0, st>>>(stats);
+  GFC_LAUNCH_CHECK("wide_stats_mark_kernel");
+  return GFC_OK;
+}
+
+int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax,
+                       const float* stats, cudaStream_t st) {
   if (!a && !b) return GFC_OK;
   DeviceInfo di;
   int rc = get_device_info(&di);
@@ -1330,7 +1405,7 @@ int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, f
   const size_t n = n_a > n_b ? n_a : n_b;
   size_t want = (n + 2047) / 2048;
   int grid = (int)(want < (size_t)di.sm_count * 4 ? (want ? want : 1) : (size_t)di.sm_count * 4);
-  wide_absmax_kernel<<<grid, 512, 0, st>>>(a, n_a, b, n_b, bscale, amax);
+  wide_absmax_kernel<<<grid, 512, 0, st>>>(a, n_a, b, n_b, bscale, amax, stats);
   GFC_LAUNCH_CHECK("wide_absmax_kernel");
   return GFC_OK;
 }

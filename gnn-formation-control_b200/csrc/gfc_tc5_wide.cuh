@@ -71,6 +71,9 @@ int launch_wide_pack(const float* h, int G, int F, int K, int mode, int cshift, 
                      cudaStream_t st);
 int launch_wide(const WideArgs& a, int G, int F, int mode, int planes, cudaStream_t st);
 // amax[0] = max |a| (n_a floats), amax[1] = max |b| * bscale (n_b floats); either pointer may be null (slot left as is)
-int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax, cudaStream_t st);
+// stats (optional, device float[4] of the forward call, gfc_use_stats): when stats[3] != 0 the pass over `a` is skipped
+int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax,
+                       const float* stats, cudaStream_t st);
+int launch_stats_mark(float* stats, cudaStream_t st);   // stats[3] = 1
 
 }  // namespace gfc

@@ -81,6 +81,7 @@ class _LSIGF(torch.autograd.Function):
             elif rc != C.GFC_ERR_UNSUPPORTED:
                 C.check(rc, "gfc_filter_fwd_pos_nm")
         done = x32 is not None
+        stats = None
         if not done:
             x32 = x.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
@@ -96,6 +97,10 @@ class _LSIGF(torch.autograd.Function):
             elif src.kind == _SRC_POS:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 0)
                 ws = _workspace(nb, dev)
+                if x.requires_grad or weight.requires_grad:
+                    # operand statistics for the backward call of this batch (max |x|: saves its extra pass over x)
+                    stats = torch.empty(4, dtype=torch.float32, device=dev)
+                    C.lib.gfc_use_stats(C.ptr(stats))
                 C.check(C.lib.gfc_filter_fwd_pos(C.ptr(x32), C.ptr(src.pos), src.radius, src.mode,
                                                  C.ptr(w32), C.ptr(b32), C.ptr(y), B, N, G, F_, K,
                                                  act, slope, prec, C.ptr(ws), nb, st), "gfc_filter_fwd_pos")
@@ -109,6 +114,7 @@ class _LSIGF(torch.autograd.Function):
                                                  C.ptr(ws), nb, st), "gfc_filter_csr_fwd")
         ctx.src, ctx.act, ctx.slope, ctx.prec = src, act, slope, prec
         ctx.has_bias = bias is not None
+        ctx.stats = stats
         ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype if bias is not None else None)
         ctx.save_for_backward(x32, w32, y if act != C.ACT_NONE else None)
         return y
@@ -137,6 +143,8 @@ class _LSIGF(torch.autograd.Function):
             elif src.kind == _SRC_POS:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 1)
                 ws = _workspace(nb, dev)
+                if ctx.stats is not None:
+                    C.lib.gfc_use_stats(C.ptr(ctx.stats))
                 C.check(C.lib.gfc_filter_bwd_pos(C.ptr(x32), C.ptr(src.pos), src.radius, src.mode,
                                                  C.ptr(w32), C.ptr(yout), C.ptr(dY), C.ptr(dX), C.ptr(dH),
                                                  C.ptr(db), B, N, G, F_, K, act, slope, prec,

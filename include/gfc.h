@@ -131,6 +131,16 @@ int gfc_filter_bwd_pos(const float* x, const float* pos, double radius, int mode
                        int act, float slope, int precision,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* Operand statistics handed from the forward call of a batch to its backward call.
+ * `stats` = device float[4], caller-owned.  gfc_use_stats(stats) applies to the NEXT gfc_filter_fwd* / gfc_filter_bwd*
+ * call of the calling thread only (thread-local, consumed by that call; NULL cancels):
+ *   - a forward call zeroes stats and, on the tcgen05 path, leaves stats[0] = max |x| (a by-product of its per-tile
+ *     operand scales) and stats[3] = 1 ("filled");
+ *   - a backward call of the same batch reads stats[3] ON THE DEVICE: if filled, its launch-wide operand scale of x
+ *     comes from stats[0] and the extra pass over x (2.1 GB at 65536 x 128 x 64) is skipped; if not (the forward took
+ *     another kernel family) it computes the maximum itself.  Results are identical either way.                       */
+int gfc_use_stats(float* stats);
+
 /* ---- (d) CSR variant for large sparse swarms ------------------------------ *
  * gfc_csr_count : deg[b,n] = in-degree under the radius rule (int32 [B,N]).
  * gfc_csr_fill  : given rowptr [B, N+1] (exclusive scan of deg per graph, int32,
