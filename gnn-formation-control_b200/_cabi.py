@@ -16,6 +16,8 @@ GFC_OK, GFC_ERR_BAD_ARG, GFC_ERR_UNSUPPORTED, GFC_ERR_WORKSPACE, GFC_ERR_CUDA, G
 GSO_BINARY_LE, GSO_SYM_NORM_LT, GSO_BINARY_LT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
 PREC_FP32_3XTF32, PREC_TF32, PREC_F16 = 0, 1, 2
+PREC_FLAG_BINARY_GSO = 0x100
+PATH_TILE, PATH_WORKSPACE, PATH_TCGEN05_WIDE = 1, 2, 3
 OPT_SKIP_GRAD_REDUCE = 1
 OPT_DISABLE_TCGEN05 = 2
 OPT_WIDE_FLUSH_EVERY = 3
@@ -36,6 +38,7 @@ SIGNATURES = {
     "gfc_last_error": (ct.c_char_p, []),
     "gfc_last_launch_count": (_i, []),
     "gfc_set_option": (_i, [_i, _i]),
+    "gfc_last_path": (_i, []),
     "gfc_set_debug_clock_buffer": (_i, [_p, _sz]),
     "gfc_device_info": (_i, [ct.POINTER(_i)] * 4),
     "gfc_use_stats": (_i, [_p]),
@@ -115,3 +118,7 @@ def tile_plan(B, N, G, F, K, backward=False, from_positions=False):
 
 def last_launch_count():
     return lib.gfc_last_launch_count()
+
+
+def last_path():
+    return lib.gfc_last_path()

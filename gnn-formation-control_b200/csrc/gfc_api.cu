@@ -67,7 +67,9 @@ struct GsoSrc {
   const float* pos;
   double radius;
   int mode;
+  int binary = 0;   // dense: the caller vouches that every entry is 0 or 1 (GFC_PREC_FLAG_BINARY_GSO)
 };
+static thread_local int g_last_path = 0;   // gfc_last_path(): kernel family of this thread's last filter call
 
 // ---- path B workspace plan -----------------------------------------------------
 struct GenericPlan {
@@ -201,8 +203,12 @@ static int rows_bwd(const GenericPlan& g, char* wsb, float* Zw, const float* h, 
 // positions (binary or sym-norm rule), G, F in {64,128}, N <= 128, fp16 headroom c (K-1) <= 21
 static bool use_wide(const GsoSrc& gs, int N, int G, int F, int K, int mode, int prec) {
   (void)prec;
-  return !g_disable_tcgen05 && gs.kind == GSRC_POS && wide_supported(N, G, F, K, mode);
+  if (g_disable_tcgen05) return false;
+  if (gs.kind == GSRC_POS) return wide_supported(N, G, F, K, mode);
+  // dense 0/1 GSO (the reference's own addGSO call): P is exact in fp16; a node may have N neighbours (self loop)
+  return gs.binary && wide_supported(N + 1, G, F, K, mode) && N <= 128;
 }
+static int wide_cshift_of(const GsoSrc& gs, int N, bool norm) { return wide_cshift(gs.kind == GSRC_POS ? N : N + 1, norm); }
 static int wide_planes(int prec) { return prec == GFC_PREC_FP32_3XTF32 ? 2 : 1; }
 // workspace behind the tile plan's own: [packed taps | amax (256 B) | dH partials | db partials | dY o act'(y)]
 struct WideWs {
@@ -226,9 +232,10 @@ static WideWs wide_ws(int B, int N, int G, int F, int K, int backward) {
   return o;
 }
 static size_t wide_ws_extra(int B, int N, int G, int F, int K, int backward) { return wide_ws(B, N, G, F, K, backward).bytes; }
-static void fill_wide_graph(WideGraph& g, const GsoSrc& gs, const TileArgs& a, bool norm) {
+static void fill_wide_graph(WideGraph& g, const GsoSrc& gs, const TileArgs& a, bool norm, int N, int transpose) {
   g = WideGraph{};
   g.pos = gs.pos; g.thr = a.thr; g.thr_lo = a.thr_lo; g.thr_hi = a.thr_hi; g.norm = norm ? 1 : 0;
+  if (gs.kind == GSRC_DENSE) { g.pos = nullptr; g.S = gs.S; g.s_bstride = (long long)N * N; g.s_transpose = transpose; g.norm = 0; }
 }
 
 // ---- forward ------------------------------------------------------------------
@@ -251,7 +258,9 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     if (rc) return rc;
   }
   TilePlan p;
+  g_last_path = 2;
   if (E == 1 && plan_tile(B, N, G, F, K, 0, gs.kind, &p)) {
+    g_last_path = 1;
     rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(B, N, G, F, K, 0));
     if (rc) return rc;
     TileArgs a{};
@@ -265,11 +274,12 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       // tcgen05 / TMEM path: fp16 hi/lo planes, hops and taps on the tensor cores
       const WideWs wws = wide_ws(B, N, G, F, K, 0);
       unsigned char* hp = reinterpret_cast<unsigned char*>(ws) + p.ws_bytes + wws.pack;
-      const int cs = wide_cshift(N, norm), np = wide_planes(prec);
+      const int cs = wide_cshift_of(gs, N, norm), np = wide_planes(prec);
       rc = launch_wide_pack(h, G, F, K, 0, cs, np, hp, st);
       if (rc) return rc;
       WideArgs wa{};
-      fill_wide_graph(wa.g, gs, a, norm);
+      fill_wide_graph(wa.g, gs, a, norm, N, 1);   // forward hop: z_{k+1} = z_k S  ->  P = S^T
+      g_last_path = 3;
       wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
       wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
       wa.amax = stats;   // stats[0] = max |x|: a by-product of the per-tile operand scales
@@ -344,7 +354,9 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     if (rc) return rc;
   }
   TilePlan p;
+  g_last_path = 2;
   if (E == 1 && plan_tile(B, N, G, F, K, 1, gs.kind, &p)) {
+    g_last_path = 1;
     rc = need_ws(fn, ws, ws_bytes, p.ws_bytes + wide_ws_extra(B, N, G, F, K, 1));
     if (rc) return rc;
     char* wsb = static_cast<char*>(ws);
@@ -364,7 +376,8 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       // tensor memory across all tiles of a CTA)
       const WideWs wws = wide_ws(B, N, G, F, K, 1);
       char* wb = wsb + p.ws_bytes;
-      const int cs = wide_cshift(N, norm), np = wide_planes(prec);
+      const int cs = wide_cshift_of(gs, N, norm), np = wide_planes(prec);
+      g_last_path = 3;
       float* amax = reinterpret_cast<float*>(wb + wws.amax);
       float* wide_dpre = nullptr;
       const bool want_grads = dH != nullptr;   // db alone is served below by the tile kernels
@@ -375,7 +388,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         rc = launch_wide_pack(h, G, F, K, 1, cs, np, hp, st);
         if (rc) return rc;
         WideArgs wa{};
-        fill_wide_graph(wa.g, gs, a, norm);
+        fill_wide_graph(wa.g, gs, a, norm, N, 0);   // backward hop: V_{k+1} = S V_k  ->  P = S
         wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
         wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
         if (want_grads) {
@@ -396,7 +409,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         rc = launch_wide_absmax(x, (size_t)B * G * N, dX ? nullptr : dY, (size_t)B * N * F, vbound, amax, stats, st);
         if (rc) return rc;
         WideDhArgs da{};
-        fill_wide_graph(da.g, gs, a, norm);
+        fill_wide_graph(da.g, gs, a, norm, N, 0);
         da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre; da.amax = amax;
         da.dHp = dhp; da.dbp = db ? dbp : nullptr;
         da.B = B; da.N = N; da.K = K; da.cshift = cs; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
@@ -580,6 +593,8 @@ extern "C" int gfc_filter_fwd(const float* x, const float* S, const float* h, co
                               int B, int N, int G, int F, int K, int E, int act, float slope, int precision,
                               void* workspace, size_t workspace_bytes, void* stream) {
   GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
+  gs.binary = (precision & GFC_PREC_FLAG_BINARY_GSO) != 0 && E == 1;
+  precision &= ~GFC_PREC_FLAG_BINARY_GSO;
   return filter_fwd_impl("gfc_filter_fwd", gs, x, h, bias, y, B, N, G, F, K, E, act, slope, precision,
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -624,7 +639,8 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   rc = launch_wide_pack(h, G, F, K, 0, cs, np, hp, st);
   if (rc) return rc;
   WideArgs wa{};
-  fill_wide_graph(wa.g, gs, a, norm);
+  fill_wide_graph(wa.g, gs, a, norm, N, 1);
+  g_last_path = 3;
   wa.in = x_nm; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
   wa.act = act; wa.slope = slope;
   return launch_wide(wa, G, F, 2, np, st);
@@ -635,6 +651,8 @@ extern "C" int gfc_filter_bwd(const float* x, const float* S, const float* h, co
                               int B, int N, int G, int F, int K, int E, int act, float slope, int precision,
                               void* workspace, size_t workspace_bytes, void* stream) {
   GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
+  gs.binary = (precision & GFC_PREC_FLAG_BINARY_GSO) != 0 && E == 1;
+  precision &= ~GFC_PREC_FLAG_BINARY_GSO;
   return filter_bwd_impl("gfc_filter_bwd", gs, x, h, y_out, dY, dX, dH, db, B, N, G, F, K, E, act, slope,
                          precision, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -669,6 +687,8 @@ extern "C" int gfc_filter_bwd_dp(const float* x, const float* S, const float* h,
                                  void* const* peer_buf, void* const* peer_sig, int rank, int world, float scale,
                                  void* stream) {
   GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
+  gs.binary = (precision & GFC_PREC_FLAG_BINARY_GSO) != 0 && E == 1;
+  precision &= ~GFC_PREC_FLAG_BINARY_GSO;
   DpCtx dp{peer_buf, peer_sig, rank, world, scale};
   if (!grads) { set_error("gfc_filter_bwd_dp: NULL gradient bucket"); return GFC_ERR_BAD_ARG; }
   return filter_bwd_impl("gfc_filter_bwd_dp", gs, x, h, y_out, dY, dX, grads, grads + (size_t)F * E * K * G,
@@ -807,3 +827,5 @@ extern "C" int gfc_use_stats(float* stats) {
   g_next_stats = stats;
   return GFC_OK;
 }
+
+extern "C" int gfc_last_path(void) { return g_last_path; }

@@ -136,6 +136,27 @@ __device__ __forceinline__ uint32_t adjacency8(const float2* __restrict__ sp, fl
   }
   return bits;
 }
+// Dense 0/1 GSO (the reference's own addGSO call, graphML.py:2449-2456; the caller vouches for the entries with
+// GFC_PREC_FLAG_BINARY_GSO): the 8 entries of P row `pr` = (graph jr, node nr) for the tile rows c0..c0+7, as a bit mask.
+// Forward (transpose): P[(j,n)][(j,m)] = S_j[m][n] (z_{k+1} = z_k S, graphML.py:2350); backward: S_j[n][m].  A nonzero
+// diagonal is kept (the rule-built GSOs have none, a user's S may).
+__device__ __forceinline__ uint32_t dense8(const float* __restrict__ Sg, int N, int transpose, int nr, int pr, int c0,
+                                           int c_lo, int c_hi, int rows_used) {
+  const int lo = max(c_lo, c0) - c0, hi = min(min(c_hi, rows_used), c0 + 8) - c0;
+  if (hi <= lo || pr >= rows_used) return 0u;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = c0 + i - c_lo;
+    const bool ok = i >= lo && i < hi;
+    const float* p = transpose ? Sg + (size_t)(ok ? m : 0) * N + nr : Sg + (size_t)nr * N + (ok ? m : 0);
+    v[i] = ok ? __ldg(p) : 0.f;
+  }
+  uint32_t bits = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bits |= (v[i] != 0.f ? 1u : 0u) << i;
+  return bits;
+}
 // two adjacency bits -> one word of two fp16 (pv = the fp16 pattern of an edge, 2^-c), bit `lo` at the lower address
 __device__ __forceinline__ uint32_t p_word(uint32_t bits, int lo, uint32_t pv) {
   return ((bits >> lo) & 1u) * pv + ((bits >> (lo + 1)) & 1u) * (pv << 16);
@@ -397,7 +418,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
     auto load_pos = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int gcount = min(w.gpc, w.B - b0);
-      if (wa < 128)   // position of tile row wa
+      if (wa < 128 && w.g.pos)   // position of tile row wa (dense GSO: none)
         mypos = (wa < gcount * N) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wa)
                                   : make_float2(0.f, 0.f);
     };
@@ -415,7 +436,9 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         const int qc = 2 * t + half;   // chunk of 8 source rows = 4 TMEM columns
         uint32_t bits = 0;
         if (row_ok && qc * 8 < c_hi && qc * 8 + 8 > c_lo)
-          bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+          bits = w.g.S ? dense8(w.g.S + (size_t)(tile * w.gpc + jr) * w.g.s_bstride, N, w.g.s_transpose, r - c_lo, r,
+                                qc * 8, c_lo, c_hi, rows_used)
+                       : adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
         degcnt += __popc(bits);
         tc5::tmem_st4(tm_lane + L::TM_P + pbuf * 64 + qc * 4, p_word(bits, 0, pval), p_word(bits, 2, pval),
                       p_word(bits, 4, pval), p_word(bits, 6, pval));
@@ -952,7 +975,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     auto load_pos = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
-      if (wa < 128)
+      if (wa < 128 && w.g.pos)
         mypos = (wa < rows_used) ? __ldg(reinterpret_cast<const float2*>(w.g.pos) + (size_t)b0 * N + wa) : make_float2(0.f, 0.f);
     };
     // P[r][c] (smem, K-major A operand): this thread owns row r and every second chunk of 8 source rows; slots t0..t1-1.
@@ -968,7 +991,10 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         for (int t = t0; t < t1; ++t) {
           const int qc = 2 * t + half;
           if (qc * 8 < c_hi && qc * 8 + 8 > c_lo) {
-            const uint32_t bits = adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
+            const uint32_t bits =
+                w.g.S ? dense8(w.g.S + (size_t)(tile * w.gpc + jr) * w.g.s_bstride, N, w.g.s_transpose, r - c_lo, r, qc * 8,
+                               c_lo, c_hi, rows_used)
+                      : adjacency8(sp, me, r, qc * 8, c_lo, c_hi, rows_used, w.g.thr, w.g.thr_lo, w.g.thr_hi);
             degcnt += __popc(bits);
             *reinterpret_cast<uint4*>(pb + qc * L::PW + r * 16) =
                 make_uint4(p_word(bits, 0, pval), p_word(bits, 2, pval), p_word(bits, 4, pval), p_word(bits, 6, pval));

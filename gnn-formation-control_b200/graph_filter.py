@@ -45,11 +45,23 @@ def _require_cuda(t, what):
                            "fallback (the reference's CPU path lives in oracle/ for tests only)" % what)
 
 
+def _is_binary(S32, E, G, F):
+    """True when a dense GSO holds only 0/1 entries (what Scene.readADjMatrix produces, scene.py:140-154) AND the layer
+    has a shape the tcgen05 wide kernels serve — only then is the check (one reduction + one host read per addGSO)
+    worth making.  During CUDA-graph capture the host read is impossible: the generic dense kernels are used."""
+    if E != 1 or G not in (64, 128) or F not in (64, 128) or S32.shape[-1] > 127:
+        return False
+    if torch.cuda.is_current_stream_capturing():
+        return False
+    return bool(((S32 == 0) | (S32 == 1)).all().item())
+
+
 class _Src:
     """graph source handed to the autograd function (not a tensor argument)."""
 
-    def __init__(self, kind, S=None, pos=None, radius=0.0, mode=0, csr=None):
+    def __init__(self, kind, S=None, pos=None, radius=0.0, mode=0, csr=None, binary=False):
         self.kind, self.S, self.pos, self.radius, self.mode, self.csr = kind, S, pos, radius, mode, csr
+        self.binary = binary     # dense S with 0/1 entries only: eligible for the tcgen05 wide kernels
 
 
 class _LSIGF(torch.autograd.Function):
@@ -91,8 +103,9 @@ class _LSIGF(torch.autograd.Function):
             elif src.kind == _SRC_DENSE:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 0)
                 ws = _workspace(nb, dev)
+                pflag = prec | (C.PREC_FLAG_BINARY_GSO if src.binary else 0)
                 C.check(C.lib.gfc_filter_fwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(b32), C.ptr(y),
-                                             B, N, G, F_, K, E, act, slope, prec, C.ptr(ws), nb, st),
+                                             B, N, G, F_, K, E, act, slope, pflag, C.ptr(ws), nb, st),
                         "gfc_filter_fwd")
             elif src.kind == _SRC_POS:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 0)
@@ -137,9 +150,10 @@ class _LSIGF(torch.autograd.Function):
             if src.kind == _SRC_DENSE:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 1)
                 ws = _workspace(nb, dev)
+                pflag = prec | (C.PREC_FLAG_BINARY_GSO if src.binary else 0)
                 C.check(C.lib.gfc_filter_bwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(yout), C.ptr(dY),
                                              C.ptr(dX), C.ptr(dH), C.ptr(db), B, N, G, F_, K, E,
-                                             act, slope, prec, C.ptr(ws), nb, st), "gfc_filter_bwd")
+                                             act, slope, pflag, C.ptr(ws), nb, st), "gfc_filter_bwd")
             elif src.kind == _SRC_POS:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 1)
                 ws = _workspace(nb, dev)
@@ -238,7 +252,8 @@ class GraphFilterBatch(nn.Module):
             S = self.S
             assert S is not None, "call addGSO / addPositions before forward"
             _require_cuda(S, "the GSO")
-            self._src = _Src(_SRC_DENSE, S=S.detach().to(device=device, dtype=torch.float32).contiguous())
+            S32 = S.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._src = _Src(_SRC_DENSE, S=S32, binary=_is_binary(S32, self.E, self.G, self.F))
         return self._src
 
     # ---- forward ----------------------------------------------------------------
@@ -305,7 +320,8 @@ class GraphFilter(GraphFilterBatch):
             assert S is not None, "call addGSO before forward"
             _require_cuda(S, "the GSO")
             S32 = S.detach().to(device=device, dtype=torch.float32)
-            self._src = _Src(_SRC_DENSE, S=S32.unsqueeze(0).expand(B, -1, -1, -1).contiguous())
+            self._src = _Src(_SRC_DENSE, S=S32.unsqueeze(0).expand(B, -1, -1, -1).contiguous(),
+                             binary=_is_binary(S32, self.E, self.G, self.F))
             self._srcB = B
         return self._src
 

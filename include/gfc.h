@@ -65,8 +65,14 @@ enum { GFC_ACT_NONE = 0, GFC_ACT_RELU = 1, GFC_ACT_LEAKY_RELU = 2 };
 enum {
   GFC_PREC_FP32_3XTF32 = 0, /* tensor cores, hi/lo split, fp32-equivalent (<=1e-5) */
   GFC_PREC_TF32 = 1,        /* single pass tf32, looser bound (~1e-3), opt-in       */
-  GFC_PREC_F16 = 2          /* single fp16 plane on the tcgen05 wide path (1 MMA per product, stated bound 2e-3);
+  GFC_PREC_F16 = 2,         /* single fp16 plane on the tcgen05 wide path (1 MMA per product, stated bound 2e-3);
                                shapes outside that path run as GFC_PREC_TF32         */
+  /* flag, OR-ed into `precision` of the DENSE entry points (gfc_filter_fwd / _bwd / _bwd_dp): the caller vouches that
+     every entry of S is exactly 0 or 1 (the adjacency Scene.readADjMatrix produces, scene.py:140-154, possibly
+     asymmetric, possibly with a diagonal).  The hop matrix is then exact in fp16 and wide shapes (G, F in {64,128},
+     N <= 127) run on the tcgen05 kernels like the position-built GSOs; without the flag a dense S runs on the
+     mma.sync tile kernels (any weights).  gnnfc.GraphFilterBatch.addGSO checks the entries itself.                  */
+  GFC_PREC_FLAG_BINARY_GSO = 0x100
 };
 
 int gfc_version(void);
@@ -251,6 +257,9 @@ enum {
   GFC_OPT_DP_TIMEOUT_MS = 7 /* bound of the peer-exchange poll in milliseconds (default 10000), see gfc_dp_status */
 };
 int gfc_set_option(int key, int value);
+/* kernel family of the calling thread's last gfc_filter_fwd* / gfc_filter_bwd* call: 1 = fused tile kernels (mma.sync, or the
+ * tcgen05 kernels of the 8-node shape), 2 = workspace pipeline, 3 = warp-specialised tcgen05 / TMEM wide kernels */
+int gfc_last_path(void);
 /* Debug aid: a device buffer of >= 1184*16 int64 in which the fused tile kernels stamp the SM
  * clock at their phase boundaries (first tile of every CTA).  NULL switches it off (default). */
 int gfc_set_debug_clock_buffer(void* device_i64, size_t bytes);
