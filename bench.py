@@ -166,7 +166,8 @@ class HotPath:
             self.y2 = [torch.empty(B, N, F, device=dev) for _ in range(ring)]
             self.xt = torch.empty(B, F, N, device=dev)
         self.launches_per_step = 0
-        self.use_stats = True
+        # the hand-over only exists on the tcgen05 wide path (elsewhere it would just add a 16-byte memset to the step)
+        self.use_stats = G in (64, 128) and F in (64, 128) and N <= 128
 
     def stream(self):
         return self.C.ct.c_void_p(self.torch.cuda.current_stream().cuda_stream)
@@ -228,13 +229,14 @@ class HotPath:
 
 
 def tensor_flops_per_graph(w):
-    """bf16 tensor-core flops ISSUED per graph by the tcgen05 wide path (fp32 accuracy costs 6 bf16 MMAs per tap
-    product and 3 per hop product; 128-row tiles of floor(128/N) graphs, block-diagonal hop matrix) and the
-    algorithmic fp32-equivalent flops of SURVEY §8d, forward (+ backward when training)."""
+    """fp16 tensor-core flops ISSUED per graph by the tcgen05 wide path (fp32 accuracy costs 3 fp16 MMAs per tap
+    product — hi hi + hi lo + lo hi — and 2 per hop product, the 0/1 hop matrix being exact in one plane; 128-row tiles of
+    floor(128/N) graphs, block-diagonal hop matrix) and the algorithmic fp32-equivalent flops of SURVEY §8d, forward
+    (+ backward when training)."""
     N, G, F, K = w["N"], w["G"], w["F"], w["K"]
     gpc = max(1, 128 // N)
-    taps = 2 * 128 * (K * G) * F * 6 / gpc                  # per graph share of a tile
-    hops = (K - 1) * 2 * 128 * (((gpc * N + 15) // 16) * 16) * G * 3 / gpc
+    taps = 2 * 128 * (K * G) * F * 3 / gpc                  # per graph share of a tile
+    hops = (K - 1) * 2 * 128 * (((gpc * N + 15) // 16) * 16) * G * 2 / gpc
     issued_fwd = taps + hops
     useful_fwd = 2 * (K - 1) * G * N * N + 2 * N * K * G * F
     layers = w.get("layers", 1)

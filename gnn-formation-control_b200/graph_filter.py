@@ -110,7 +110,7 @@ class _LSIGF(torch.autograd.Function):
             elif src.kind == _SRC_POS:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 0)
                 ws = _workspace(nb, dev)
-                if x.requires_grad or weight.requires_grad:
+                if (x.requires_grad or weight.requires_grad) and G in (64, 128) and F_ in (64, 128) and N <= 128:
                     # operand statistics for the backward call of this batch (max |x|: saves its extra pass over x)
                     stats = torch.empty(4, dtype=torch.float32, device=dev)
                     C.lib.gfc_use_stats(C.ptr(stats))
