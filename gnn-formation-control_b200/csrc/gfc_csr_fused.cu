@@ -15,6 +15,24 @@ namespace gfc {
 
 constexpr int kFusedThreads = 1024, kFusedItems = 8;   // float4 gather results per thread
 
+// One row of a hop: sum over the row's list entries i in [beg, end) of w_i * state[m_i] (a float4 = four channels).
+// (Tried in round 2: reading the list four entries at a time, one group ahead of their use.  The index loads hit L1 and
+// the kernels sit at the 64-register limit of a 1024-thread CTA: forward 269 -> 304 us, backward 453 -> 502 us. Dropped.)
+__device__ __forceinline__ float4 gather_row(const float* __restrict__ src, int stride, const int32_t* __restrict__ ci,
+                                             const float* __restrict__ vv, int beg, int end) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = beg; i < end; ++i) {
+    const int m = ci[i];
+    const float w = vv ? vv[i] : 1.f;
+    const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * stride);
+    acc.x = fmaf(w, z.x, acc.x);
+    acc.y = fmaf(w, z.y, acc.y);
+    acc.z = fmaf(w, z.z, acc.z);
+    acc.w = fmaf(w, z.w, acc.w);
+  }
+  return acc;
+}
+
 template <int NT>   // F / 8 output column tiles, compile time: the accumulators must stay in registers
 __global__ void __launch_bounds__(kFusedThreads, 1)
 csr_fwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ rowptr,
@@ -105,17 +123,7 @@ csr_fwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ ro
       nxt[it] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (idx < total) {
         const int n = idx / G4, g4 = idx - n * G4;
-        const int beg = rp[n], end = rp[n + 1];
-        const float* src = zs + g4 * 4;
-        for (int i = beg; i < end; ++i) {
-          const int m = ci[i];
-          const float w = vv ? vv[i] : 1.f;
-          const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * GS);
-          nxt[it].x = fmaf(w, z.x, nxt[it].x);
-          nxt[it].y = fmaf(w, z.y, nxt[it].y);
-          nxt[it].z = fmaf(w, z.z, nxt[it].z);
-          nxt[it].w = fmaf(w, z.w, nxt[it].w);
-        }
+        nxt[it] = gather_row(zs + g4 * 4, GS, ci, vv, rp[n], rp[n + 1]);
       }
     }
     __syncthreads();                                      // every tap MMA and every gather of z_k is done
@@ -154,6 +162,7 @@ csr_bwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ ro
   float4* Hs = reinterpret_cast<float4*>(smem + (size_t)MT * 16 * FS);     // taps, B fragments of H_k^T (for_bwd)
   float* dHs = smem + (size_t)MT * 16 * FS + (size_t)KG * F * 2;           // [F][KG] running dH of this graph
   float* dbs = dHs + (size_t)F * KG;                                       // [F]
+  float* dbw = dbs + F;                                                    // [32 warps][F] per-warp column sums of V_0
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int F4 = F >> 2, total = N * F4;
@@ -185,13 +194,21 @@ csr_bwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ ro
       *reinterpret_cast<float4*>(vs + (size_t)n * FS + f4 * 4) = v;
       cs.x += v.x; cs.y += v.y; cs.z += v.z; cs.w += v.w;
     }
-    if (want_db && (kFusedThreads % F4) == 0) {
-      const int f4 = tid % F4;
-      atomicAdd(dbs + f4 * 4, cs.x); atomicAdd(dbs + f4 * 4 + 1, cs.y);
-      atomicAdd(dbs + f4 * 4 + 2, cs.z); atomicAdd(dbs + f4 * 4 + 3, cs.w);
+    if (want_db) {
+      // deterministic: lanes with the same column group (lane % F4) meet by shuffles, the 32 per-warp sums in fixed order
+      for (int o = F4; o < 32; o <<= 1) {
+        cs.x += __shfl_xor_sync(0xffffffffu, cs.x, o); cs.y += __shfl_xor_sync(0xffffffffu, cs.y, o);
+        cs.z += __shfl_xor_sync(0xffffffffu, cs.z, o); cs.w += __shfl_xor_sync(0xffffffffu, cs.w, o);
+      }
+      if (lane < F4) *reinterpret_cast<float4*>(dbw + (size_t)warp * F + lane * 4) = cs;
     }
   }
   __syncthreads();
+  if (want_db && tid < F) {
+    float sum = 0.f;
+    for (int wq = 0; wq < kFusedThreads / 32; ++wq) sum += dbw[(size_t)wq * F + tid];
+    dbs[tid] = sum;
+  }
 
   for (int k = 0; k < K; ++k) {
     // ---- (a) dX[rows of this warp][g] (+)= sum_f V_k[row][f] h[f][k*G + g] ----------------------------------
@@ -254,8 +271,11 @@ csr_bwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ ro
       }
       float* row0 = dHs + (size_t)(mtf * 16 + g) * KG + k * G + nt * 8 + 2 * t;
       float* row1 = row0 + (size_t)8 * KG;
-      atomicAdd(row0, acc[0]); atomicAdd(row0 + 1, acc[1]);
-      atomicAdd(row1, acc[2]); atomicAdd(row1 + 1, acc[3]);
+      // the node groups add their partial tiles one after the other: fixed order, bitwise reproducible gradients
+      for (int gi = 0; gi < ngrp; ++gi) {
+        if (grp == gi) { row0[0] += acc[0]; row0[1] += acc[1]; row1[0] += acc[2]; row1[1] += acc[3]; }
+        __syncthreads();
+      }
     }
     if (k == K - 1) break;
     // ---- (c) V_{k+1}[n] = sum_m S[n][m] V_k[m]: transposed lists ----------------------------------------------
@@ -266,17 +286,7 @@ csr_bwd_fused_kernel(const float* __restrict__ x, const int32_t* __restrict__ ro
       nxt[it] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (idx < total) {
         const int n = idx / F4, f4 = idx - n * F4;
-        const int beg = rp[n], end = rp[n + 1];
-        const float* src = vs + f4 * 4;
-        for (int i = beg; i < end; ++i) {
-          const int m = ci[i];
-          const float w = vv ? vv[i] : 1.f;
-          const float4 z = *reinterpret_cast<const float4*>(src + (size_t)m * FS);
-          nxt[it].x = fmaf(w, z.x, nxt[it].x);
-          nxt[it].y = fmaf(w, z.y, nxt[it].y);
-          nxt[it].z = fmaf(w, z.z, nxt[it].z);
-          nxt[it].w = fmaf(w, z.w, nxt[it].w);
-        }
+        nxt[it] = gather_row(vs + f4 * 4, FS, ci, vv, rp[n], rp[n + 1]);
       }
     }
     __syncthreads();
@@ -303,7 +313,7 @@ bool csr_bwd_fused_supported(int N, int G, int F, int K, size_t* smem_bytes) {
   if ((kFusedThreads / 32) % ((F >> 4) * (G >> 3)) != 0) return false;   // warps = output tiles x node groups
   if ((long long)N * F > (long long)kFusedThreads * kFusedItems * 4) return false;
   const size_t MT = (size_t)(N + 15) >> 4;
-  const size_t bytes = (MT * 16 * (F + 4) + (size_t)K * G * F * 2 + (size_t)F * K * G + F) * sizeof(float);
+  const size_t bytes = (MT * 16 * (F + 4) + (size_t)K * G * F * 2 + (size_t)F * K * G + F + (size_t)(kFusedThreads / 32) * F) * sizeof(float);
   DeviceInfo di;
   if (get_device_info(&di)) return false;
   if (bytes + 1024 > (size_t)di.smem_optin) return false;

@@ -1,7 +1,4 @@
 mkdir -p gpurun_out
-L=$PWD/gnn-formation-control_b200
-GFC_B=65536 timeout 45 python tools/time_wide.py cfg3 > gpurun_out/exp_cur.log 2>&1; echo "[time_wide] $(tr '\n' '|' < gpurun_out/exp_cur.log)"
-GFC_B=16384 timeout 45 python tools/time_wide.py cfg4 > gpurun_out/exp_cfg4.log 2>&1; cat gpurun_out/exp_cfg4.log
-timeout 400 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider --timeout 60 --timeout-method thread -k "wide or cfg3 or model_level or rollout or stacked or cfg1 or config_dense or dp_two or partial or statistics or dense_binary or recurrent" > gpurun_out/pytest_wide_r2d.log 2>&1
-echo "pytest wide exit $? :: $(tail -3 gpurun_out/pytest_wide_r2d.log | tr '\n' '|')"
-GFC_LIB=$L/libgfc_timeline.so timeout 60 python tools/wide_clocks.py cfg3 2368 dx 0 600 > gpurun_out/timeline_dx_r2i.log 2>&1
+timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider --timeout 100 --timeout-method thread -k "csr" > gpurun_out/pytest_csr_r2k.log 2>&1
+echo "pytest csr exit $? :: $(tail -3 gpurun_out/pytest_csr_r2k.log | tr '\n' '|')"
+timeout 120 python tools/time_csr.py > gpurun_out/time_csr_r2k.log 2>&1; head -6 gpurun_out/time_csr_r2k.log; grep "csr_.*fused" gpurun_out/time_csr_r2k.log | cut -c1-60,150-230
