@@ -270,7 +270,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
-    if (use_wide(gs, N, G, F, K, 0, prec) && a.vec_ok && aligned16(gs.pos)) {
+    if (use_wide(gs, N, G, F, K, 0, prec) && a.vec_ok && aligned16(gs.pos) && aligned16(h)) {
       // tcgen05 / TMEM path: fp16 hi/lo planes, hops and taps on the tensor cores
       const WideWs wws = wide_ws(B, N, G, F, K, 0);
       unsigned char* hp = reinterpret_cast<unsigned char*>(ws) + p.ws_bytes + wws.pack;
@@ -370,7 +370,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
                (gs.kind == GSRC_POS || aligned16(gs.S));
     a.p = p;
     a.dbg_clk = g_dbg_clk;
-    if (use_wide(gs, N, G, F, K, 1, prec) && a.vec_ok && aligned16(gs.pos) && (!dX || aligned16(dX)) &&
+    if (use_wide(gs, N, G, F, K, 1, prec) && a.vec_ok && aligned16(gs.pos) && aligned16(h) && (!dX || aligned16(dX)) &&
         (!dH || wide_dh_supported(N, G, F, K))) {
       // tcgen05 path: dX kernel (V_k = P^k (dY o act'), dX = sum_k V_k H_k) and dH / db kernel (accumulators in
       // tensor memory across all tiles of a CTA)
@@ -624,7 +624,7 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   rc = gso_mode_threshold(mode, radius, &thr, &norm);
   if (rc) return rc;
   GsoSrc gs{GSRC_POS, nullptr, pos, radius, mode};
-  GFC_REQUIRE(use_wide(gs, N, G, F, K, 0, precision) && aligned16(x_nm) && aligned16(y) && aligned16(pos),
+  GFC_REQUIRE(use_wide(gs, N, G, F, K, 0, precision) && aligned16(x_nm) && aligned16(y) && aligned16(pos) && aligned16(h),
               GFC_ERR_UNSUPPORTED, "%s: node-major input needs the tcgen05 wide path (positions, G, F in {64,128}, "
               "N <= 128, 16-byte aligned tensors); transpose to [B,G,N] and call gfc_filter_fwd_pos", fn);
   TilePlan p;
