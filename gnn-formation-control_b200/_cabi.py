@@ -17,6 +17,7 @@ GSO_BINARY_LE, GSO_SYM_NORM_LT, GSO_BINARY_LT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LEAKY_RELU = 0, 1, 2
 PREC_FP32_3XTF32, PREC_TF32, PREC_F16 = 0, 1, 2
 PREC_FLAG_BINARY_GSO = 0x100
+PREC_FLAG_SHARED_GSO = 0x200
 PATH_TILE, PATH_WORKSPACE, PATH_TCGEN05_WIDE = 1, 2, 3
 OPT_SKIP_GRAD_REDUCE = 1
 OPT_DISABLE_TCGEN05 = 2

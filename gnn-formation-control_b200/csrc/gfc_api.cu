@@ -68,6 +68,7 @@ struct GsoSrc {
   double radius;
   int mode;
   int binary = 0;   // dense: the caller vouches that every entry is 0 or 1 (GFC_PREC_FLAG_BINARY_GSO)
+  int shared = 0;   // dense: S is [E,N,N], one GSO for the whole batch (GFC_PREC_FLAG_SHARED_GSO)
 };
 static thread_local int g_last_path = 0;   // gfc_last_path(): kernel family of this thread's last filter call
 
@@ -235,7 +236,7 @@ static size_t wide_ws_extra(int B, int N, int G, int F, int K, int backward) { r
 static void fill_wide_graph(WideGraph& g, const GsoSrc& gs, const TileArgs& a, bool norm, int N, int transpose) {
   g = WideGraph{};
   g.pos = gs.pos; g.thr = a.thr; g.thr_lo = a.thr_lo; g.thr_hi = a.thr_hi; g.norm = norm ? 1 : 0;
-  if (gs.kind == GSRC_DENSE) { g.pos = nullptr; g.S = gs.S; g.s_bstride = (long long)N * N; g.s_transpose = transpose; g.norm = 0; }
+  if (gs.kind == GSRC_DENSE) { g.pos = nullptr; g.S = gs.S; g.s_bstride = gs.shared ? 0 : (long long)N * N; g.s_transpose = transpose; g.norm = 0; }
 }
 
 // ---- forward ------------------------------------------------------------------
@@ -265,6 +266,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     if (rc) return rc;
     TileArgs a{};
     a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
+    a.s_bstride = gs.shared ? 0 : (long long)N * N;
     a.x = x; a.h = h; a.bias = bias; a.y = y;
     a.act = act; a.slope = slope; a.single_pass = (prec != GFC_PREC_FP32_3XTF32);
     a.vec_ok = aligned16(x) && aligned16(y) && (gs.kind == GSRC_POS || aligned16(gs.S));
@@ -302,6 +304,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   if (rc) return rc;
   char* wsb = static_cast<char*>(ws);
   const float* S = gs.S;
+  const int s_shared = (gs.kind == GSRC_DENSE && gs.shared) ? 1 : 0;
   if (gs.kind == GSRC_POS) {
     float* Sw = reinterpret_cast<float*>(wsb + g.ws_s);
     int lc = launch_counter();
@@ -315,7 +318,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   rc = launch_xpose_in(x, Zw, B, N, G, E, K, st);
   if (rc) return rc;
   for (int k = 1; k < K; ++k) {
-    rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
+    rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, s_shared, st);
     if (rc) return rc;
   }
   if (g.rows_ok) return rows_fwd(g, wsb, Zw, h, bias, y, act, slope, prec, st);
@@ -362,6 +365,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     char* wsb = static_cast<char*>(ws);
     TileArgs a{};
     a.S = gs.S; a.pos = gs.pos; set_thresholds(a, thr, norm);
+    a.s_bstride = gs.shared ? 0 : (long long)N * N;
     a.x = x; a.h = h; a.yout = yout; a.dY = dY; a.dX = dX;
     a.dHp = dH ? reinterpret_cast<float*>(wsb + p.ws_dhp) : nullptr;
     a.dbp = db ? reinterpret_cast<float*>(wsb + p.ws_dbp) : nullptr;
@@ -444,6 +448,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   if (rc) return rc;
   char* wsb = static_cast<char*>(ws);
   const float* S = gs.S;
+  const int s_shared = (gs.kind == GSRC_DENSE && gs.shared) ? 1 : 0;
   if (gs.kind == GSRC_POS) {
     float* Sw = reinterpret_cast<float*>(wsb + g.ws_s);
     int lc = launch_counter();
@@ -462,7 +467,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       rc = launch_xpose_in(x, Zw, B, N, G, E, K, st);
       if (rc) return rc;
       for (int k = 1; k < K; ++k) {
-        rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
+        rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, s_shared, st);
         if (rc) return rc;
       }
     }
@@ -471,7 +476,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     if (rc) return rc;
     if (dX) {
       for (int k = K - 2; k >= 0; --k) {
-        rc = launch_hop_dense(Zw, S, B, N, G, E, K, k + 1, k, 1, st);
+        rc = launch_hop_dense(Zw, S, B, N, G, E, K, k + 1, k, 1, s_shared, st);
         if (rc) return rc;
       }
       rc = launch_xpose_out(Zw, dX, B, N, G, E, K, st);
@@ -492,7 +497,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_xpose_in(x, Zw, B, N, G, E, K, st);
     if (rc) return rc;
     for (int k = 1; k < K; ++k) {
-      rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, st);
+      rc = launch_hop_dense(Zw, S, B, N, G, E, K, k - 1, k, 0, s_shared, st);
       if (rc) return rc;
     }
     float* part = reinterpret_cast<float*>(wsb + g.ws_dhp);
@@ -508,7 +513,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
     rc = launch_sgemm(Dw, F, 1, h, C, 1, Zw, C, 0, rows, (int)C, F, 1, nullptr, GFC_ACT_NONE, 0.f, st);
     if (rc) return rc;
     for (int k = K - 2; k >= 0; --k) {
-      rc = launch_hop_dense(Zw, S, B, N, G, E, K, k + 1, k, 1, st);
+      rc = launch_hop_dense(Zw, S, B, N, G, E, K, k + 1, k, 1, s_shared, st);
       if (rc) return rc;
     }
     rc = launch_xpose_out(Zw, dX, B, N, G, E, K, st);
@@ -594,7 +599,8 @@ extern "C" int gfc_filter_fwd(const float* x, const float* S, const float* h, co
                               void* workspace, size_t workspace_bytes, void* stream) {
   GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
   gs.binary = (precision & GFC_PREC_FLAG_BINARY_GSO) != 0 && E == 1;
-  precision &= ~GFC_PREC_FLAG_BINARY_GSO;
+  gs.shared = (precision & GFC_PREC_FLAG_SHARED_GSO) != 0;
+  precision &= ~(GFC_PREC_FLAG_BINARY_GSO | GFC_PREC_FLAG_SHARED_GSO);
   return filter_fwd_impl("gfc_filter_fwd", gs, x, h, bias, y, B, N, G, F, K, E, act, slope, precision,
                          workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -652,7 +658,8 @@ extern "C" int gfc_filter_bwd(const float* x, const float* S, const float* h, co
                               void* workspace, size_t workspace_bytes, void* stream) {
   GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
   gs.binary = (precision & GFC_PREC_FLAG_BINARY_GSO) != 0 && E == 1;
-  precision &= ~GFC_PREC_FLAG_BINARY_GSO;
+  gs.shared = (precision & GFC_PREC_FLAG_SHARED_GSO) != 0;
+  precision &= ~(GFC_PREC_FLAG_BINARY_GSO | GFC_PREC_FLAG_SHARED_GSO);
   return filter_bwd_impl("gfc_filter_bwd", gs, x, h, y_out, dY, dX, dH, db, B, N, G, F, K, E, act, slope,
                          precision, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -688,7 +695,8 @@ extern "C" int gfc_filter_bwd_dp(const float* x, const float* S, const float* h,
                                  void* stream) {
   GsoSrc gs{GSRC_DENSE, S, nullptr, 0.0, 0};
   gs.binary = (precision & GFC_PREC_FLAG_BINARY_GSO) != 0 && E == 1;
-  precision &= ~GFC_PREC_FLAG_BINARY_GSO;
+  gs.shared = (precision & GFC_PREC_FLAG_SHARED_GSO) != 0;
+  precision &= ~(GFC_PREC_FLAG_BINARY_GSO | GFC_PREC_FLAG_SHARED_GSO);
   DpCtx dp{peer_buf, peer_sig, rank, world, scale};
   if (!grads) { set_error("gfc_filter_bwd_dp: NULL gradient bucket"); return GFC_ERR_BAD_ARG; }
   return filter_bwd_impl("gfc_filter_bwd_dp", gs, x, h, y_out, dY, dX, grads, grads + (size_t)F * E * K * G,

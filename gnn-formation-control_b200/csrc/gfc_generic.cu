@@ -62,7 +62,7 @@ xpose_out_kernel(const float* __restrict__ Uw, float* __restrict__ dX, int B, in
 template <bool T>
 __global__ void __launch_bounds__(256)
 hop_dense_kernel(float* __restrict__ W, const float* __restrict__ S, int B, int N, int G, int E, int K,
-                 int ksrc, int kdst) {
+                 int ksrc, int kdst, int s_shared) {
   const long long total = (long long)B * E * N * G;
   const int C = E * K * G;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -72,7 +72,7 @@ hop_dense_kernel(float* __restrict__ W, const float* __restrict__ S, int B, int 
     const int n = (int)(q % N); q /= N;
     const int e = (int)(q % E);
     const int b = (int)(q / E);
-    const float* Sb = S + ((size_t)b * E + e) * N * N;
+    const float* Sb = S + ((size_t)(s_shared ? 0 : b) * E + e) * N * N;
     const float* src = W + (size_t)b * N * C + (size_t)(e * K + ksrc) * G + g;
     float* dst = W + ((size_t)b * N + n) * C + (size_t)(e * K + kdst) * G + g;
     float acc = T ? *dst : 0.f;
@@ -315,11 +315,11 @@ int launch_xpose_out(const float* Uw, float* dX, int B, int N, int G, int E, int
 }
 
 int launch_hop_dense(float* W, const float* S, int B, int N, int G, int E, int K, int ksrc, int kdst,
-                     int transposed, cudaStream_t st) {
+                     int transposed, int s_shared, cudaStream_t st) {
   const long long total = (long long)B * E * N * G;
   const unsigned grid = grid_for(total, 256, 148 * 32);
-  if (transposed) hop_dense_kernel<true><<<grid, 256, 0, st>>>(W, S, B, N, G, E, K, ksrc, kdst);
-  else hop_dense_kernel<false><<<grid, 256, 0, st>>>(W, S, B, N, G, E, K, ksrc, kdst);
+  if (transposed) hop_dense_kernel<true><<<grid, 256, 0, st>>>(W, S, B, N, G, E, K, ksrc, kdst, s_shared);
+  else hop_dense_kernel<false><<<grid, 256, 0, st>>>(W, S, B, N, G, E, K, ksrc, kdst, s_shared);
   GFC_LAUNCH_CHECK("hop_dense_kernel");
   return GFC_OK;
 }

@@ -7,7 +7,7 @@ namespace gfc {
 int launch_xpose_in(const float* x, float* Zw, int B, int N, int G, int E, int K, cudaStream_t st);
 int launch_xpose_out(const float* Uw, float* dX, int B, int N, int G, int E, int K, cudaStream_t st);
 int launch_hop_dense(float* W, const float* S, int B, int N, int G, int E, int K, int ksrc, int kdst,
-                     int transposed, cudaStream_t st);
+                     int transposed, int s_shared, cudaStream_t st);
 int launch_hop_csr(float* W, const int32_t* rowptr, const int32_t* colidx, const float* vals,
                    long long nnz_stride, int B, int N, int G, int K, int ksrc, int kdst, int accum,
                    cudaStream_t st);

@@ -268,7 +268,7 @@ tc5_n8_fwd_kernel(const TileArgs a) {
     int gq = rg.begin + j;
     const float* px = a.x + ((size_t)gq * G + c) * N;
     const float2* ppos = reinterpret_cast<const float2*>(a.pos) + (size_t)gq * N + lane;
-    const float* ps = a.S + (size_t)gq * N * N + lane;
+    const float* ps = a.S + (size_t)gq * a.s_bstride + lane;
     float xcol[N];
     float2 mypos = make_float2(0.f, 0.f);
     float s0 = 0.f, s1 = 0.f;
@@ -289,7 +289,7 @@ tc5_n8_fwd_kernel(const TileArgs a) {
         s0 = okr ? __ldg(ps) : 0.f;
         s1 = okr ? __ldg(ps + 32) : 0.f;
       }
-      gq += GPC; px += (size_t)GPC * G * N; ppos += GPC * N; ps += GPC * N * N;
+      gq += GPC; px += (size_t)GPC * G * N; ppos += GPC * N; ps += (size_t)GPC * a.s_bstride;
       if (lane == 0 && gq < rg.end) tc5::bulk_prefetch_l2(px - c * N, G * N * 4);   // the tile after, into L2
     };
     auto produce = [&](int t, int buf) {
@@ -511,7 +511,7 @@ tc5_n8_bwd_kernel(const TileArgs a) {
     const float* pdy = a.dY + (size_t)gq * N * F + c;
     const float* py = a.yout + (size_t)gq * N * F + c;
     const float2* ppos = reinterpret_cast<const float2*>(a.pos) + (size_t)gq * N + lane;
-    const float* ps = a.S + (size_t)gq * N * N + lane;
+    const float* ps = a.S + (size_t)gq * a.s_bstride + lane;
     const bool has_act = a.act != GFC_ACT_NONE;
     // d(pre) = yo > 0 ? dy : dy * neg  (act_grad of gfc_common.cuh without the per-element branches; yo = 1 when
     // there is no activation)
@@ -544,7 +544,7 @@ tc5_n8_bwd_kernel(const TileArgs a) {
         }
       }
       gq += GPC; px += (size_t)GPC * G * N; pdy += (size_t)GPC * N * F; py += (size_t)GPC * N * F;
-      ppos += GPC * N; ps += GPC * N * N;
+      ppos += GPC * N; ps += (size_t)GPC * a.s_bstride;
       if (lane == 0 && gq < rg.end) {   // the tile after, into L2
         tc5::bulk_prefetch_l2(pdy - c, N * F * 4);
         if (has_act) tc5::bulk_prefetch_l2(py - c, N * F * 4);

@@ -48,6 +48,7 @@ int plan_tile(int B, int N, int G, int F, int K, int backward, int gsrc, TilePla
 struct TileArgs {
   // graph source
   const float* S;      // [B,N,N] dense (E = 1)
+  long long s_bstride; // floats between consecutive graphs of S: N*N, or 0 = one GSO shared by the whole batch
   const float* pos;    // [B,N,2]
   double thr;          // squared-distance threshold (GSRC_POS), fp64 rule
   float thr_lo, thr_hi;  // fp32 band: s < thr_lo surely inside, s > thr_hi surely outside

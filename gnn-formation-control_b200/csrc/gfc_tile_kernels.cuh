@@ -197,13 +197,17 @@ __device__ __forceinline__ void load_gso_tile(float* __restrict__ Ss, float* __r
   const int NN = N * N;
   if (GSRC == GSRC_DENSE) {
     const int total = gcount * NN;
-    const float* src = a.S + (size_t)b0 * NN;
-    if (a.vec_ok && (NN & 3) == 0) {
-      const float4* src4 = reinterpret_cast<const float4*>(src);
-      float4* dst4 = reinterpret_cast<float4*>(Ss);
-      for (int i = tid; i < (total >> 2); i += CFG::kThreads) dst4[i] = __ldg(src4 + i);
+    if (a.s_bstride == 0) {   // one GSO shared by the whole batch (GraphFilter, graphML.py:1111): every slot gets the same matrix
+      for (int i = tid; i < total; i += CFG::kThreads) Ss[i] = __ldg(a.S + i % NN);
     } else {
-      for (int i = tid; i < total; i += CFG::kThreads) Ss[i] = __ldg(src + i);
+      const float* src = a.S + (size_t)b0 * NN;
+      if (a.vec_ok && (NN & 3) == 0) {
+        const float4* src4 = reinterpret_cast<const float4*>(src);
+        float4* dst4 = reinterpret_cast<float4*>(Ss);
+        for (int i = tid; i < (total >> 2); i += CFG::kThreads) dst4[i] = __ldg(src4 + i);
+      } else {
+        for (int i = tid; i < total; i += CFG::kThreads) Ss[i] = __ldg(src + i);
+      }
     }
   } else {
     const int nn = gcount * N;

@@ -59,9 +59,13 @@ def _is_binary(S32, E, G, F):
 class _Src:
     """graph source handed to the autograd function (not a tensor argument)."""
 
-    def __init__(self, kind, S=None, pos=None, radius=0.0, mode=0, csr=None, binary=False):
+    def __init__(self, kind, S=None, pos=None, radius=0.0, mode=0, csr=None, binary=False, shared=False):
         self.kind, self.S, self.pos, self.radius, self.mode, self.csr = kind, S, pos, radius, mode, csr
         self.binary = binary     # dense S with 0/1 entries only: eligible for the tcgen05 wide kernels
+        self.shared = shared     # dense S is [E,N,N]: one GSO for the whole batch (GraphFilter)
+
+    def flags(self):
+        return (C.PREC_FLAG_BINARY_GSO if self.binary else 0) | (C.PREC_FLAG_SHARED_GSO if self.shared else 0)
 
 
 class _LSIGF(torch.autograd.Function):
@@ -103,7 +107,7 @@ class _LSIGF(torch.autograd.Function):
             elif src.kind == _SRC_DENSE:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 0)
                 ws = _workspace(nb, dev)
-                pflag = prec | (C.PREC_FLAG_BINARY_GSO if src.binary else 0)
+                pflag = prec | src.flags()
                 C.check(C.lib.gfc_filter_fwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(b32), C.ptr(y),
                                              B, N, G, F_, K, E, act, slope, pflag, C.ptr(ws), nb, st),
                         "gfc_filter_fwd")
@@ -150,7 +154,7 @@ class _LSIGF(torch.autograd.Function):
             if src.kind == _SRC_DENSE:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 1)
                 ws = _workspace(nb, dev)
-                pflag = prec | (C.PREC_FLAG_BINARY_GSO if src.binary else 0)
+                pflag = prec | src.flags()
                 C.check(C.lib.gfc_filter_bwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(yout), C.ptr(dY),
                                              C.ptr(dX), C.ptr(dH), C.ptr(db), B, N, G, F_, K, E,
                                              act, slope, pflag, C.ptr(ws), nb, st), "gfc_filter_bwd")
@@ -320,8 +324,8 @@ class GraphFilter(GraphFilterBatch):
             assert S is not None, "call addGSO before forward"
             _require_cuda(S, "the GSO")
             S32 = S.detach().to(device=device, dtype=torch.float32)
-            self._src = _Src(_SRC_DENSE, S=S32.unsqueeze(0).expand(B, -1, -1, -1).contiguous(),
-                             binary=_is_binary(S32, self.E, self.G, self.F))
+            # ONE copy of S [E,N,N]; the kernels index it with a zero batch stride (GFC_PREC_FLAG_SHARED_GSO)
+            self._src = _Src(_SRC_DENSE, S=S32.contiguous(), binary=_is_binary(S32, self.E, self.G, self.F), shared=True)
             self._srcB = B
         return self._src
 

@@ -72,7 +72,10 @@ enum {
      asymmetric, possibly with a diagonal).  The hop matrix is then exact in fp16 and wide shapes (G, F in {64,128},
      N <= 127) run on the tcgen05 kernels like the position-built GSOs; without the flag a dense S runs on the
      mma.sync tile kernels (any weights).  gnnfc.GraphFilterBatch.addGSO checks the entries itself.                  */
-  GFC_PREC_FLAG_BINARY_GSO = 0x100
+  GFC_PREC_FLAG_BINARY_GSO = 0x100,
+  /* flag, same entry points: S is [E,N,N] — ONE GSO shared by all B graphs of the batch (the reference's same-GSO layer
+     GraphFilter / LSIGF, graphML.py:1111, :48) — instead of [B,E,N,N]; no per-graph copies are made or read            */
+  GFC_PREC_FLAG_SHARED_GSO = 0x200
 };
 
 int gfc_version(void);
