@@ -671,7 +671,9 @@ def per_kernel_times(torch, hp, reps):
     calls = dict(fwd=lambda i: hp.fwd(i, hp.stream()))
     if hp.train:
         calls["bwd_dx"] = lambda i: bwd_partial(i, hp.stream(), True, False)
-        calls["bwd_dh"] = lambda i: bwd_partial(i, hp.stream(), False, True)
+        # the dH / db kernel as it runs inside the step (fed by the dX kernel's dY o act'(y) and batch maximum) = the whole
+        # backward call minus the dX-only call; a dH-only call would add a pass over dY and read dY + y instead of one tensor
+        calls["bwd_all"] = lambda i: bwd_partial(i, hp.stream(), True, True)
         C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 1), "gfc_set_option")
     try:
         for name, call in calls.items():
@@ -690,6 +692,10 @@ def per_kernel_times(torch, hp, reps):
                 g.replay()
             e1.record(); torch.cuda.synchronize()
             out[name] = dict(ms=e0.elapsed_time(e1) / (reps * hp.ring), launches=nl)
+        if "bwd_all" in out:
+            allb = out.pop("bwd_all")
+            out["bwd_dh"] = dict(ms=max(allb["ms"] - out["bwd_dx"]["ms"], 1e-6), launches=allb["launches"] - out["bwd_dx"]["launches"],
+                                 how="whole backward call minus the dX-only call")
     finally:
         if hp.train:
             C.check(C.lib.gfc_set_option(C.OPT_SKIP_GRAD_REDUCE, 0), "gfc_set_option")

@@ -1,3 +1,4 @@
 mkdir -p gpurun_out
-timeout 500 python -m pytest tests -x -q -m gpu -p no:cacheprovider --timeout 120 --timeout-method thread > gpurun_out/pytest_gpu_r2n.log 2>&1
-echo "pytest exit $? :: $(tail -3 gpurun_out/pytest_gpu_r2n.log | tr '\n' '|')"
+L=$PWD/gnn-formation-control_b200
+GFC_LIB=$L/libgfc_timeline.so timeout 60 python tools/wide_clocks.py cfg4 16384 fwd 0 500 > gpurun_out/timeline_cfg4_fwd.log 2>&1
+echo "timeline exit $?"

@@ -5,10 +5,10 @@
 LIB=${1:-gnn-formation-control_b200/libgfc.so}
 echo "# $(basename $LIB): $(stat -c %s $LIB) bytes, $(date -u +%F)"
 cuobjdump -sass "$LIB" | awk '
-  /Function :/ { fn=$3; sub(/^_ZN3gfc/,"",fn); names[fn]=1; next }
+  /Function :/ { fn=$3; sub(/^_ZN3gfc[0-9]*/,"",fn); sub(/I[LN].*$/,"",fn); sub(/E?v?P[KF].*$/,"",fn); names[fn]=1; next }
   { for (m in pat) if ($0 ~ pat[m]) cnt[fn,m]++ }
   BEGIN { pat["UTCHMMA"]="UTCHMMA"; pat["UTCQMMA"]="UTCQMMA"; pat["LDTM"]="LDTM"; pat["STTM"]="STTM"; pat["UTMALDG"]="UTMALDG"; pat["UTMASTG"]="UTMASTG";
-          pat["UBLKCP"]="UBLKCP"; pat["UBLKPF"]="UBLKPF"; pat["HMMA"]="HMMA"; pat["SYNCS"]="SYNCS"; pat["REDG"]="RED\\."; pat["UTCBAR"]="UTCBAR" }
+          pat["UBLKCP"]="UBLKCP"; pat["UBLKPF"]="UBLKPF"; pat["HMMA"]="[^C]HMMA"; pat["SYNCS"]="SYNCS"; pat["REDG"]="REDG"; pat["UTCBAR"]="UTCBAR" }
   END { printf "%-70s", "kernel"; n=split("UTCHMMA LDTM STTM UTMALDG UTMASTG UBLKCP UBLKPF UTCBAR SYNCS HMMA REDG", ord, " ");
         for (i=1;i<=n;i++) printf "%8s", ord[i]; printf "\n";
         for (f in names) { tot=0; for (i=1;i<=n;i++) tot+=cnt[f,ord[i]]; if (tot==0) continue;
