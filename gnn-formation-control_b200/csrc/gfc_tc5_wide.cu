@@ -99,7 +99,8 @@ __device__ __forceinline__ int row_degree4(const int* sdeg, int pbuf, int row) {
 // waited ~11k of every 20k cycles per tile.  The dH kernel still uses all 16 warps as one set.
 constexpr int kWideThreads = 576;
 constexpr int kGroupWarps = 8;
-int g_wide_flush_every = 2;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY)
+int g_wide_flush_every = 3;   // gfc_set_option(GFC_OPT_WIDE_FLUSH_EVERY); cfg3 full batch (tools/wide_flush_accuracy.py): dH error vs fp64
+                              // 0.9e-6 / 1.4e-6 / 1.8e-6 / 2.2e-6 / 4.6e-6 at 1 / 2 / 3 / 4 / 8 tiles, dH call 4.81 / 4.15 / 3.98 / 3.92 / 4.02 ms
 int g_wide_no_prefetch = 0;    // experiment switch
 
 // exact fp64 rule, kept out of line so the (rare) rounding-band case is a real branch and the fp64 /

@@ -253,7 +253,7 @@ int gfc_tile_plan_info(int B, int N, int G, int F, int K, int backward, int from
 enum {
   GFC_OPT_SKIP_GRAD_REDUCE = 1,
   GFC_OPT_DISABLE_TCGEN05 = 2, /* 1: use the mma.sync tile kernels where a tcgen05 kernel exists (A/B comparison) */
-  GFC_OPT_WIDE_FLUSH_EVERY = 3, /* tiles chained into the TMEM dH accumulators between drains (default 2) */
+  GFC_OPT_WIDE_FLUSH_EVERY = 3, /* tiles chained into the TMEM dH accumulators between drains (default 3) */
   GFC_OPT_PDL = 4, /* 1 (default): the cfg2-shape kernels and the gradient reduction use programmatic dependent launch */
   GFC_OPT_CSR_FUSED = 5, /* 1 (default): one-CTA-per-graph fused CSR forward / backward kernels; 0: workspace pipeline (A/B) */
   GFC_OPT_WIDE_NO_PREFETCH = 6, /* 1: tcgen05 wide kernels skip the L2 bulk prefetch of the next tiles (experiment; default 0) */

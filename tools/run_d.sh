@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-L=$PWD/gnn-formation-control_b200
-GFC_LIB=$L/libgfc_timeline.so timeout 60 python tools/wide_clocks.py cfg4 16384 fwd 0 500 > gpurun_out/timeline_cfg4_fwd.log 2>&1
-echo "timeline exit $?"
+timeout 200 python tools/wide_flush_accuracy.py 1 2 3 4 6 8 > gpurun_out/flush_acc_r2q.log 2>&1; cat gpurun_out/flush_acc_r2q.log
