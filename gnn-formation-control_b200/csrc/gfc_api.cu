@@ -541,7 +541,7 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_WIDE_NO_PREFETCH) { g_wide_no_prefetch = value; return GFC_OK; }
   if (key == GFC_OPT_DP_TIMEOUT_MS) { g_dp_timeout_ms = value > 0 ? value : 10000; return GFC_OK; }
   if (key == GFC_OPT_CSR_FUSED) { g_csr_fused = value ? 1 : 0; return GFC_OK; }
-  if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 2; return GFC_OK; }
+  if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 3; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
   return GFC_ERR_BAD_ARG;
 }
