@@ -646,6 +646,14 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       const float4* p = reinterpret_cast<const float4*>(w.in + (size_t)b0 * N * CIN);
       const int n4 = gcount * N * (CIN / 4);
       float m = 0.f;
+      if (MODE == 1 && w.act != GFC_ACT_NONE) {
+        // dX: the slab loads that follow read dY (in L2 after this pass) AND y (still in DRAM: every batch then waited a DRAM
+        // round trip, ~2.5k cycles instead of ~0.8k).  Pull the tile's y lines into L2 now, one 128-byte line per request.
+        const char* yb = reinterpret_cast<const char*>(w.yout + (size_t)b0 * N * CIN);
+        const int bytes = n4 * 16;
+        for (int off = wt * 128; off < bytes; off += 32 * kGroupWarps * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + off));
+      }
       // eight independent 16-byte loads in flight per thread and round trip (a full 128 x 128 tile = 2 round trips)
 #pragma unroll 1
       for (int i0 = wt; i0 < n4; i0 += 8 * 32 * kGroupWarps) {
