@@ -1142,6 +1142,11 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
                 const int j = rr / N, n = rr - j * N;
                 const float4 v = ldg_f32x4(w.x + ((size_t)(b0 + j) * G + g) * N + n, g < G && rr < rows_used);
                 dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+                if (qq == 0) {   // the second row quarter is loaded right after the first one's store: pull its lines into L2 now
+                  const int r2 = rr + 32, j2 = r2 / N, n2 = r2 - j2 * N;
+                  if (g < G && r2 < rows_used)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(w.x + ((size_t)(b0 + j2) * G + g) * N + n2));
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
