@@ -30,5 +30,6 @@ def fb():
 print("fwd+bwd   %.3f ms" % t(fb))
 import torch.profiler as tp
 with tp.profile(activities=[tp.ProfilerActivity.CUDA]) as prof:
+    gnnfc.build_csr(pos, 2.0, "binary_le", max_degree=64); gnnfc.build_csr(pos, 2.0, "sym_norm_lt", max_degree=64)
     fb(); torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60))
