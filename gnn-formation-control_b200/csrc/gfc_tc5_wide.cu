@@ -654,6 +654,13 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         for (int off = wt * 128; off < bytes; off += 32 * kGroupWarps * 128)
           asm volatile("prefetch.global.L2 [%0];" ::"l"(yb + off));
       }
+      // ... and the NEXT tile's input lines, which this pass will read first thing in the next iteration
+      if (tile + 1 < t_end) {
+        const int nb = min(w.gpc, w.B - (b0 + w.gpc)) * N * CIN * 4;
+        const char* db = reinterpret_cast<const char*>(w.in + (size_t)(b0 + w.gpc) * N * CIN);
+        for (int off = wt * 128; off < nb; off += 32 * kGroupWarps * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(db + off));
+      }
       // eight independent 16-byte loads in flight per thread and round trip (a full 128 x 128 tile = 2 round trips)
 #pragma unroll 1
       for (int i0 = wt; i0 < n4; i0 += 8 * 32 * kGroupWarps) {

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -p no:cacheprovider --timeout 100 --timeout-method thread -k "csr" > gpurun_out/pytest_csr_r2x.log 2>&1
-echo "pytest csr exit $? :: $(tail -3 gpurun_out/pytest_csr_r2x.log | tr '\n' '|')"
-timeout 120 python tools/time_csr.py > gpurun_out/time_csr_r2x.log 2>&1; grep -E "build_csr|csr_|forward|fwd" gpurun_out/time_csr_r2x.log | cut -c1-70,150-235
+GFC_B=65536 timeout 45 python tools/time_wide.py cfg3 > gpurun_out/exp_cur.log 2>&1; echo "[bulk on ] $(tr '\n' '|' < gpurun_out/exp_cur.log)"
+NOPF=1 GFC_B=65536 timeout 45 python tools/time_wide.py cfg3 > gpurun_out/exp_cur2.log 2>&1; echo "[bulk off] $(tr '\n' '|' < gpurun_out/exp_cur2.log)"
+GFC_B=16384 timeout 45 python tools/time_wide.py cfg4 > gpurun_out/exp_cfg4.log 2>&1; cat gpurun_out/exp_cfg4.log
+NOPF=1 GFC_B=16384 timeout 45 python tools/time_wide.py cfg4 > gpurun_out/exp_cfg4.log 2>&1; cat gpurun_out/exp_cfg4.log
