@@ -867,6 +867,11 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
   const bool norm = w.g.norm != 0;
   const int fh = blockIdx.x % L::NFH, part = blockIdx.x / L::NFH, nparts = gridDim.x / L::NFH;
   const int TM_HOP = L::TM_ACC + K * FH;
+  // Both planes of V_k in ONE hop MMA per k-step (N = 2 FH: the planes are adjacent chunk arrays, so one descriptor spans
+  // them) when the tensor memory has room for the two result halves.  A hop MMA reads both operands from shared memory:
+  // with one MMA per plane the 4 KB slice of P was read twice per k-step, 6 KB per 32-cycle MMA = more than the 128 B/cycle
+  // of shared memory (measured ~58 cycles per MMA, 16 per hop); merged it is 8 KB per 64-cycle MMA, 8 per hop.
+  const bool merged = NP == 2 && (K + 2) * FH <= 384;
   // contiguous tile range per CTA group (see tc5_wide_kernel)
   const int tiles_per_part = (w.ntiles + nparts - 1) / nparts;
   const int t_begin = min(w.ntiles, part * tiles_per_part);
@@ -903,6 +908,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     // =========================== MMA issuer (one elected thread) ===============================
     if (tc5::elect_one()) {
       constexpr uint32_t kIdesc = tc5::idesc_f16(128, FH, 0, 1);   // B = V planes, MN-major
+      constexpr uint32_t kIdescHop2 = tc5::idesc_f16(128, 2 * FH, 0, 1);   // B = [V hi | V lo]
       const uint32_t v_addr = tc5::smem_u32(Vb), p_addr = tc5::smem_u32(Pb);
       uint32_t par_vr = 0, par_v0 = 0, par_pr = 0, par_xr = 0;
       const int ksteps = (w.gpc * N + 15) >> 4;
@@ -957,10 +963,15 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
 #pragma unroll 1
             for (int j = 0; j < ksteps; ++j) {
               const uint64_t da = make_desc(pa + j * 2 * L::PW, L::PW, 128);
-#pragma unroll
-              for (int pl = 0; pl < NP; ++pl) {
-                tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdesc, acc);
+              if (merged) {
+                tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + j * 256, 128, L::PW), kIdescHop2, acc);
                 acc = 1;
+              } else {
+#pragma unroll
+                for (int pl = 0; pl < NP; ++pl) {
+                  tc5::mma_bf16_ss(tmem + TM_HOP, da, make_desc(vs + pl * L::PLANE + j * 256, 128, L::PW), kIdesc, acc);
+                  acc = 1;
+                }
               }
             }
             tc5::mma_commit(hop_done);
@@ -1063,15 +1074,24 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         if (norm && k == 0) wbf = dtab[128 + row_degree(sdeg, it & 1, r)];
         unsigned char* base = Vb + ((vbase + k + 1) % 3) * L::VBUF + (half * (CPA / 8)) * L::PW + r * 16;
         const uint32_t taddr = tm_lane + TM_HOP + half * CPA;
-        uint32_t v[CPA];
-        if constexpr (CPA == 32) tc5::tmem_ld32(taddr, v); else tc5::tmem_ld16(taddr, v);
-        tc5::tmem_ld_wait();
+        // merged hop: columns [0, FH) hold P V_hi, [FH, 2 FH) hold P V_lo (same scale): V_{k+1} = their sum
 #pragma unroll
-        for (int c = 0; c < CPA / 8; ++c) {
-          float f[8];
+        for (int hh = 0; hh < CPA / 16; ++hh) {
+          uint32_t v[16], v2[16];
+          tc5::tmem_ld16(taddr + hh * 16, v);
+          if (merged) tc5::tmem_ld16(taddr + FH + hh * 16, v2);
+          tc5::tmem_ld_wait();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[i] = norm ? __uint_as_float(v[c * 8 + i]) * wbf : __uint_as_float(v[c * 8 + i]);
-          store_chunk_f16<NP>(base + c * L::PW, L::PLANE, f);
+          for (int c = 0; c < 2; ++c) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float t = __uint_as_float(v[c * 8 + i]);
+              if (merged) t += __uint_as_float(v2[c * 8 + i]);
+              f[i] = norm ? t * wbf : t;
+            }
+            store_chunk_f16<NP>(base + (hh * 2 + c) * L::PW, L::PLANE, f);
+          }
         }
         publish(v_ready);
         GFC_KSTAMP(300 + k);
