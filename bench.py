@@ -46,6 +46,11 @@ WORKLOADS = {
                      B=262144, N=8, G=32, F=32, K=3, box=5.0, seed=1, mode="binary_le", train=True),
     "cfg3": dict(desc="cfg3: 64-agent synthetic swarm, K=4, F=128->128, batch 65536 graphs",
                  B=65536, N=64, G=128, F=128, K=4, box=10.0, seed=2, mode="binary_le", train=True),
+    # the SAME kernels as cfg3 with one fp16 plane per operand (1 MMA per product instead of 3): NOT the parity mode — opt-in,
+    # stated bound 2e-3 (tests/test_gpu_parity.py::test_f16_single_plane_mode_has_the_stated_bound).  Reported beside cfg3
+    # ("state this next to the numbers") to show the kernels' rate when the fp32 split is not required.
+    "cfg3_f16": dict(desc="cfg3 shapes in the opt-in single-fp16-plane mode (GFC_PREC_F16, bound 2e-3; not the parity mode)",
+                     B=65536, N=64, G=128, F=128, K=4, box=10.0, seed=2, mode="binary_le", train=True, prec="f16"),
     "cfg4": dict(desc="cfg4: rollout inference, 16384 parallel 12-robot swarms, per-step GSO rebuild + "
                       "2-layer graph filter 128->128->128, K=3", B=16384, N=12, G=128, F=128, K=3, box=6.0,
                  seed=3, mode="binary_le", train=False, layers=2),
@@ -150,6 +155,7 @@ class HotPath:
         self.mode = C.GSO_MODES[w["mode"]]
         self.train = w["train"]
         self.layers = w.get("layers", 1)
+        self.prec = C.PRECISIONS[w.get("prec", "fp32")]   # every config runs the fp32-parity mode unless it names another
         nbf = C.lib.gfc_filter_workspace_bytes(B, N, G, F, K, 1, 0)
         self.wsf = torch.empty(max(nbf, 256), dtype=torch.uint8, device=dev); self.nbf = nbf
         # operand statistics handed from each batch's forward call to its backward call (gfc_use_stats)
@@ -179,14 +185,14 @@ class HotPath:
             C.lib.gfc_use_stats(C.ptr(self.stats[i]))
         C.check(C.lib.gfc_filter_fwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                          C.ptr(self.b), C.ptr(self.y[i]), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
-                                         C.PREC_FP32_3XTF32, C.ptr(self.wsf), self.nbf, st), "gfc_filter_fwd_pos")
+                                         self.prec, C.ptr(self.wsf), self.nbf, st), "gfc_filter_fwd_pos")
         n = C.last_launch_count()
         if self.layers == 2:
             # layer 2 consumes layer 1's node-major output in place (the reference hands the next GraphFilterBatch
             # a [B,F,N] view over exactly this memory, graphML.py:2362): no transposing copy between the layers
             C.check(C.lib.gfc_filter_fwd_pos_nm(C.ptr(self.y[i]), C.ptr(self.pos[i]), RADIUS, self.mode,
                                                 C.ptr(self.h2), C.ptr(self.b2), C.ptr(self.y2[i]), B, N, G, F, K,
-                                                C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32, C.ptr(self.wsf),
+                                                C.ACT_LEAKY_RELU, SLOPE, self.prec, C.ptr(self.wsf),
                                                 self.nbf, st), "gfc_filter_fwd_pos_nm")
             n += C.last_launch_count()
         return n
@@ -199,7 +205,7 @@ class HotPath:
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                          C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.dH),
                                          C.ptr(self.db), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
-                                         C.PREC_FP32_3XTF32, C.ptr(self.wsb), self.nbb, st), "gfc_filter_bwd_pos")
+                                         self.prec, C.ptr(self.wsb), self.nbb, st), "gfc_filter_bwd_pos")
         return C.last_launch_count()
 
     def enable_peer_exchange(self, px):
@@ -214,7 +220,7 @@ class HotPath:
             C.lib.gfc_use_stats(C.ptr(self.stats[i]))
         C.check(C.lib.gfc_filter_bwd_pos_dp(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                             C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.grads),
-                                            B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32,
+                                            B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, self.prec,
                                             C.ptr(self.wsb), self.nbb, px.buf_ptrs, px.sig_ptrs, px.rank, px.world,
                                             1.0, st), "gfc_filter_bwd_pos_dp")
         return C.last_launch_count()
@@ -235,8 +241,9 @@ def tensor_flops_per_graph(w):
     (+ backward when training)."""
     N, G, F, K = w["N"], w["G"], w["F"], w["K"]
     gpc = max(1, 128 // N)
-    taps = 2 * 128 * (K * G) * F * 3 / gpc                  # per graph share of a tile
-    hops = (K - 1) * 2 * 128 * (((gpc * N + 15) // 16) * 16) * G * 2 / gpc
+    single = w.get("prec", "fp32") != "fp32" and G == 128 and F == 128 and K <= 5   # opt-in single fp16 plane (GFC_PREC_F16)
+    taps = 2 * 128 * (K * G) * F * (1 if single else 3) / gpc                  # per graph share of a tile
+    hops = (K - 1) * 2 * 128 * (((gpc * N + 15) // 16) * 16) * G * (1 if single else 2) / gpc
     issued_fwd = taps + hops
     useful_fwd = 2 * (K - 1) * G * N * N + 2 * N * K * G * F
     layers = w.get("layers", 1)
@@ -683,7 +690,7 @@ def per_kernel_times(torch, hp, reps):
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(hp.x[i]), C.ptr(hp.pos[i]), RADIUS, hp.mode, C.ptr(hp.h),
                                          C.ptr(hp.y[i]), C.ptr(hp.dY[i]), C.ptr(hp.dX[i]) if want_dx else None,
                                          C.ptr(hp.dH) if want_dh else None, C.ptr(hp.db) if want_dh else None,
-                                         B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, C.PREC_FP32_3XTF32,
+                                         B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, hp.prec,
                                          C.ptr(hp.wsb), hp.nbb, st), "gfc_filter_bwd_pos")
         return C.last_launch_count()
 
@@ -754,10 +761,15 @@ def roofline_of(torch, w, hp, cfg_name, step_ms, peaks):
     kbytes = dict(fwd=8 * N + 4 * G * N + 4 * F * N, bwd_dx=8 * N + 8 * F * N + 4 * G * N, bwd_dh=8 * N + 4 * F * N + 4 * G * N)
     dom = max(kt, key=lambda k: kt[k]["ms"])
     per = {}
+    # fp16 flops the tensor pipe actually executes per graph and kernel (each of the three kernels issues the forward's MMA
+    # volume: 128-row block-diagonal hops, 3 / 2 MMAs per tap / hop product in the fp32-parity mode)
+    issued_fwd = tensor_flops_per_graph(dict(w, train=False, layers=1))[0]
     for k, v in kt.items():
         tf = B * fl[k] / (v["ms"] * 1e-3) / 1e12
         gb = B * kbytes[k] / (v["ms"] * 1e-3) / 1e9
+        itf = B * issued_fwd / (v["ms"] * 1e-3) / 1e12
         per[k] = dict(ms=v["ms"], launches=v["launches"], useful_tflops=tf, tensor_frac=tf / peaks["tf_burst"],
+                      issued_fp16_tflops=itf, issued_tensor_frac=itf / peaks["tf_burst"],
                       algorithmic_GBps=gb, hbm_frac=gb / peaks["hbm"])
     names = dict(fwd="tc5_wide_kernel<fwd>", bwd_dx="tc5_wide_kernel<dX>", bwd_dh="tc5_wide_dh_kernel")
     total_fl = sum(fl[k] for k in kt)
@@ -773,9 +785,12 @@ def roofline_of(torch, w, hp, cfg_name, step_ms, peaks):
                                 hbm_frac=step_gb / peaks["hbm"]),
                 issued_over_useful=tensor_flops_per_graph(w)[0] / max(tensor_flops_per_graph(w)[1], 1),
                 peak_source=peaks["src"] + ": dense bf16 burst for a kernel timed alone, sustained for the whole step; hbm_gbs",
-                note="achieved = USEFUL fp32-equivalent flops (SURVEY 8d: dense hops 2(K-1)GN^2 + taps 2NKGF per pass) of the "
-                     "dominant kernel / its duration; fp32 parity costs 3 half-precision MMAs per tap product (fp16 hi/lo "
-                     "split), so at most ~1/3 of the dense peak is reachable in this mode",
+                note=("achieved = USEFUL flops (SURVEY 8d: dense hops 2(K-1)GN^2 + taps 2NKGF per pass) of the dominant kernel / "
+                      "its duration; single fp16 plane per operand: 1 MMA per product, bound 2e-3, NOT the parity mode"
+                      if w.get("prec", "fp32") != "fp32" else
+                      "achieved = USEFUL fp32-equivalent flops (SURVEY 8d: dense hops 2(K-1)GN^2 + taps 2NKGF per pass) of the "
+                      "dominant kernel / its duration; fp32 parity costs 3 half-precision MMAs per tap product (fp16 hi/lo "
+                      "split), so at most ~1/3 of the dense peak is reachable in this mode"),
                 how="CUDA events around %d back-to-back launches x %d replays per kernel, other outputs switched off" % (ring, reps))
 
 
@@ -821,6 +836,10 @@ def side_measurement(torch, dist, name, w2, dev, peaks, cpu_budget):
                steps=st2, config=config_dict(w2), roofline=roofline_of(torch, w2, hp2, name, step_ms, peaks))
     del hp2
     torch.cuda.empty_cache()
+    if "prec" in w2:      # a precision variant of another config: the CPU reference is that config's
+        rec["precision"] = w2["prec"]
+        rec["cpu_baseline"] = "same workload as cfg3: see the headline's cpu_baseline"
+        return rec
     cb, _, _ = time_cpu(w2, 50, 1, budget_s=cpu_budget)
     rec["cpu_baseline"] = cb
     return rec
@@ -919,7 +938,7 @@ def main():
 
     extra = {}
     if rank == 0 and world == 1 and not args.no_extra:
-        for name in ("cfg2", "cfg2_x64", "cfg3", "cfg4", "cfg1"):
+        for name in ("cfg2", "cfg2_x64", "cfg3", "cfg3_f16", "cfg4", "cfg1"):
             if name == args.config:
                 continue
             try:

@@ -48,6 +48,7 @@ int get_device_info(DeviceInfo* out) {
 int gso_mode_threshold(int mode, double radius, double* thr, bool* norm);  // gfc_gso.cu
 
 static int g_csr_fused = 1;
+static int g_wide_mask_handover = 1;   // gfc_set_option(GFC_OPT_WIDE_MASK_HANDOVER)
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // fp32 screening band around the fp64 threshold: the fp32 squared distance differs from the
@@ -210,7 +211,13 @@ static bool use_wide(const GsoSrc& gs, int N, int G, int F, int K, int mode, int
   return gs.binary && wide_supported(N + 1, G, F, K, mode) && N <= 128;
 }
 static int wide_cshift_of(const GsoSrc& gs, int N, bool norm) { return wide_cshift(gs.kind == GSRC_POS ? N : N + 1, norm); }
-static int wide_planes(int prec) { return prec == GFC_PREC_FP32_3XTF32 ? 2 : 1; }
+// fp16 planes per operand: 2 (hi/lo, fp32-equivalent) unless a looser mode was asked for AND the single-plane kernels
+// are instantiated for the shape (128 -> 128, dH feature slice 64: K <= 5); elsewhere the looser modes simply get the
+// two-plane kernels (more accurate than requested, never less)
+static int wide_planes(int prec, int G, int F, int K) {
+  if (prec == GFC_PREC_FP32_3XTF32) return 2;
+  return (G == 128 && F == 128 && (K + 1) * 64 <= 384) ? 1 : 2;
+}
 // workspace behind the tile plan's own: [packed taps | amax (256 B) | dH partials | db partials | dY o act'(y)]
 struct WideWs {
   size_t pack, amax, dhp, dbp, dpre, bytes;
@@ -226,7 +233,12 @@ static WideWs wide_ws(int B, int N, int G, int F, int K, int backward) {
       const size_t np = (size_t)wide_dh_nparts(B, N, F, K);
       o.dhp = off; off += align_up(np * F * K * G * sizeof(float), 256);
       o.dbp = off; off += align_up(np * F * sizeof(float), 256);
-      o.dpre = off; off += align_up((size_t)B * N * F * sizeof(float), 256);   // dY o act'(y), handed from the dX kernel to the dH kernel
+      // hand-over from the dX kernel to the dH kernel: the activation mask as bits, 2 KB per tile (default), or
+      // dY o act'(y) itself (GFC_OPT_WIDE_MASK_HANDOVER = 0)
+      int gpc = 128 / (N > 0 ? N : 1); if (gpc > B) gpc = B; if (gpc < 1) gpc = 1;
+      const size_t ntiles = ((size_t)B + gpc - 1) / gpc;
+      const size_t full = (size_t)B * N * F * sizeof(float), bits = ntiles * 2048;
+      o.dpre = off; off += align_up(full > bits ? full : bits, 256);
     }
   }
   o.bytes = off;
@@ -276,7 +288,7 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       // tcgen05 / TMEM path: fp16 hi/lo planes, hops and taps on the tensor cores
       const WideWs wws = wide_ws(B, N, G, F, K, 0);
       unsigned char* hp = reinterpret_cast<unsigned char*>(ws) + p.ws_bytes + wws.pack;
-      const int cs = wide_cshift_of(gs, N, norm), np = wide_planes(prec);
+      const int cs = wide_cshift_of(gs, N, norm), np = wide_planes(prec, G, F, K);
       rc = launch_wide_pack(h, G, F, K, 0, cs, np, hp, st);
       if (rc) return rc;
       WideArgs wa{};
@@ -380,10 +392,11 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       // tensor memory across all tiles of a CTA)
       const WideWs wws = wide_ws(B, N, G, F, K, 1);
       char* wb = wsb + p.ws_bytes;
-      const int cs = wide_cshift_of(gs, N, norm), np = wide_planes(prec);
+      const int cs = wide_cshift_of(gs, N, norm), np = wide_planes(prec, G, F, K);
       g_last_path = 3;
       float* amax = reinterpret_cast<float*>(wb + wws.amax);
       float* wide_dpre = nullptr;
+      uint32_t* wide_vmask = nullptr;
       const bool want_grads = dH != nullptr;   // db alone is served below by the tile kernels
       if (!want_grads && db && !dX) goto tile_path;
       if (want_grads) GFC_CUDA_TRY(cudaMemsetAsync(amax, 0, 2 * sizeof(float), st));
@@ -397,7 +410,9 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
         if (want_grads) {
           wa.amax = amax;   // max |dY o act'(y)| of the batch: by-product of the tile scales
-          if (act != GFC_ACT_NONE) { wide_dpre = reinterpret_cast<float*>(wb + wws.dpre); wa.d_out = wide_dpre; }
+          // hand-over to the dH kernel: the activation mask as bits (default; 1/32 of the bytes) or dY o act'(y) itself
+          if (act != GFC_ACT_NONE && g_wide_mask_handover) { wide_vmask = reinterpret_cast<uint32_t*>(wb + wws.dpre); wa.vmask = wide_vmask; }
+          else if (act != GFC_ACT_NONE) { wide_dpre = reinterpret_cast<float*>(wb + wws.dpre); wa.d_out = wide_dpre; }
         }
         rc = launch_wide(wa, G, F, 1, np, st);
         if (rc) return rc;
@@ -414,7 +429,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         if (rc) return rc;
         WideDhArgs da{};
         fill_wide_graph(da.g, gs, a, norm, N, 0);
-        da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre; da.amax = amax;
+        da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre; da.vmask = wide_vmask; da.amax = amax;
         da.dHp = dhp; da.dbp = db ? dbp : nullptr;
         da.B = B; da.N = N; da.K = K; da.cshift = cs; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
         GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)npart * nH * sizeof(float), st));   // partials are accumulated with red.add
@@ -540,6 +555,7 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_PDL) { g_pdl = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_NO_PREFETCH) { g_wide_no_prefetch = value; return GFC_OK; }
   if (key == GFC_OPT_DP_TIMEOUT_MS) { g_dp_timeout_ms = value > 0 ? value : 10000; return GFC_OK; }
+  if (key == GFC_OPT_WIDE_MASK_HANDOVER) { g_wide_mask_handover = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_CSR_FUSED) { g_csr_fused = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 3; return GFC_OK; }
   set_error("gfc_set_option: unknown key %d", key);
@@ -641,7 +657,7 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   set_thresholds(a, thr, norm);
   const WideWs wws = wide_ws(B, N, G, F, K, 0);
   unsigned char* hp = reinterpret_cast<unsigned char*>(workspace) + p.ws_bytes + wws.pack;
-  const int cs = wide_cshift(N, norm), np = wide_planes(precision);
+  const int cs = wide_cshift(N, norm), np = wide_planes(precision, G, F, K);
   rc = launch_wide_pack(h, G, F, K, 0, cs, np, hp, st);
   if (rc) return rc;
   WideArgs wa{};

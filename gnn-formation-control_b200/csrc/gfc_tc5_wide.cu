@@ -176,6 +176,24 @@ __device__ __forceinline__ float ldg_f32(const float* p, bool pred) {
       : "l"(p), "r"((int)pred));
   return v;
 }
+// Activation mask handed from the dX kernel to the dH kernel (WideArgs::vmask): 2 KB per tile, word
+// [tile][row block gw = tile row / 16][slab s = channel / (F/2)][lane of the dX kernel's load mapping], bit 4 i + e =
+// (forward output > 0) of tile row 16 gw + RPI i + lane / PPR, channel s F/2 + 4 (lane % PPR) + e, with the dX
+// kernel's PPR = F/8 pieces per row and slab and RPI = 32 / PPR rows per warp instruction.
+__device__ __forceinline__ size_t wide_mask_word(int tile, int gw, int s, int lane) {
+  return (((size_t)tile * 8 + gw) * 2 + s) * 32 + lane;
+}
+__device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p, bool pred) {
+  uint32_t v;
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "mov.b32 %0, 0;\n\t"
+      "@q ld.global.nc.b32 %0, [%1];\n\t}"
+      : "=r"(v)
+      : "l"(p), "r"((int)pred));
+  return v;
+}
 __device__ __forceinline__ float4 ldg_f32x4(const float* p, bool pred) {
   float4 v;
   asm volatile(
@@ -569,6 +587,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         // 19k of every 33k cycles per tile in the dX kernel, profiles/r2/wide_timeline_notes.md).
         const int rows_used = gcount * N;
         const bool masked = MODE == 1 && w.act != GFC_ACT_NONE;
+        uint32_t mword = 0;
 #pragma unroll
         for (int hb = 0; hb < NPC; hb += 4) {
           float4 vv[4], yy[4];
@@ -593,12 +612,22 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
               // hand dY o act'(y) to the dH kernel: it then streams ONE tensor and never waits on the mask
               if (w.d_out && ok[i]) *reinterpret_cast<float4*>(w.d_out + off[i]) = vv[i];
             }
+            if (w.vmask) {
+              // ... or only the MASK (y > 0), one nibble per piece: the NPC pieces of this thread and slab fill ONE word
+              // (bit 4 piece + e), stored below with one coalesced 128-byte line per warp — 1/32 of the bytes of d_out
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+                mword |= ((yy[i].x > 0.f ? 1u : 0u) | (yy[i].y > 0.f ? 2u : 0u) | (yy[i].z > 0.f ? 4u : 0u) |
+                          (yy[i].w > 0.f ? 8u : 0u)) << (4 * (hb + i));
+            }
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             xin[4 * (hb + i)] = vv[i].x; xin[4 * (hb + i) + 1] = vv[i].y; xin[4 * (hb + i) + 2] = vv[i].z; xin[4 * (hb + i) + 3] = vv[i].w;
           }
         }
+        // mask words of a tile: [8 row blocks of 16][2 slabs][32 lanes] = 2 KB (wide_mask_word)
+        if (masked && w.vmask) w.vmask[wide_mask_word(tile, gw, s, lane)] = mword;
       }
     };
     // registers of load_slab -> the fp16 planes of W_0[slab s] (scaled by the tile scale, D^-1/2 for sym-norm)
@@ -1142,7 +1171,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         tc5::bulk_prefetch_l2(w.dpre + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
       } else {
         tc5::bulk_prefetch_l2(w.dY + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
-        if (w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+        if (w.act != GFC_ACT_NONE && !w.vmask) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
       }
       if (fh == 0) tc5::bulk_prefetch_l2(w.x + (size_t)b0 * G * N, (uint32_t)gcount * G * N * 4u);
     };
@@ -1237,8 +1266,43 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
     auto load_v0 = [&](int tile) {
       const int b0 = tile * w.gpc;
       const int rows_used = min(w.gpc, w.B - b0) * N;
-      const bool masked = w.dpre == nullptr && w.act != GFC_ACT_NONE;
+      const bool bits = w.dpre == nullptr && w.vmask != nullptr && w.act != GFC_ACT_NONE;
+      const bool masked = w.dpre == nullptr && !bits && w.act != GFC_ACT_NONE;
       const float* src = w.dpre ? w.dpre : w.dY;
+      if (bits) {
+        // dY + the mask words of the dX kernel (wide_mask_word).  ALL loads of the tile — the 16-byte pieces and the
+        // mask — are issued before the first use: one DRAM round trip.  When this kernel's feature slice is the dX
+        // kernel's channel slab (FH = F/2, e.g. cfg3) the two load mappings coincide: ONE word per thread and tile.
+        // (__fmul_rn: never contracted into the db sums, so both hand-overs give the same V_0 bit for bit)
+        const bool relu = w.act == GFC_ACT_RELU;   // elements whose forward output was <= 0: 0 (ReLU) or dY * slope
+        constexpr int PPRX = F / 8, RPIX = 32 / PPRX;   // the dX kernel's mapping (CIN = F, slab = F/2 channels)
+        constexpr bool same_map = (2 * FH == F);
+        uint32_t mw[same_map ? 1 : NPC];
+#pragma unroll
+        for (int i = 0; i < NPC; ++i) {
+          const int ro = RPI * i + lane / PPR;           // row inside this warp's 16-row block
+          const int row = 16 * gw + ro;
+          const bool ok = row < rows_used;
+          const size_t off = ((size_t)b0 * N + row) * F + fh * FH + 4 * (lane % PPR);
+          const float4 v = ldg_f32x4(src + off, ok);
+          xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+          if (same_map) {
+            if (i == 0) mw[0] = ldg_u32(w.vmask + wide_mask_word(tile, gw, fh, lane), true);
+          } else {
+            const int q = (fh * FH) / 4 + lane % PPR;    // 4-channel piece of the row
+            mw[i] = ldg_u32(w.vmask + wide_mask_word(tile, gw, q / PPRX, (ro % RPIX) * PPRX + q % PPRX), true);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NPC; ++i) {
+          const int ro = RPI * i + lane / PPR;
+          const uint32_t nib = same_map ? (mw[0] >> (4 * i)) : (mw[same_map ? 0 : i] >> (4 * (ro / RPIX)));
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            xin[4 * i + e] = ((nib >> e) & 1u) ? xin[4 * i + e] : relu ? 0.f : __fmul_rn(xin[4 * i + e], w.slope);
+        }
+        return;
+      }
 #pragma unroll
       for (int hb = 0; hb < NPC; hb += 4) {
         float4 vv[4], yy[4];

@@ -25,6 +25,8 @@ struct WideArgs {
   const float* bias;       // MODE 0: [F] or null
   float* out;              // MODE 0: y [B,N,F];  MODE 1: dX [B,G,N]
   float* d_out;            // MODE 1, optional: dY o act'(y) [B,N,F] written for the dH kernel (else null)
+  uint32_t* vmask;         // MODE 1, optional: activation mask bits (y > 0) for the dH kernel, one bit per element of
+                           //   [B*N rows][F]: word row * (F/32) + f/32, bit f%32 — 1/32 of the bytes of d_out (else null)
   float* amax;             // optional device float[2]: running max |x| (MODE 0/2 -> [0]) / max |dY o act'| (MODE 1 -> [1])
   int B, N, K;
   int cshift;              // per-hop headroom bits: W_k is carried as W_k 2^(-cshift k), the taps as H_k 2^(+cshift k)
@@ -41,6 +43,7 @@ struct WideDhArgs {
   const float* dY;         // [B,N,F]
   const float* yout;       // [B,N,F] forward output (activation mask) or null
   const float* dpre;       // optional [B,N,F]: dY o act'(y) already formed by the dX kernel (then dY / yout are not read)
+  const uint32_t* vmask;   // optional: the mask bits written by the dX kernel (WideArgs::vmask); dY is read, yout is not
   const float* amax;       // device float[2]: {max |x|, max |dY o act'|} over the WHOLE batch (launch-wide operand scales)
   float* dHp;              // [nparts][F*K*G] per-CTA-group partial gradients (zeroed by the caller, accumulated with red.add)
   float* dbp;              // [nparts][F] or null

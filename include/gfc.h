@@ -257,7 +257,9 @@ enum {
   GFC_OPT_PDL = 4, /* 1 (default): the cfg2-shape kernels and the gradient reduction use programmatic dependent launch */
   GFC_OPT_CSR_FUSED = 5, /* 1 (default): one-CTA-per-graph fused CSR forward / backward kernels; 0: workspace pipeline (A/B) */
   GFC_OPT_WIDE_NO_PREFETCH = 6, /* 1: tcgen05 wide kernels skip the L2 bulk prefetch of the next tiles (experiment; default 0) */
-  GFC_OPT_DP_TIMEOUT_MS = 7 /* bound of the peer-exchange poll in milliseconds (default 10000), see gfc_dp_status */
+  GFC_OPT_DP_TIMEOUT_MS = 7, /* bound of the peer-exchange poll in milliseconds (default 10000), see gfc_dp_status */
+  GFC_OPT_WIDE_MASK_HANDOVER = 8 /* 1 (default): the tcgen05 dX kernel hands the activation mask to the dH kernel as bits (1/32 of
+                                    the bytes); 0: it writes dY o act'(y) [B,N,F] to the workspace as in earlier builds (A/B) */
 };
 int gfc_set_option(int key, int value);
 /* kernel family of the calling thread's last gfc_filter_fwd* / gfc_filter_bwd* call: 1 = fused tile kernels (mma.sync, or the

@@ -5,6 +5,8 @@ import numpy as np
 TOL = 1e-5
 # stated looser bound of the opt-in single-pass TF32 tap contraction
 TOL_TF32 = 5e-3
+# stated bound of the opt-in single fp16 plane mode of the tcgen05 wide path (include/gfc.h: GFC_PREC_F16)
+TOL_F16 = 2e-3
 
 
 def rel_err(got, ref):
