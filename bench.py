@@ -172,6 +172,11 @@ class HotPath:
             self.y2 = [torch.empty(B, N, F, device=dev) for _ in range(ring)]
             self.xt = torch.empty(B, F, N, device=dev)
         self.launches_per_step = 0
+        # activation mask handed from each batch's forward call to its backward call (gfc_use_mask): the tcgen05 backward
+        # kernels then read 1 bit per output element instead of y
+        nbm = C.lib.gfc_filter_mask_bytes(B, N, G, F, K) if self.train else 0
+        self.masks = [torch.empty(nbm // 4, dtype=torch.int32, device=dev) for _ in range(ring)] if nbm else None
+        self.mask_ok = [False] * ring
         # the hand-over only exists on the tcgen05 wide path (elsewhere it would just add a 16-byte memset to the step)
         self.use_stats = G in (64, 128) and F in (64, 128) and N <= 128
 
@@ -183,10 +188,14 @@ class HotPath:
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
         if self.train and self.use_stats:
             C.lib.gfc_use_stats(C.ptr(self.stats[i]))
+        if self.masks is not None:
+            C.check(C.lib.gfc_use_mask(C.ptr(self.masks[i]), self.masks[i].numel() * 4), "gfc_use_mask")
         C.check(C.lib.gfc_filter_fwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                          C.ptr(self.b), C.ptr(self.y[i]), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
                                          self.prec, C.ptr(self.wsf), self.nbf, st), "gfc_filter_fwd_pos")
         n = C.last_launch_count()
+        if self.masks is not None:
+            self.mask_ok[i] = bool(C.lib.gfc_mask_filled())
         if self.layers == 2:
             # layer 2 consumes layer 1's node-major output in place (the reference hands the next GraphFilterBatch
             # a [B,F,N] view over exactly this memory, graphML.py:2362): no transposing copy between the layers
@@ -197,11 +206,16 @@ class HotPath:
             n += C.last_launch_count()
         return n
 
+    def offer_mask(self, i):
+        if self.masks is not None and self.mask_ok[i]:
+            self.C.check(self.C.lib.gfc_use_mask(self.C.ptr(self.masks[i]), self.masks[i].numel() * 4), "gfc_use_mask")
+
     def bwd(self, i, st):
         C, w = self.C, self.w
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
         if self.use_stats:
             C.lib.gfc_use_stats(C.ptr(self.stats[i]))
+        self.offer_mask(i)
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                          C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.dH),
                                          C.ptr(self.db), B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE,
@@ -218,6 +232,7 @@ class HotPath:
         B, N, G, F, K = w["B"], w["N"], w["G"], w["F"], w["K"]
         if self.use_stats:
             C.lib.gfc_use_stats(C.ptr(self.stats[i]))
+        self.offer_mask(i)
         C.check(C.lib.gfc_filter_bwd_pos_dp(C.ptr(self.x[i]), C.ptr(self.pos[i]), RADIUS, self.mode, C.ptr(self.h),
                                             C.ptr(self.y[i]), C.ptr(self.dY[i]), C.ptr(self.dX[i]), C.ptr(self.grads),
                                             B, N, G, F, K, C.ACT_LEAKY_RELU, SLOPE, self.prec,
@@ -687,6 +702,7 @@ def per_kernel_times(torch, hp, reps):
     def bwd_partial(i, st, want_dx, want_dh):
         if hp.use_stats:
             C.lib.gfc_use_stats(C.ptr(hp.stats[i]))   # filled by the forward call of this ring slot during the step
+        hp.offer_mask(i)                               # likewise the activation mask
         C.check(C.lib.gfc_filter_bwd_pos(C.ptr(hp.x[i]), C.ptr(hp.pos[i]), RADIUS, hp.mode, C.ptr(hp.h),
                                          C.ptr(hp.y[i]), C.ptr(hp.dY[i]), C.ptr(hp.dX[i]) if want_dx else None,
                                          C.ptr(hp.dH) if want_dh else None, C.ptr(hp.db) if want_dh else None,

@@ -27,6 +27,7 @@ OPT_CSR_FUSED = 5
 OPT_WIDE_NO_PREFETCH = 6
 OPT_DP_TIMEOUT_MS = 7
 OPT_WIDE_MASK_HANDOVER = 8
+OPT_WIDE_FWD_MASK = 9
 
 GSO_MODES = {"binary_le": GSO_BINARY_LE, "sym_norm_lt": GSO_SYM_NORM_LT, "binary_lt": GSO_BINARY_LT}
 ACTIVATIONS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU}
@@ -44,6 +45,9 @@ SIGNATURES = {
     "gfc_set_debug_clock_buffer": (_i, [_p, _sz]),
     "gfc_device_info": (_i, [ct.POINTER(_i)] * 4),
     "gfc_use_stats": (_i, [_p]),
+    "gfc_use_mask": (_i, [_p, _sz]),
+    "gfc_mask_filled": (_i, []),
+    "gfc_filter_mask_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "gfc_gso_build": (_i, [_p, _i, _i, _d, _i, _p, _p, _p]),
     "gfc_filter_workspace_bytes": (_sz, [_i] * 7),
     "gfc_filter_path": (_i, [_i] * 7),

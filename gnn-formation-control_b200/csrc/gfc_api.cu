@@ -14,6 +14,9 @@ static thread_local char g_err[512] = "";
 static thread_local int g_launches = 0;
 static int g_skip_grad_reduce = 0;
 static thread_local float* g_next_stats = nullptr;   // gfc_use_stats: applies to the next filter call of this thread
+static thread_local uint32_t* g_next_mask = nullptr; // gfc_use_mask: likewise
+static thread_local size_t g_next_mask_bytes = 0;
+static thread_local int g_mask_filled = 0;           // gfc_mask_filled: did the last forward call of this thread write its mask
 static long long* g_dbg_clk = nullptr;  // device buffer [>= grid][16], see gfc_set_debug_clock_buffer
 
 void set_error(const char* fmt, ...) {
@@ -48,6 +51,7 @@ int get_device_info(DeviceInfo* out) {
 int gso_mode_threshold(int mode, double radius, double* thr, bool* norm);  // gfc_gso.cu
 
 static int g_csr_fused = 1;
+static int g_wide_fwd_mask = 1;        // gfc_set_option(GFC_OPT_WIDE_FWD_MASK)
 static int g_wide_mask_handover = 1;   // gfc_set_option(GFC_OPT_WIDE_MASK_HANDOVER)
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -258,6 +262,9 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   launch_counter() = 0;
   float* stats = g_next_stats;   // one-shot
   g_next_stats = nullptr;
+  uint32_t* fmask = g_next_mask;
+  const size_t fmask_bytes = g_next_mask_bytes;
+  g_next_mask = nullptr; g_next_mask_bytes = 0; g_mask_filled = 0;
   int rc = check_common(fn, B, N, G, F, K, E, act, prec, slope);
   if (rc) return rc;
   if (stats) GFC_CUDA_TRY(cudaMemsetAsync(stats, 0, 4 * sizeof(float), st));   // stats[3] stays 0: "not filled"
@@ -297,6 +304,10 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
       wa.in = x; wa.hpack = hp; wa.bias = bias; wa.out = y; wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs;
       wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
       wa.amax = stats;   // stats[0] = max |x|: a by-product of the per-tile operand scales
+      if (fmask && g_wide_fwd_mask && act != GFC_ACT_NONE && fmask_bytes >= wide_mask_bytes(B, N)) {
+        wa.fmask_out = fmask;   // signs of the outputs, 2 KB per tile: the backward call of this batch then never reads y
+        g_mask_filled = 1;
+      }
       rc = launch_wide(wa, G, F, 0, np, st);
       if (rc || !stats) return rc;
       return launch_stats_mark(stats, st);   // stats[3] = 1: filled
@@ -347,6 +358,9 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
   launch_counter() = 0;
   const float* stats = g_next_stats;   // one-shot
   g_next_stats = nullptr;
+  const uint32_t* fmask = g_next_mask;   // filled by the forward call of this batch (the caller vouches: gfc_mask_filled)
+  if (fmask && g_next_mask_bytes < wide_mask_bytes(B, N)) fmask = nullptr;
+  g_next_mask = nullptr; g_next_mask_bytes = 0;
   int rc = check_common(fn, B, N, G, F, K, E, act, prec, slope);
   if (rc) return rc;
   const size_t nH = (size_t)F * E * K * G;
@@ -408,10 +422,12 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         fill_wide_graph(wa.g, gs, a, norm, N, 0);   // backward hop: V_{k+1} = S V_k  ->  P = S
         wa.in = dY; wa.yout = (act != GFC_ACT_NONE) ? yout : nullptr; wa.hpack = hp; wa.out = dX;
         wa.B = B; wa.N = N; wa.K = K; wa.cshift = cs; wa.act = act; wa.slope = slope; wa.dbg = g_dbg_clk;
+        if (act != GFC_ACT_NONE && fmask) wa.fmask = fmask;   // the forward kernel's mask: y is not read
         if (want_grads) {
           wa.amax = amax;   // max |dY o act'(y)| of the batch: by-product of the tile scales
           // hand-over to the dH kernel: the activation mask as bits (default; 1/32 of the bytes) or dY o act'(y) itself
-          if (act != GFC_ACT_NONE && g_wide_mask_handover) { wide_vmask = reinterpret_cast<uint32_t*>(wb + wws.dpre); wa.vmask = wide_vmask; }
+          if (act != GFC_ACT_NONE && fmask) {}   // the dH kernel reads the forward kernel's mask as well
+          else if (act != GFC_ACT_NONE && g_wide_mask_handover) { wide_vmask = reinterpret_cast<uint32_t*>(wb + wws.dpre); wa.vmask = wide_vmask; }
           else if (act != GFC_ACT_NONE) { wide_dpre = reinterpret_cast<float*>(wb + wws.dpre); wa.d_out = wide_dpre; }
         }
         rc = launch_wide(wa, G, F, 1, np, st);
@@ -430,6 +446,7 @@ static int filter_bwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         WideDhArgs da{};
         fill_wide_graph(da.g, gs, a, norm, N, 0);
         da.x = x; da.dY = dY; da.yout = (act != GFC_ACT_NONE) ? yout : nullptr; da.dpre = wide_dpre; da.vmask = wide_vmask; da.amax = amax;
+        if (act != GFC_ACT_NONE && fmask) da.fmask = fmask;
         da.dHp = dhp; da.dbp = db ? dbp : nullptr;
         da.B = B; da.N = N; da.K = K; da.cshift = cs; da.act = act; da.slope = slope; da.dbg = g_dbg_clk;
         GFC_CUDA_TRY(cudaMemsetAsync(dhp, 0, (size_t)npart * nH * sizeof(float), st));   // partials are accumulated with red.add
@@ -555,6 +572,7 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_PDL) { g_pdl = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_NO_PREFETCH) { g_wide_no_prefetch = value; return GFC_OK; }
   if (key == GFC_OPT_DP_TIMEOUT_MS) { g_dp_timeout_ms = value > 0 ? value : 10000; return GFC_OK; }
+  if (key == GFC_OPT_WIDE_FWD_MASK) { g_wide_fwd_mask = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_MASK_HANDOVER) { g_wide_mask_handover = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_CSR_FUSED) { g_csr_fused = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_FLUSH_EVERY) { g_wide_flush_every = value > 0 ? value : 3; return GFC_OK; }
@@ -638,6 +656,7 @@ extern "C" int gfc_filter_fwd_pos_nm(const float* x_nm, const float* pos, double
   cudaStream_t st = (cudaStream_t)stream;
   launch_counter() = 0;
   g_next_stats = nullptr;   // the node-major entry has no backward partner: a pending gfc_use_stats is dropped
+  g_next_mask = nullptr; g_next_mask_bytes = 0; g_mask_filled = 0;
   int rc = check_common(fn, B, N, G, F, K, 1, act, precision, slope);
   if (rc) return rc;
   if (B == 0) return GFC_OK;
@@ -850,6 +869,19 @@ extern "C" int gfc_filter_csr_bwd(const float* x, const int32_t* rowptr, const i
 extern "C" int gfc_use_stats(float* stats) {
   g_next_stats = stats;
   return GFC_OK;
+}
+
+extern "C" int gfc_use_mask(void* mask, size_t bytes) {
+  GFC_REQUIRE(!mask || (reinterpret_cast<uintptr_t>(mask) & 127) == 0, GFC_ERR_BAD_ARG, "gfc_use_mask: the buffer must be 128-byte aligned");
+  g_next_mask = static_cast<uint32_t*>(mask);
+  g_next_mask_bytes = mask ? bytes : 0;
+  return GFC_OK;
+}
+extern "C" int gfc_mask_filled(void) { return g_mask_filled; }
+extern "C" size_t gfc_filter_mask_bytes(int B, int N, int G, int F, int K) {
+  (void)K;
+  if (B < 1 || !(G == 64 || G == 128) || !(F == 64 || F == 128)) return 0;   // shapes of the tcgen05 wide kernels
+  return wide_mask_bytes(B, N);
 }
 
 extern "C" int gfc_last_path(void) { return g_last_path; }

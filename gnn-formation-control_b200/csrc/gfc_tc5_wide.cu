@@ -183,6 +183,18 @@ __device__ __forceinline__ float ldg_f32(const float* p, bool pred) {
 __device__ __forceinline__ size_t wide_mask_word(int tile, int gw, int s, int lane) {
   return (((size_t)tile * 8 + gw) * 2 + s) * 32 + lane;
 }
+// Activation mask written by the FORWARD kernel's epilogue (WideArgs::fmask_out, gfc_use_mask): 2 KB per tile, word
+// [tile][epilogue warp gw][pcw][lane] = the signs (y > 0) of 32 consecutive output channels of ONE tile row:
+// row = 32 q + lane with q = (gw + 2) & 3 (the warp's TMEM lane quadrant), channels (gw >> 2) F/2 + 32 pcw + bit.
+__device__ __forceinline__ size_t wide_fmask_word(int tile, int gw, int pcw, int lane) {
+  return (((size_t)tile * 8 + gw) * 2 + pcw) * 32 + lane;
+}
+// reader side: word and bit of channel c (any multiple of 4: its nibble lies inside one word) of tile row `row`; F channels
+__device__ __forceinline__ size_t wide_fmask_locate(int tile, int row, int c, int F, int* shift) {
+  const int hc = F >> 1, half = c >= hc ? 1 : 0, cc = c - half * hc;
+  *shift = cc & 31;
+  return wide_fmask_word(tile, half * 4 + (((row >> 5) + 2) & 3), cc >> 5, row & 31);
+}
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p, bool pred) {
   uint32_t v;
   asm volatile(
@@ -397,7 +409,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         const uint32_t bytes = (uint32_t)gcount * (uint32_t)N * CIN * 4u;   // multiple of 16 (CIN % 32 == 0)
         const size_t off = (size_t)b0 * N * CIN;
         tc5::bulk_prefetch_l2(w.in + off, bytes);
-        if (MODE == 1 && w.act != GFC_ACT_NONE) tc5::bulk_prefetch_l2(w.yout + off, bytes);
+        if (MODE == 1 && w.act != GFC_ACT_NONE && !w.fmask) tc5::bulk_prefetch_l2(w.yout + off, bytes);
       };
       prefetch_tile(t_begin); prefetch_tile(t_begin + 1);
       for (int tile = t_begin; tile < t_end; ++tile) {
@@ -586,6 +598,30 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
         // load / use / load / use every piece cost a full L2 round trip (8 per slab, ~7k cycles: the issuer idled
         // 19k of every 33k cycles per tile in the dX kernel, profiles/r2/wide_timeline_notes.md).
         const int rows_used = gcount * N;
+        if (MODE == 1 && w.fmask != nullptr && w.act != GFC_ACT_NONE) {
+          // dY + the mask words of the FORWARD kernel (wide_fmask_locate): y is not read at all, and every load of the
+          // slab — 16-byte pieces and mask words — is in flight before the first use (one round trip per slab)
+          const bool relu = w.act == GFC_ACT_RELU;   // outputs <= 0: gradient 0 (ReLU) or dY * slope, as act_grad
+          const int c = s * L::CS + 4 * (lane % PPR);
+          uint32_t mw[NPC];
+          int sh = 0;
+#pragma unroll
+          for (int i = 0; i < NPC; ++i) {
+            const int row = 16 * gw + RPI * i + lane / PPR;
+            const bool ok = row < rows_used;
+            const float4 v = ldg_f32x4(w.in + ((size_t)b0 * N + row) * CIN + c, ok);
+            xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+            mw[i] = ldg_u32(w.fmask + wide_fmask_locate(tile, row, c, CIN, &sh), true);
+          }
+#pragma unroll
+          for (int i = 0; i < NPC; ++i) {
+            const uint32_t nib = mw[i] >> sh;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              xin[4 * i + e] = ((nib >> e) & 1u) ? xin[4 * i + e] : relu ? 0.f : __fmul_rn(xin[4 * i + e], w.slope);
+          }
+          return;
+        }
         const bool masked = MODE == 1 && w.act != GFC_ACT_NONE;
         uint32_t mword = 0;
 #pragma unroll
@@ -675,7 +711,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       const float4* p = reinterpret_cast<const float4*>(w.in + (size_t)b0 * N * CIN);
       const int n4 = gcount * N * (CIN / 4);
       float m = 0.f;
-      if (MODE == 1 && w.act != GFC_ACT_NONE) {
+      if (MODE == 1 && w.act != GFC_ACT_NONE && !w.fmask) {
         // dX: the slab loads that follow read dY (in L2 after this pass) AND y (still in DRAM: every batch then waited a DRAM
         // round trip, ~2.5k cycles instead of ~0.8k).  Pull the tile's y lines into L2 now, one 128-byte line per request.
         const char* yb = reinterpret_cast<const char*>(w.yout + (size_t)b0 * N * CIN);
@@ -712,6 +748,8 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
       tc5::mbar_wait_suspend(&out_full[ob], (par_ofl >> ob) & 1); par_ofl ^= 1u << ob;
       tc5::fence_after_sync();
       GFC_KSTAMP(500);
+      uint32_t fmw = 0;
+      static_assert((COUT / 32) % 2 == 0, "two 16-channel pieces per mask word");
 #pragma unroll 1
       for (int pc = 0; pc < COUT / 32; ++pc) {
         const int col = half * (COUT / 2) + pc * 16;
@@ -727,6 +765,17 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
             o[i4].y = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 1]), inv, bb.y), act_neg, act_min);
             o[i4].z = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 2]), inv, bb.z), act_neg, act_min);
             o[i4].w = act_fast(fmaf(__uint_as_float(v[i4 * 4 + 3]), inv, bb.w), act_neg, act_min);
+          }
+          if (w.fmask_out) {
+            // signs of this row's 16 outputs -> the row's mask word (two pieces of 16 channels per word, wide_fmask_word):
+            // the backward kernels read these 2 KB per tile instead of the 64 KB of y
+            uint32_t b16 = 0;
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4)
+              b16 |= ((o[i4].x > 0.f ? 1u : 0u) | (o[i4].y > 0.f ? 2u : 0u) | (o[i4].z > 0.f ? 4u : 0u) |
+                      (o[i4].w > 0.f ? 8u : 0u)) << (4 * i4);
+            fmw |= b16 << ((pc & 1) * 16);
+            if (pc & 1) { w.fmask_out[wide_fmask_word(tile, gw, pc >> 1, lane)] = fmw; fmw = 0; }
           }
           // the TMA store of the previous piece has finished reading the staging slot
           if (lane == 0) tc5::tma_store_wait_read();
@@ -1171,7 +1220,7 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
         tc5::bulk_prefetch_l2(w.dpre + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
       } else {
         tc5::bulk_prefetch_l2(w.dY + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
-        if (w.act != GFC_ACT_NONE && !w.vmask) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
+        if (w.act != GFC_ACT_NONE && !w.vmask && !w.fmask) tc5::bulk_prefetch_l2(w.yout + (size_t)b0 * N * F, (uint32_t)gcount * N * F * 4u);
       }
       if (fh == 0) tc5::bulk_prefetch_l2(w.x + (size_t)b0 * G * N, (uint32_t)gcount * G * N * 4u);
     };
@@ -1269,6 +1318,36 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       const bool bits = w.dpre == nullptr && w.vmask != nullptr && w.act != GFC_ACT_NONE;
       const bool masked = w.dpre == nullptr && !bits && w.act != GFC_ACT_NONE;
       const float* src = w.dpre ? w.dpre : w.dY;
+      if (w.fmask != nullptr && w.act != GFC_ACT_NONE) {
+        // dY + the mask words of the FORWARD kernel (wide_fmask_locate): neither y nor a hand-over of the dX kernel is read.
+        // All 16-byte loads are issued first; the mask words follow in two halves (register budget) — a thread's words
+        // share one 128-byte line, so the second half hits L1.
+        const bool relu = w.act == GFC_ACT_RELU;
+        const int c = fh * FH + 4 * (lane % PPR);
+#pragma unroll
+        for (int i = 0; i < NPC; ++i) {
+          const int row = 16 * gw + RPI * i + lane / PPR;
+          const float4 v = ldg_f32x4(w.dY + ((size_t)b0 * N + row) * F + c, row < rows_used);
+          xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int hb = 0; hb < NPC; hb += NPC / 2) {
+          uint32_t mw[NPC / 2];
+          int sh = 0;
+#pragma unroll
+          for (int i = 0; i < NPC / 2; ++i)
+            mw[i] = ldg_u32(w.fmask + wide_fmask_locate(tile, 16 * gw + RPI * (hb + i) + lane / PPR, c, F, &sh), true);
+#pragma unroll
+          for (int i = 0; i < NPC / 2; ++i) {
+            const uint32_t nib = mw[i] >> sh;
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              xin[4 * (hb + i) + e] = ((nib >> e) & 1u) ? xin[4 * (hb + i) + e]
+                                                        : relu ? 0.f : __fmul_rn(xin[4 * (hb + i) + e], w.slope);
+          }
+        }
+        return;
+      }
       if (bits) {
         // dY + the mask words of the dX kernel (wide_mask_word).  ALL loads of the tile — the 16-byte pieces and the
         // mask — are issued before the first use: one DRAM round trip.  When this kernel's feature slice is the dX
@@ -1556,6 +1635,12 @@ int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, f
   wide_absmax_kernel<<<grid, 512, 0, st>>>(a, n_a, b, n_b, bscale, amax, stats);
   GFC_LAUNCH_CHECK("wide_absmax_kernel");
   return GFC_OK;
+}
+
+size_t wide_mask_bytes(int B, int N) {
+  if (B < 1 || N < 1 || N > 128) return 0;
+  int gpc = 128 / N; if (gpc > B) gpc = B;
+  return (size_t)ceil_div(B, gpc) * 2048;
 }
 
 int wide_cshift(int N, int norm) {

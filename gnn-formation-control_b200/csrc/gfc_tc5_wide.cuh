@@ -27,6 +27,9 @@ struct WideArgs {
   float* d_out;            // MODE 1, optional: dY o act'(y) [B,N,F] written for the dH kernel (else null)
   uint32_t* vmask;         // MODE 1, optional: activation mask bits (y > 0) for the dH kernel, one bit per element of
                            //   [B*N rows][F]: word row * (F/32) + f/32, bit f%32 — 1/32 of the bytes of d_out (else null)
+  uint32_t* fmask_out;     // MODE 0 / 2, optional: activation mask bits (y > 0) of the output for the backward kernels, 2 KB per
+                           //   tile (gfc_use_mask; layout: wide_fmask_word in gfc_tc5_wide.cu) — the backward then never reads y
+  const uint32_t* fmask;   // MODE 1, optional: that mask; yout is not read, d_out / vmask are not needed
   float* amax;             // optional device float[2]: running max |x| (MODE 0/2 -> [0]) / max |dY o act'| (MODE 1 -> [1])
   int B, N, K;
   int cshift;              // per-hop headroom bits: W_k is carried as W_k 2^(-cshift k), the taps as H_k 2^(+cshift k)
@@ -44,6 +47,7 @@ struct WideDhArgs {
   const float* yout;       // [B,N,F] forward output (activation mask) or null
   const float* dpre;       // optional [B,N,F]: dY o act'(y) already formed by the dX kernel (then dY / yout are not read)
   const uint32_t* vmask;   // optional: the mask bits written by the dX kernel (WideArgs::vmask); dY is read, yout is not
+  const uint32_t* fmask;   // optional: the mask bits written by the FORWARD kernel (WideArgs::fmask_out); dY is read, yout is not
   const float* amax;       // device float[2]: {max |x|, max |dY o act'|} over the WHOLE batch (launch-wide operand scales)
   float* dHp;              // [nparts][F*K*G] per-CTA-group partial gradients (zeroed by the caller, accumulated with red.add)
   float* dbp;              // [nparts][F] or null
@@ -78,5 +82,6 @@ int launch_wide(const WideArgs& a, int G, int F, int mode, int planes, cudaStrea
 int launch_wide_absmax(const float* a, size_t n_a, const float* b, size_t n_b, float bscale, float* amax,
                        const float* stats, cudaStream_t st);
 int launch_stats_mark(float* stats, cudaStream_t st);   // stats[3] = 1
+size_t wide_mask_bytes(int B, int N);   // bytes of the forward / dX activation-mask hand-over: 2 KB per 128-row tile
 
 }  // namespace gfc

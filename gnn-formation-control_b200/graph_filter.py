@@ -98,6 +98,7 @@ class _LSIGF(torch.autograd.Function):
                 C.check(rc, "gfc_filter_fwd_pos_nm")
         done = x32 is not None
         stats = None
+        mask = None
         if not done:
             x32 = x.detach().to(torch.float32).contiguous()
         with torch.cuda.device(dev):
@@ -108,9 +109,11 @@ class _LSIGF(torch.autograd.Function):
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 0)
                 ws = _workspace(nb, dev)
                 pflag = prec | src.flags()
+                mask = _LSIGF._offer_mask(x, weight, act, B, N, G, F_, K, dev)
                 C.check(C.lib.gfc_filter_fwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(b32), C.ptr(y),
                                              B, N, G, F_, K, E, act, slope, pflag, C.ptr(ws), nb, st),
                         "gfc_filter_fwd")
+                mask = mask if (mask is not None and C.lib.gfc_mask_filled()) else None
             elif src.kind == _SRC_POS:
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, 1, 0)
                 ws = _workspace(nb, dev)
@@ -118,9 +121,11 @@ class _LSIGF(torch.autograd.Function):
                     # operand statistics for the backward call of this batch (max |x|: saves its extra pass over x)
                     stats = torch.empty(4, dtype=torch.float32, device=dev)
                     C.lib.gfc_use_stats(C.ptr(stats))
+                mask = _LSIGF._offer_mask(x, weight, act, B, N, G, F_, K, dev)
                 C.check(C.lib.gfc_filter_fwd_pos(C.ptr(x32), C.ptr(src.pos), src.radius, src.mode,
                                                  C.ptr(w32), C.ptr(b32), C.ptr(y), B, N, G, F_, K,
                                                  act, slope, prec, C.ptr(ws), nb, st), "gfc_filter_fwd_pos")
+                mask = mask if (mask is not None and C.lib.gfc_mask_filled()) else None
             else:
                 csr = src.csr
                 nb = C.lib.gfc_filter_csr_workspace_bytes(B, N, G, F_, K, 0)
@@ -132,9 +137,22 @@ class _LSIGF(torch.autograd.Function):
         ctx.src, ctx.act, ctx.slope, ctx.prec = src, act, slope, prec
         ctx.has_bias = bias is not None
         ctx.stats = stats
+        ctx.mask = mask      # signs of y written by the tcgen05 forward kernel: the backward reads them instead of y
         ctx.in_dtypes = (x.dtype, weight.dtype, bias.dtype if bias is not None else None)
         ctx.save_for_backward(x32, w32, y if act != C.ACT_NONE else None)
         return y
+
+    @staticmethod
+    def _offer_mask(x, weight, act, B, N, G, F_, K, dev):
+        """activation-mask buffer for the forward call that follows (gfc_use_mask), when a backward pass may come"""
+        if act == C.ACT_NONE or not (x.requires_grad or weight.requires_grad):
+            return None
+        nbm = C.lib.gfc_filter_mask_bytes(B, N, G, F_, K)
+        if nbm == 0:
+            return None
+        mask = torch.empty(nbm // 4, dtype=torch.int32, device=dev)
+        C.check(C.lib.gfc_use_mask(C.ptr(mask), nbm), "gfc_use_mask")
+        return mask
 
     @staticmethod
     def backward(ctx, dY):
@@ -155,6 +173,8 @@ class _LSIGF(torch.autograd.Function):
                 nb = C.lib.gfc_filter_workspace_bytes(B, N, G, F_, K, E, 1)
                 ws = _workspace(nb, dev)
                 pflag = prec | src.flags()
+                if ctx.mask is not None:
+                    C.check(C.lib.gfc_use_mask(C.ptr(ctx.mask), ctx.mask.numel() * 4), "gfc_use_mask")
                 C.check(C.lib.gfc_filter_bwd(C.ptr(x32), C.ptr(src.S), C.ptr(w32), C.ptr(yout), C.ptr(dY),
                                              C.ptr(dX), C.ptr(dH), C.ptr(db), B, N, G, F_, K, E,
                                              act, slope, pflag, C.ptr(ws), nb, st), "gfc_filter_bwd")
@@ -163,6 +183,8 @@ class _LSIGF(torch.autograd.Function):
                 ws = _workspace(nb, dev)
                 if ctx.stats is not None:
                     C.lib.gfc_use_stats(C.ptr(ctx.stats))
+                if ctx.mask is not None:
+                    C.check(C.lib.gfc_use_mask(C.ptr(ctx.mask), ctx.mask.numel() * 4), "gfc_use_mask")
                 C.check(C.lib.gfc_filter_bwd_pos(C.ptr(x32), C.ptr(src.pos), src.radius, src.mode,
                                                  C.ptr(w32), C.ptr(yout), C.ptr(dY), C.ptr(dX), C.ptr(dH),
                                                  C.ptr(db), B, N, G, F_, K, act, slope, prec,

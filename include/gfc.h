@@ -150,6 +150,20 @@ int gfc_filter_bwd_pos(const float* x, const float* pos, double radius, int mode
  *     another kernel family) it computes the maximum itself.  Results are identical either way.                       */
 int gfc_use_stats(float* stats);
 
+/* Activation mask handed from the forward call of a batch to its backward call (tcgen05 wide kernels, fused
+ * LeakyReLU / ReLU).  `mask` = caller-owned device buffer, 128-byte aligned, of at least
+ * gfc_filter_mask_bytes(B, N, G, F, K) bytes (2 KB per 128-row tile; 0 = the shape has no such kernel).
+ * gfc_use_mask(mask, bytes) applies to the NEXT gfc_filter_fwd* / gfc_filter_bwd* call of the calling thread only
+ * (thread-local, consumed by that call; NULL cancels):
+ *   - a forward call on the tcgen05 wide path writes one bit per output element (y > 0) into it; gfc_mask_filled()
+ *     then returns 1 for the calling thread (0 if the call took another kernel family or had no fused activation);
+ *   - a backward call of the SAME batch given a filled mask reads it instead of y_out (1/32 of the bytes: the dX and
+ *     dH kernels then stream dY only).  Pass a mask to the backward ONLY if gfc_mask_filled() was 1 right after the
+ *     forward call that received it.  Results are bit-identical to the y_out path (same predicate y > 0).          */
+int gfc_use_mask(void* mask, size_t bytes);
+int gfc_mask_filled(void);
+size_t gfc_filter_mask_bytes(int B, int N, int G, int F, int K);
+
 /* ---- (d) CSR variant for large sparse swarms ------------------------------ *
  * gfc_csr_count : deg[b,n] = in-degree under the radius rule (int32 [B,N]).
  * gfc_csr_fill  : given rowptr [B, N+1] (exclusive scan of deg per graph, int32,
@@ -258,6 +272,7 @@ enum {
   GFC_OPT_CSR_FUSED = 5, /* 1 (default): one-CTA-per-graph fused CSR forward / backward kernels; 0: workspace pipeline (A/B) */
   GFC_OPT_WIDE_NO_PREFETCH = 6, /* 1: tcgen05 wide kernels skip the L2 bulk prefetch of the next tiles (experiment; default 0) */
   GFC_OPT_DP_TIMEOUT_MS = 7, /* bound of the peer-exchange poll in milliseconds (default 10000), see gfc_dp_status */
+  GFC_OPT_WIDE_FWD_MASK = 9, /* 1 (default): a forward call given a buffer with gfc_use_mask fills it; 0: it never does (A/B) */
   GFC_OPT_WIDE_MASK_HANDOVER = 8 /* 1 (default): the tcgen05 dX kernel hands the activation mask to the dH kernel as bits (1/32 of
                                     the bytes); 0: it writes dY o act'(y) [B,N,F] to the workspace as in earlier builds (A/B) */
 };
