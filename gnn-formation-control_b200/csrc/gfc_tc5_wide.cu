@@ -774,6 +774,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
             for (int i4 = 0; i4 < 4; ++i4)
               b16 |= ((o[i4].x > 0.f ? 1u : 0u) | (o[i4].y > 0.f ? 2u : 0u) | (o[i4].z > 0.f ? 4u : 0u) |
                       (o[i4].w > 0.f ? 8u : 0u)) << (4 * i4);
+            if (r >= min(w.gpc, w.B - b0) * N) b16 = 0;   // padding rows of the tile carry no output
             fmw |= b16 << ((pc & 1) * 16);
             if (pc & 1) { w.fmask_out[wide_fmask_word(tile, gw, pc >> 1, lane)] = fmw; fmw = 0; }
           }
