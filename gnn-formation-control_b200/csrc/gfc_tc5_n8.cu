@@ -372,6 +372,10 @@ tc5_n8_fwd_kernel(const TileArgs a) {
   if (warp == kProducers / 32) tc5::tmem_dealloc(*tmem_ptr, L::TMEM_COLS);
 }
 
+// (Tried at the end of round 2: the activation mask as bits for this shape too — the forward epilogue storing one byte per
+// row and column group, the backward reading 32 bytes of mask per graph instead of 1 KB of y, gfc_use_mask.  The
+// producers are bound by instruction issue, not by bytes: cfg2 step 19.9 -> 20.2 us, 64 batches per launch 0.581 ->
+// 0.599 ms.  Dropped; the wide kernels keep it, where it removes 4.2 GB per cfg3 step.)
 // ======================================================================================================
 // backward
 // ======================================================================================================
