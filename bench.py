@@ -940,7 +940,7 @@ def main():
     torch.cuda.empty_cache()
 
     # end-to-end through the module API with host buffers
-    e2e_n = max(3, min(steps, 200 if small else 5))
+    e2e_n = max(3, min(steps, 200 if small else 10))
     e_ms, h2d, d2h, _ = e2e_steps(torch, w, dev, e2e_n, 3, world, dist, use_graph)
     te = torch.tensor([e_ms], device=dev, dtype=torch.float64)
     if world > 1:
