@@ -1321,31 +1321,28 @@ tc5_wide_dh_kernel(const __grid_constant__ WideDhArgs w) {
       const float* src = w.dpre ? w.dpre : w.dY;
       if (w.fmask != nullptr && w.act != GFC_ACT_NONE) {
         // dY + the mask words of the FORWARD kernel (wide_fmask_locate): neither y nor a hand-over of the dX kernel is read.
-        // All 16-byte loads are issued first; the mask words follow in two halves (register budget) — a thread's words
-        // share one 128-byte line, so the second half hits L1.
+        // This warp's 16 rows x FH channels are 16 x FH/32 <= 32 mask words: lane l loads the word of row l % 16 and
+        // channel block l / 16 together with the 16-byte pieces (one round trip, one register), and every piece takes
+        // its row's word from the loading lane by shuffle.
         const bool relu = w.act == GFC_ACT_RELU;
         const int c = fh * FH + 4 * (lane % PPR);
+        int sh_unused = 0;
+        const int wc_l = (lane >> 4) < FH / 32 ? (lane >> 4) : 0;
+        const uint32_t myword =
+            ldg_u32(w.fmask + wide_fmask_locate(tile, 16 * gw + (lane & 15), fh * FH + 32 * wc_l, F, &sh_unused), true);
 #pragma unroll
         for (int i = 0; i < NPC; ++i) {
           const int row = 16 * gw + RPI * i + lane / PPR;
           const float4 v = ldg_f32x4(w.dY + ((size_t)b0 * N + row) * F + c, row < rows_used);
           xin[4 * i] = v.x; xin[4 * i + 1] = v.y; xin[4 * i + 2] = v.z; xin[4 * i + 3] = v.w;
         }
+        const int wc = (4 * (lane % PPR)) >> 5, sh = (4 * (lane % PPR)) & 31;   // fh * FH and F / 2 are multiples of 32
 #pragma unroll
-        for (int hb = 0; hb < NPC; hb += NPC / 2) {
-          uint32_t mw[NPC / 2];
-          int sh = 0;
+        for (int i = 0; i < NPC; ++i) {
+          const uint32_t nib = __shfl_sync(0xffffffffu, myword, wc * 16 + RPI * i + lane / PPR) >> sh;
 #pragma unroll
-          for (int i = 0; i < NPC / 2; ++i)
-            mw[i] = ldg_u32(w.fmask + wide_fmask_locate(tile, 16 * gw + RPI * (hb + i) + lane / PPR, c, F, &sh), true);
-#pragma unroll
-          for (int i = 0; i < NPC / 2; ++i) {
-            const uint32_t nib = mw[i] >> sh;
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              xin[4 * (hb + i) + e] = ((nib >> e) & 1u) ? xin[4 * (hb + i) + e]
-                                                        : relu ? 0.f : __fmul_rn(xin[4 * (hb + i) + e], w.slope);
-          }
+          for (int e = 0; e < 4; ++e)
+            xin[4 * i + e] = ((nib >> e) & 1u) ? xin[4 * i + e] : relu ? 0.f : __fmul_rn(xin[4 * i + e], w.slope);
         }
         return;
       }
