@@ -28,6 +28,7 @@ OPT_WIDE_NO_PREFETCH = 6
 OPT_DP_TIMEOUT_MS = 7
 OPT_WIDE_MASK_HANDOVER = 8
 OPT_WIDE_FWD_MASK = 9
+OPT_CSR_STAGE_IDX = 10
 
 GSO_MODES = {"binary_le": GSO_BINARY_LE, "sym_norm_lt": GSO_SYM_NORM_LT, "binary_lt": GSO_BINARY_LT}
 ACTIVATIONS = {None: ACT_NONE, "none": ACT_NONE, "relu": ACT_RELU, "leaky_relu": ACT_LEAKY_RELU}
@@ -91,6 +92,8 @@ if os.environ.get("GFC_PDL") is not None:   # A/B switches (profiling aids)
     lib.gfc_set_option(OPT_PDL, int(os.environ["GFC_PDL"]))
 if os.environ.get("GFC_DISABLE_TCGEN05") is not None:
     lib.gfc_set_option(OPT_DISABLE_TCGEN05, int(os.environ["GFC_DISABLE_TCGEN05"]))
+for _kv in filter(None, os.environ.get("GFC_SET_OPTIONS", "").split(",")):   # e.g. GFC_SET_OPTIONS="10=0,9=0": any gfc_set_option key
+    lib.gfc_set_option(int(_kv.split("=")[0]), int(_kv.split("=")[1]))
 if os.environ.get("GFC_WIDE_MASK_HANDOVER") is not None:
     lib.gfc_set_option(OPT_WIDE_MASK_HANDOVER, int(os.environ["GFC_WIDE_MASK_HANDOVER"]))
 

@@ -572,6 +572,7 @@ extern "C" int gfc_set_option(int key, int value) {
   if (key == GFC_OPT_PDL) { g_pdl = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_NO_PREFETCH) { g_wide_no_prefetch = value; return GFC_OK; }
   if (key == GFC_OPT_DP_TIMEOUT_MS) { g_dp_timeout_ms = value > 0 ? value : 10000; return GFC_OK; }
+  if (key == GFC_OPT_CSR_STAGE_IDX) { g_csr_stage_idx = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_FWD_MASK) { g_wide_fwd_mask = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_WIDE_MASK_HANDOVER) { g_wide_mask_handover = value ? 1 : 0; return GFC_OK; }
   if (key == GFC_OPT_CSR_FUSED) { g_csr_fused = value ? 1 : 0; return GFC_OK; }

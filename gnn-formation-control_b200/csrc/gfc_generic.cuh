@@ -37,4 +37,6 @@ int launch_sgemm(const float* A, long long a_rs, long long a_cs, const float* Bm
                  float* C, long long ldc, long long c_zstride, long long M, int Nn, long long Kd,
                  int nsplit, const float* bias, int act, float slope, cudaStream_t st);
 
+extern int g_csr_stage_idx;   // gfc_set_option(GFC_OPT_CSR_STAGE_IDX): fused CSR kernels keep the lists in shared memory as 16-bit numbers
+
 }  // namespace gfc

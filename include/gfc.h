@@ -272,6 +272,7 @@ enum {
   GFC_OPT_CSR_FUSED = 5, /* 1 (default): one-CTA-per-graph fused CSR forward / backward kernels; 0: workspace pipeline (A/B) */
   GFC_OPT_WIDE_NO_PREFETCH = 6, /* 1: tcgen05 wide kernels skip the L2 bulk prefetch of the next tiles (experiment; default 0) */
   GFC_OPT_DP_TIMEOUT_MS = 7, /* bound of the peer-exchange poll in milliseconds (default 10000), see gfc_dp_status */
+  GFC_OPT_CSR_STAGE_IDX = 10, /* 1 (default): the fused CSR kernels stage a graph's neighbour lists in shared memory as 16-bit numbers; 0: read from global (A/B) */
   GFC_OPT_WIDE_FWD_MASK = 9, /* 1 (default): a forward call given a buffer with gfc_use_mask fills it; 0: it never does (A/B) */
   GFC_OPT_WIDE_MASK_HANDOVER = 8 /* 1 (default): the tcgen05 dX kernel hands the activation mask to the dH kernel as bits (1/32 of
                                     the bytes); 0: it writes dY o act'(y) [B,N,F] to the workspace as in earlier builds (A/B) */
