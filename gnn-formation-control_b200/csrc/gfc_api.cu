@@ -308,9 +308,8 @@ static int filter_fwd_impl(const char* fn, const GsoSrc& gs, const float* x, con
         wa.fmask_out = fmask;   // signs of the outputs, 2 KB per tile: the backward call of this batch then never reads y
         g_mask_filled = 1;
       }
-      rc = launch_wide(wa, G, F, 0, np, st);
-      if (rc || !stats) return rc;
-      return launch_stats_mark(stats, st);   // stats[3] = 1: filled
+      wa.mark_stats = stats ? 1 : 0;   // stats[3] = 1 ("filled") is written by the kernel itself
+      return launch_wide(wa, G, F, 0, np, st);
     }
     if (!p.h_smem) {
       float4* hp = reinterpret_cast<float4*>(static_cast<char*>(ws) + p.ws_hpack);

@@ -826,6 +826,7 @@ tc5_wide_kernel(const __grid_constant__ WideArgs w, const __grid_constant__ Wide
 #pragma unroll
         for (int i = 1; i < kGroupWarps; ++i) mt = max(mt, smax[i]);
         if (w.amax && wt == 0) atomicMax(reinterpret_cast<unsigned int*>(w.amax) + (MODE == 1 ? 1 : 0), mt);
+        if (MODE == 0 && w.mark_stats && w.amax && wt == 0 && blockIdx.x == 0 && itn == 0) w.amax[3] = 1.f;
         scale_next = tc5::pow2_scale(mt, kWideTop, &inv_next);
         rowf_next = 1.f;
         if (norm && K > 1) {   // the degrees of `next` are published by group A together with its P
@@ -1614,6 +1615,8 @@ wide_absmax_kernel(const float* __restrict__ a, size_t n_a, const float* __restr
   }
 }
 
+// (the forward kernel marks its statistics itself since the end of round 2 — WideArgs::mark_stats; kept for callers that fill
+// a statistics buffer by other means)
 __global__ void wide_stats_mark_kernel(float* stats) { stats[3] = 1.f; }
 int launch_stats_mark(float* stats, cudaStream_t st) {
   wide_stats_mark_kernel<<<1, 1, 0, st>>>(stats);

@@ -31,6 +31,8 @@ struct WideArgs {
                            //   tile (gfc_use_mask; layout: wide_fmask_word in gfc_tc5_wide.cu) — the backward then never reads y
   const uint32_t* fmask;   // MODE 1, optional: that mask; yout is not read, d_out / vmask are not needed
   float* amax;             // optional device float[2]: running max |x| (MODE 0/2 -> [0]) / max |dY o act'| (MODE 1 -> [1])
+  int mark_stats;          // MODE 0: amax is a gfc_use_stats buffer (float[4]); the kernel also sets amax[3] = 1 ("filled") —
+                           //   read by later kernels of the stream only, so no separate marking launch is needed
   int B, N, K;
   int cshift;              // per-hop headroom bits: W_k is carried as W_k 2^(-cshift k), the taps as H_k 2^(+cshift k)
   int gpc, ntiles;         // filled by launch_wide
