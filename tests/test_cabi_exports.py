@@ -49,6 +49,38 @@ def test_version_and_errors_without_gpu():
     assert C.lib.gfc_gso_build(None, 0, 3, 2.0, 0, None, None, None) == C.GFC_OK
 
 
+def test_mask_handover_host_side_without_gpu():
+    """gfc_use_mask / gfc_filter_mask_bytes / the option switches are host logic (include/gfc.h): sizes, alignment
+    check and option keys can be checked without a device."""
+    import gnnfc
+    C = gnnfc._cabi
+    assert C.lib.gfc_filter_mask_bytes(65536, 64, 128, 128, 4) == (65536 // 2) * 2048     # cfg3: 2 graphs per 128-row tile
+    assert C.lib.gfc_filter_mask_bytes(16384, 12, 128, 128, 3) == -(-16384 // 10) * 2048  # cfg4 shape: 10 graphs per tile
+    assert C.lib.gfc_filter_mask_bytes(1, 3, 64, 64, 3) == 2048
+    assert C.lib.gfc_filter_mask_bytes(4096, 8, 32, 32, 3) == 0                            # narrow features: no such kernel
+    assert C.lib.gfc_filter_mask_bytes(0, 8, 128, 128, 3) == 0
+    assert C.lib.gfc_use_mask(ctypes.c_void_p(0x1004), 4096) == C.GFC_ERR_BAD_ARG
+    assert b"aligned" in C.lib.gfc_last_error()
+    assert C.lib.gfc_use_mask(None, 0) == C.GFC_OK                                         # NULL cancels
+    assert C.lib.gfc_mask_filled() == 0
+    for key in (C.OPT_WIDE_MASK_HANDOVER, C.OPT_WIDE_FWD_MASK, C.OPT_CSR_STAGE_IDX):
+        assert C.lib.gfc_set_option(key, 0) == C.GFC_OK
+        assert C.lib.gfc_set_option(key, 1) == C.GFC_OK                                    # defaults restored
+    assert C.lib.gfc_set_option(12345, 1) == C.GFC_ERR_BAD_ARG
+
+
+def test_option_environment_hook():
+    """GFC_SET_OPTIONS="key=value,..." (an A/B aid of the tools) is applied when the binding loads"""
+    code = ("import gnnfc; C = gnnfc._cabi; "
+            "assert C.lib.gfc_set_option(C.OPT_CSR_STAGE_IDX, 1) == 0; print('ok')")
+    env = dict(os.environ, GFC_SET_OPTIONS="10=0,9=1", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    out = subprocess.run(["python", "-c", code], capture_output=True, text=True, env=env, cwd=ROOT)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-400:]
+    bad = subprocess.run(["python", "-c", "import gnnfc"], capture_output=True, text=True,
+                         env=dict(env, GFC_SET_OPTIONS="nonsense"), cwd=ROOT)
+    assert bad.returncode != 0                                                             # malformed: fails loudly
+
+
 def test_library_is_sm100a_only_and_uses_tensor_cores():
     import gnnfc
     out = subprocess.run(["cuobjdump", "-lelf", gnnfc._cabi.LIB_PATH], capture_output=True, text=True)
